@@ -134,6 +134,21 @@ class Background:
         lib().sbo_derived(C.byref(self.p), _p(d))
         self.derived = dict(zip(("Omega_g", "Omega_nu", "Omega_h", "Omega_L", "fHe", "y0", "Irho0", "kpivot", "As"), d))
 
+    @classmethod
+    def from_knots(cls, pars, t, y, dy, tau0, kappa0, taurec=0.0):
+        """Wrap externally computed spline knots (e.g. the product's background) so that the oracle's perturbation
+        solver can be run on exactly the same background."""
+        self = cls.__new__(cls)
+        self.pars = dict(pars)
+        self.p = make_params(pars)
+        self.t, self.y, self.dy = np.ascontiguousarray(t), np.ascontiguousarray(y), np.ascontiguousarray(dy)
+        self.tau0, self.kappa0, self.taurec, self.retcode, self.naccept, self.nreject = tau0, kappa0, taurec, 0, 0, 0
+        self.N = lib().sbo_nstate(C.byref(self.p))
+        d = np.zeros(9)
+        lib().sbo_derived(C.byref(self.p), _p(d))
+        self.derived = dict(zip(("Omega_g", "Omega_nu", "Omega_h", "Omega_L", "fHe", "y0", "Irho0", "kpivot", "As"), d))
+        return self
+
     def observe(self, taus):
         taus = np.ascontiguousarray(taus, dtype=float)
         out = np.zeros((len(taus), 16))

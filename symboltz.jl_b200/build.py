@@ -1,0 +1,82 @@
+"""Problem-build-time compilation: sympy model -> generated CUDA header -> nvcc (sm_100a) -> in-tree shared library.
+
+Mirrors what `CosmologyProblem(M, pars)` does in the reference (src/solve.jl:129-236: symbolic compilation, "expensive,
+do not repeat", docs/src/solve.md:26-28): one shared library per model structure (lmax, nx, w0wa), cached under
+symboltz.jl_b200/_build/<key>/ and reused for every parameter set."""
+import json
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD_DIR = os.path.join(_HERE, "_build")
+CSRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the B200 path cannot be built (there is no CPU fallback)")
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def model_key(lmax, nx, w0wa):
+    return f"l{lmax}_x{nx}_{'w0wa' if w0wa else 'lcdm'}"
+
+
+def build_model(lmax=10, nx=4, w0wa=False, force=False, verbose=False):
+    """Generate + compile the per-model engine. Returns (path to .so, info dict)."""
+    key = model_key(lmax, nx, w0wa)
+    d = os.path.join(BUILD_DIR, key)
+    so = os.path.join(d, f"libsbm_{key}.so")
+    hdr = os.path.join(d, "sb_model_gen.h")
+    meta = os.path.join(d, "info.json")
+    gen_srcs = [os.path.join(_HERE, "codegen", f) for f in ("model.py", "lower.py")]
+    c_srcs = [os.path.join(CSRC, f) for f in ("sb_engine.cu", "sb_debug.cpp", "sb_rodas.h")]
+    if not force and _newer(so, gen_srcs + c_srcs) and os.path.exists(meta):
+        return so, json.load(open(meta))
+    os.makedirs(d, exist_ok=True)
+    if force or not (_newer(hdr, gen_srcs) and os.path.exists(meta)):
+        from .codegen.model import Model
+        from .codegen.lower import generate
+        text, info = generate(Model(lmax=lmax, nx=nx, w0wa=w0wa))
+        info.pop("L", None)
+        with open(hdr, "w") as f:
+            f.write(text)
+        json.dump(info, open(meta, "w"))
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", d, "-I", CSRC, "-o", so, c_srcs[0], c_srcs[1]]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return so, json.load(open(meta))
+
+
+def build_los(force=False, verbose=False):
+    so = os.path.join(BUILD_DIR, "libsbl.so")
+    src = os.path.join(CSRC, "sb_los.cu")
+    if not force and _newer(so, [src]):
+        return so
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", so, src]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return so
+
+
+DEFAULT_MODELS = [dict(lmax=10, nx=4, w0wa=False), dict(lmax=5, nx=4, w0wa=False), dict(lmax=10, nx=4, w0wa=True)]
+
+
+def build_all(force=False, verbose=False):
+    out = [build_los(force=force, verbose=verbose)]
+    for m in DEFAULT_MODELS:
+        out.append(build_model(force=force, verbose=verbose, **m)[0])
+    return out

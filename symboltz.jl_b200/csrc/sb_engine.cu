@@ -1,0 +1,713 @@
+// symboltz.jl_b200 -- per-model engine: host background solver + sm_100a perturbation kernels + C ABI.
+//
+// Compiled once per model (lmax, nx, w0wa) together with the generated header sb_model_gen.h
+// (codegen/lower.py), mirroring the reference's problem-build-time compilation (src/solve.jl:129-236).
+//
+// Replaces, for the hot path only (file:line relative to the reference tree):
+//   solvebg                         src/solve.jl:427-435       -> sbm_solvebg (host, Rodas5P dense, analytic J)
+//   spline(bgsol)                   src/utils.jl:118-127       -> knots (t, y, y') uploaded; β-table built on device
+//   setuppt/solvept, Rodas5P + KLU  src/solve.jl:496-569, 329  -> sb_integrate_kernel (one warp per k-mode, persistent,
+//                                                                 atomic work queue, tables from the code generator)
+//   getsym(prob.pt, Ss) sources     src/observables/fourier.jl:267-281, src/models/cosmologies.jl:99-104 -> sb_source_kernel
+//   Δm for P(k)                     src/observables/fourier.jl:39-52, 90-97 -> sb_deltam_kernel
+//
+// There is deliberately NO CPU fallback for the perturbation path: every sbm_* device entry point returns a CUDA
+// error code if no GPU is present.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "sb_model_gen.h"
+#include "sb_rodas.h"
+
+#define SB_WARP 32
+#define SB_FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------ tableau
+__constant__ double cA[8][8] = SB_R5_A_INIT;
+__constant__ double cC[8][8] = SB_R5_C_INIT;
+__constant__ double cc[8] = SB_R5_c_INIT;
+__constant__ double cd[8] = SB_R5_d_INIT;
+__constant__ double cH[3][8] = SB_R5_H_INIT;
+__constant__ int cslot[8] = SB_R5_TIMESLOT_INIT;
+static const double hA[8][8] = SB_R5_A_INIT;
+static const double hC[8][8] = SB_R5_C_INIT;
+static const double hc[8] = SB_R5_c_INIT;
+static const double hd[8] = SB_R5_d_INIT;
+static const double hH[3][8] = SB_R5_H_INIT;
+
+enum { SB_RC_SUCCESS = 0, SB_RC_MAXITERS = 1, SB_RC_DTMIN = 2, SB_RC_UNSTABLE = 3 };
+
+// ------------------------------------------------------------------------------------------------ spline (host+device)
+// Cubic Hermite spline of the background unknowns (reference: DataInterpolations.CubicHermiteSpline, utils.jl:126)
+struct SbSpline {
+    int nb;
+    const double *t, *y, *dy;
+};
+SB_HD static inline int sb_spl_find(const SbSpline& s, double tr) {
+    int lo = 0, hi = s.nb - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (s.t[mid] <= tr) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+SB_HD static inline void sb_spl_eval(const SbSpline& s, double tau, double* y, double* yp) {
+    int i = sb_spl_find(s, tau);
+    double h = s.t[i + 1] - s.t[i], d0 = tau - s.t[i], d1 = tau - s.t[i + 1];
+    for (int j = 0; j < 5; j++) {
+        double u0 = s.y[5 * i + j], u1 = s.y[5 * i + 5 + j], v0 = s.dy[5 * i + j], v1 = s.dy[5 * i + 5 + j];
+        double c1 = (u1 - u0 - v0 * h) / (h * h), c2 = (v1 - v0 - 2 * c1 * h) / (h * h);
+        y[j] = u0 + d0 * v0 + d0 * d0 * (c1 + d1 * c2);
+        if (yp) yp[j] = v0 + 2 * d0 * (c1 + d1 * c2) + d0 * d0 * c2;
+    }
+}
+
+// ================================================================================================ HOST: background
+// Small dense Rodas5P for the 5 background unknowns with the analytic Jacobian from the generator
+// (reference: Rodas5P + RFLUFactorization, reltol = abstol = 1e-7, src/solve.jl:313-325, 382).
+namespace bgsolve {
+static bool lu5(double* A, int* piv) {
+    const int n = 5;
+    for (int k = 0; k < n; k++) {
+        int p = k; double m = fabs(A[k * n + k]);
+        for (int i = k + 1; i < n; i++) if (fabs(A[i * n + k]) > m) { m = fabs(A[i * n + k]); p = i; }
+        piv[k] = p;
+        if (!(m > 0)) return false;
+        if (p != k) for (int j = 0; j < n; j++) std::swap(A[k * n + j], A[p * n + j]);
+        for (int i = k + 1; i < n; i++) { double l = A[i * n + k] / A[k * n + k]; A[i * n + k] = l; for (int j = k + 1; j < n; j++) A[i * n + j] -= l * A[k * n + j]; }
+    }
+    return true;
+}
+static void lusolve5(const double* A, const int* piv, double* b) {
+    const int n = 5;
+    for (int k = 0; k < n; k++) if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+    for (int i = 1; i < n; i++) for (int j = 0; j < i; j++) b[i] -= A[i * n + j] * b[j];
+    for (int i = n - 1; i >= 0; i--) { for (int j = i + 1; j < n; j++) b[i] -= A[i * n + j] * b[j]; b[i] /= A[i * n + i]; }
+}
+struct Step {
+    double ks[8][5], unew[5], K[3][5];
+    bool run(const double* P, const double* u, double dt) {
+        double f0[5], J[25], W[25], U[5], du[5]; int piv[5];
+        sb_bg_rhs_jac(u, P, f0, J);
+        double dg = 1.0 / (SB_R5_GAMMA * dt);
+        for (int i = 0; i < 25; i++) W[i] = -J[i];
+        for (int i = 0; i < 5; i++) W[i * 5 + i] += dg;
+        if (!lu5(W, piv)) return false;
+        for (int s = 0; s < 8; s++) {
+            const double* fs = f0;
+            if (s > 0) {
+                if (s <= 5) for (int i = 0; i < 5; i++) { double v = u[i]; for (int j = 0; j < s; j++) v += hA[s][j] * ks[j][i]; U[i] = v; }
+                else for (int i = 0; i < 5; i++) U[i] += ks[s - 1][i];
+                sb_bg_rhs(U, P, du); fs = du;
+            }
+            for (int i = 0; i < 5; i++) { double v = fs[i]; for (int j = 0; j < s; j++) v += hC[s][j] / dt * ks[j][i]; ks[s][i] = v; } // autonomous: dT = 0
+            lusolve5(W, piv, ks[s]);
+        }
+        for (int i = 0; i < 5; i++) {
+            unew[i] = U[i] + ks[7][i];
+            for (int q = 0; q < 3; q++) { double s = 0; for (int j = 0; j < 8; j++) s += hH[q][j] * ks[j][i]; K[q][i] = s; }
+        }
+        return true;
+    }
+    void interp(const double* u0, const double* u1, double th, double* out) const {
+        for (int i = 0; i < 5; i++) out[i] = (1 - th) * u0[i] + th * (u1[i] + (1 - th) * (K[0][i] + th * (K[1][i] + th * K[2][i])));
+    }
+    void dinterp(const double* u0, const double* u1, double th, double dt, double* out) const {
+        for (int i = 0; i < 5; i++) out[i] = (K[0][i] + th * (-2 * K[0][i] + 2 * K[1][i] + th * (-3 * K[1][i] + 3 * K[2][i] - 4 * th * K[2][i])) - u0[i] + u1[i]) / dt;
+    }
+};
+static double errnorm(const double* k8, const double* u0, const double* u1, double abstol, double reltol) {
+    double s = 0;
+    for (int i = 0; i < 5; i++) { double r = k8[i] / (abstol + reltol * fmax(fabs(u0[i]), fabs(u1[i]))); s += r * r; }
+    return sqrt(s / 5);
+}
+} // namespace bgsolve
+
+// PI step controller with OrdinaryDiffEq's defaults for an order-5 method (β1 = 7/50, β2 = 2/25, γ = 0.9, q ∈ [1/5, 10], qoldinit 1e-4)
+struct SbController {
+    double qold, q11;
+    SB_HD void init() { qold = 1e-4; q11 = 1.0; }
+    SB_HD double q_of(double EEst) {
+        if (EEst == 0.0) return 0.1;
+        q11 = pow(EEst, 7.0 / 50.0);
+        double q = q11 / pow(qold, 2.0 / 25.0);
+        return fmax(0.1, fmin(5.0, q / 0.9));
+    }
+    SB_HD double accept(double dt, double q, double EEst) { qold = fmax(EEst, 1e-4); return dt / q; }
+    SB_HD double reject(double dt) { return dt / fmin(5.0, q11 / 0.9); }
+};
+
+extern "C" {
+
+// out[0..15] = N, NPAR, NBETA, NB, LMAX, NX, W0WA, NNZ_FULL, FLOPS_F, FLOPS_LU, FLOPS_SOLVE, NLEVELS, NBLOCKS, P_KAPPA0, P_TAU0, NSLOT
+int sbm_info(int* out) {
+    int v[16] = {SB_N, SB_NPAR, SB_NBETA, SB_NB, SB_LMAX, SB_NX, SB_W0WA, SB_NNZ_FULL, SB_FLOPS_F, SB_FLOPS_LU, SB_FLOPS_SOLVE, SB_NLEVELS, SB_NBLOCKS, SB_P_KAPPA0, SB_P_TAU0, SB_NSLOT};
+    memcpy(out, v, sizeof(v));
+    return 0;
+}
+const char* sbm_key(void) { return SB_MODEL_KEY; }
+
+// Background solve on the host.  Returns the number of spline knots, or -1 if cap is too small.
+// info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
+int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info) {
+    using namespace bgsolve;
+    // a(τini) from ℋ = 1/τ (reference src/models/cosmologies.jl:76), Newton on ȧ τ / a − 1
+    double a = sqrt(P[3] + P[4]) * tini;
+    for (int it = 0; it < 100; it++) {
+        auto F = [&](double aa) { double yy[5] = {aa, 0, 1, 1, 0}, g[5]; sb_bg_rhs(yy, P, g); return g[0] * tini / aa - 1.0; };
+        double f = F(a), h = a * 1e-7, fp = (F(a + h) - F(a - h)) / (2 * h), an = a - f / fp;
+        bool done = fabs(an - a) <= 1e-15 * fabs(a);
+        a = an;
+        if (done) break;
+    }
+    double u[5] = {a, 0, 1, 1, 0};
+    std::vector<double> T, Y, DY;
+    T.push_back(tini); Y.insert(Y.end(), u, u + 5);
+    Step S; SbController ctl; ctl.init();
+    // automatic initial step (Hairer), as in OrdinaryDiffEq
+    double dt;
+    {
+        double f0[5], f1[5], u1[5], sk[5], d0 = 0, d1 = 0, d2 = 0;
+        sb_bg_rhs(u, P, f0);
+        for (int i = 0; i < 5; i++) { sk[i] = abstol + fabs(u[i]) * reltol; d0 += (u[i] / sk[i]) * (u[i] / sk[i]); d1 += (f0[i] / sk[i]) * (f0[i] / sk[i]); }
+        d0 = sqrt(d0 / 5); d1 = sqrt(d1 / 5);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        dt0 = fmin(dt0, tmax - tini);
+        for (int i = 0; i < 5; i++) u1[i] = u[i] + dt0 * f0[i];
+        sb_bg_rhs(u1, P, f1);
+        for (int i = 0; i < 5; i++) { double r = (f1[i] - f0[i]) / sk[i]; d2 += r * r; }
+        d2 = sqrt(d2 / 5) / dt0;
+        double dm = fmax(d1, d2);
+        double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 5.0);
+        dt = fmin(fmin(100 * dt0, dt1), tmax - tini);
+    }
+    double tt = tini; int rc = SB_RC_SUCCESS; long nacc = 0, nrej = 0; bool first = true;
+    double tau0 = 0, kappa0 = 0;
+    for (long it = 0;; it++) {
+        if (it >= 100000) { rc = SB_RC_MAXITERS; break; }
+        if (tt + dt > tmax) dt = tmax - tt;
+        if (!S.run(P, u, dt)) { rc = SB_RC_UNSTABLE; break; }
+        double EEst = errnorm(S.ks[7], u, S.unew, abstol, reltol);
+        if (!isfinite(EEst)) { nrej++; dt /= 5; if (dt < 1e-14 * tt) { rc = SB_RC_UNSTABLE; break; } continue; }
+        double q = ctl.q_of(EEst);
+        if (EEst > 1) { nrej++; dt = ctl.reject(dt); if (dt < 1e-14 * tt) { rc = SB_RC_DTMIN; break; } continue; }
+        nacc++;
+        double dtnew = ctl.accept(dt, q, EEst), d[5];
+        if (first) { S.dinterp(u, S.unew, 0.0, dt, d); DY.insert(DY.end(), d, d + 5); first = false; }
+        if (S.unew[0] - 1.0 >= 0) { // "today" callback: right-root of a − 1 on the dense output (src/solve.jl:158-202)
+            double lo = 0, hi = 1, tmp[5];
+            for (int b = 0; b < 200; b++) { double mid = 0.5 * (lo + hi); if (mid == lo || mid == hi) break; S.interp(u, S.unew, mid, tmp); if (tmp[0] - 1.0 >= 0) hi = mid; else lo = mid; }
+            double uend[5], dend[5]; S.interp(u, S.unew, hi, uend);
+            double dtr = hi * dt, tr = tt + dtr;
+            Step S2; // dense-output vectors of the shortened step (what OrdinaryDiffEq recomputes after moving t)
+            if (S2.run(P, u, dtr)) S2.dinterp(u, uend, 1.0, dtr, dend); else sb_bg_rhs(uend, P, dend);
+            T.push_back(tr); Y.insert(Y.end(), uend, uend + 5); DY.insert(DY.end(), dend, dend + 5);
+            tau0 = tr; kappa0 = uend[1];
+            break;
+        }
+        S.dinterp(u, S.unew, 1.0, dt, d);
+        tt += dt; memcpy(u, S.unew, sizeof(u));
+        T.push_back(tt); Y.insert(Y.end(), u, u + 5); DY.insert(DY.end(), d, d + 5);
+        if (tt >= tmax) { tau0 = tt; kappa0 = u[1]; break; }
+        dt = dtnew;
+    }
+    int nb = (int)T.size();
+    // τrec: knot of maximal visibility over solver steps (src/solve.jl:183-189)
+    double vmax = -1, taurec = tau0;
+    for (int i = 0; i < nb; i++) { double g[5]; sb_bg_rhs(&Y[5 * i], P, g); double v = -g[1] * exp(-(Y[5 * i + 1] - kappa0)); if (v > vmax) { vmax = v; taurec = T[i]; } }
+    info[0] = tau0; info[1] = kappa0; info[2] = taurec; info[3] = rc; info[4] = (double)nacc; info[5] = (double)nrej;
+    if (nb > cap || (int)DY.size() != 5 * nb) return -1;
+    memcpy(t, T.data(), nb * sizeof(double)); memcpy(y, Y.data(), 5 * nb * sizeof(double)); memcpy(dy, DY.data(), 5 * nb * sizeof(double));
+    return nb;
+}
+
+} // extern "C"
+
+// ================================================================================================ DEVICE
+// β-table: node j at s_j = s0 + j·ds (s = ln τ): tab[j][0][m] = β_m(τ_j), tab[j][1][m] = ds·dβ_m/ds = ds·τ_j·dβ_m/dτ.
+// Cubic Hermite in s between nodes.  The table replaces per-stage re-evaluation of the thermodynamics
+// (exp/tanh/pow chains) inside the integrator; its interpolation error is measured by tests (≤ 1e-9 relative).
+__global__ void sb_table_kernel(const double* __restrict__ P, SbSpline spl, int nT, double s0, double ds, double* __restrict__ tab) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nT) return;
+    double tau = exp(s0 + j * ds);
+    double y[5], yp[5], beta[SB_NBETA], betad[SB_NBETA];
+    sb_spl_eval(spl, tau, y, yp);
+    sb_beta(tau, y, yp, P, beta, betad);
+    double* o = tab + (size_t)j * 2 * SB_NBETA;
+    for (int m = 0; m < SB_NBETA; m++) { o[m] = beta[m]; o[SB_NBETA + m] = ds * tau * betad[m]; }
+}
+
+struct SbTable {
+    int nT;
+    double s0, ds, inv_ds;
+    const double* tab;
+};
+
+struct SbSolveArgs {
+    const double* P;
+    SbSpline spl;
+    SbTable tb;
+    int nk;
+    const double *ks, *tini;
+    const int* order;
+    double tend;
+    int nsave;
+    const double* saveat;
+    double reltol, abstol;
+    int maxiters;
+    double *usave, *uend;
+    int* retcode;
+    long long* stats; // [nk][4] = naccept, nreject, nf, nsolve
+    int* queue;
+};
+
+// shared-memory layout per warp (doubles)
+#define SB_SM_U 0
+#define SB_SM_UU (SB_SM_U + SB_N)
+#define SB_SM_K (SB_SM_UU + SB_N)
+#define SB_SM_DT (SB_SM_K + 8 * SB_N)
+#define SB_SM_F0 (SB_SM_DT + SB_N)
+#define SB_SM_D (SB_SM_F0 + SB_N)
+#define SB_SM_UP (SB_SM_D + SB_N)
+#define SB_SM_MM (SB_SM_UP + SB_N)
+#define SB_SM_ZP (SB_SM_MM + SB_N)
+#define SB_SM_ZQ (SB_SM_ZP + SB_N)
+#define SB_SM_BS (SB_SM_ZQ + SB_N)
+#define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
+#define SB_SM_BLK (SB_SM_BD + SB_NB)
+#define SB_SM_KP (SB_SM_BLK + SB_BLKSTORE)
+#define SB_SM_DOUBLES (SB_SM_KP + 8)
+#define SB_SM_BYTES (SB_SM_DOUBLES * 8 + SB_N * 4)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SB_FULL, v, o);
+    return v;
+}
+
+// basis functions b_m = k^e β_m(τ) (and optionally ḃ_m) from the β-table; lanes over m
+__device__ __forceinline__ void sb_basis_at(const SbTable& tb, double tau, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
+    double s = log(tau);
+    double fi = (s - tb.s0) * tb.inv_ds;
+    int i = (int)floor(fi);
+    i = max(0, min(i, tb.nT - 2));
+    double w = fi - i, w1 = w - 1.0;
+    double h00 = (1 + 2 * w) * w1 * w1, h10 = w * w1 * w1, h01 = w * w * (3 - 2 * w), h11 = w * w * w1;
+    double g00 = 6 * w * w1, g10 = (3 * w - 1) * w1, g11 = w * (3 * w - 2); // derivatives wrt w (g01 = -g00)
+    const double* n0 = tb.tab + (size_t)i * 2 * SB_NBETA;
+    const double* n1 = n0 + 2 * SB_NBETA;
+    for (int m = lane; m < SB_NB; m += SB_WARP) {
+        int be = sb_basis_beta[m];
+        double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n1 + be), d1 = __ldg(n1 + SB_NBETA + be);
+        double kk = kp[sb_basis_kpow[m] + 3];
+        b[m] = kk * (h00 * v0 + h10 * d0 + h01 * v1 + h11 * d1);
+        if (bd) bd[m] = kk * (g00 * (v0 - v1) + g10 * d0 + g11 * d1) * tb.inv_ds / tau; // dβ/dτ = (dβ/dw)/(ds·τ)
+    }
+}
+
+// out = J(b)·U  (table-driven: local CSR rows + the two hub functionals)
+__device__ __forceinline__ void sb_eval_f(const double* b, const double* U, double* out, int lane) {
+    double sphi = 0, spsi = 0;
+    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) sphi += sb_hcoef[t] * b[sb_hb[t]] * U[sb_hidx[t]];
+    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) spsi += sb_hcoef[t] * b[sb_hb[t]] * U[sb_hidx[t]];
+    sphi = warp_sum(sphi); spsi = warp_sum(spsi);
+    for (int i = lane; i < SB_N; i += SB_WARP) {
+        double acc = 0;
+        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * b[sb_bidx[e]] * U[sb_col[e]];
+        out[i] = acc;
+    }
+    __syncwarp();
+    for (int t = sb_hptr[0] + lane; t < sb_hptr[1]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * sphi;
+    __syncwarp();
+    for (int t = sb_hptr[1] + lane; t < sb_hptr[2]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * spsi;
+    __syncwarp();
+}
+// product rule for ∂f/∂τ = J'u:  J' = J_local(ḃ) + ṗ φᵀ + p φ̇ᵀ + q̇ ψᵀ + q ψ̇ᵀ
+__device__ __forceinline__ void sb_eval_dT(const double* b, const double* bd, const double* U, double* out, int lane) {
+    double sphi = 0, spsi = 0, sphid = 0, spsid = 0;
+    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) { double cu = sb_hcoef[t] * U[sb_hidx[t]]; sphi += cu * b[sb_hb[t]]; sphid += cu * bd[sb_hb[t]]; }
+    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) { double cu = sb_hcoef[t] * U[sb_hidx[t]]; spsi += cu * b[sb_hb[t]]; spsid += cu * bd[sb_hb[t]]; }
+    sphi = warp_sum(sphi); spsi = warp_sum(spsi); sphid = warp_sum(sphid); spsid = warp_sum(spsid);
+    for (int i = lane; i < SB_N; i += SB_WARP) {
+        double acc = 0;
+        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * bd[sb_bidx[e]] * U[sb_col[e]];
+        out[i] = acc;
+    }
+    __syncwarp();
+    for (int t = sb_hptr[0] + lane; t < sb_hptr[1]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * (bd[sb_hb[t]] * sphi + b[sb_hb[t]] * sphid);
+    __syncwarp();
+    for (int t = sb_hptr[1] + lane; t < sb_hptr[2]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * (bd[sb_hb[t]] * spsi + b[sb_hb[t]] * spsid);
+    __syncwarp();
+}
+
+// Factor B = x·I − J_local(b) with the generated elimination forest (no fill) + pivoted dense 2-core blocks.
+__device__ __forceinline__ void sb_factor(double x, const double* b, double* d, double* up, double* mm, double* blk, int* bpiv, int lane) {
+    for (int i = lane; i < SB_N; i += SB_WARP) { d[i] = x; up[i] = 0; mm[i] = 0; }
+    for (int i = lane; i < SB_BLKSTORE; i += SB_WARP) blk[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < SB_N; i += SB_WARP) {
+        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) {
+            double v = -sb_coef[e] * b[sb_bidx[e]];
+            int kind = sb_rkind[e], r = sb_ridx[e];
+            if (kind == 0) d[i] += v;
+            else if (kind == 1) up[i] += v;
+            else if (kind == 2) mm[r] += v;
+            else { int bb = sb_blkid[i]; int nb = sb_bptr[bb + 1] - sb_bptr[bb]; blk[sb_boff[bb] + sb_blkpos[i] * nb + r] += v; }
+        }
+    }
+    __syncwarp();
+    for (int lv = 1; lv < SB_NLEVELS; lv++) {
+        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
+            int v = sb_lvorder[q];
+            double dj = d[v];
+            for (int c = sb_chptr[v]; c < sb_chptr[v + 1]; c++) { int ch = sb_chidx[c]; double m = mm[ch] / d[ch]; mm[ch] = m; dj -= m * up[ch]; }
+            d[v] = dj;
+        }
+        __syncwarp();
+    }
+    for (int bb = lane; bb < SB_NBLOCKS; bb += SB_WARP) { // dense LU with partial pivoting, one lane per block
+        int nb = sb_bptr[bb + 1] - sb_bptr[bb];
+        double* A = blk + sb_boff[bb];
+        int* pv = bpiv + sb_bptr[bb];
+        for (int i = 0; i < nb; i++) A[i * nb + i] = d[sb_bvert[sb_bptr[bb] + i]];
+        for (int kx = 0; kx < nb; kx++) {
+            int p = kx; double mx = fabs(A[kx * nb + kx]);
+            for (int i = kx + 1; i < nb; i++) { double a = fabs(A[i * nb + kx]); if (a > mx) { mx = a; p = i; } }
+            pv[kx] = p;
+            if (p != kx) for (int j = 0; j < nb; j++) { double tt = A[kx * nb + j]; A[kx * nb + j] = A[p * nb + j]; A[p * nb + j] = tt; }
+            double inv = 1.0 / A[kx * nb + kx];
+            for (int i = kx + 1; i < nb; i++) { double l = A[i * nb + kx] * inv; A[i * nb + kx] = l; for (int j = kx + 1; j < nb; j++) A[i * nb + j] -= l * A[kx * nb + j]; }
+        }
+    }
+    __syncwarp();
+}
+
+// r <- B^{-1} r
+__device__ __forceinline__ void sb_bsolve(double* r, const double* d, const double* up, const double* mm, const double* blk, const int* bpiv, int lane) {
+    for (int lv = 1; lv < SB_NLEVELS; lv++) {
+        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
+            int v = sb_lvorder[q];
+            double acc = r[v];
+            for (int c = sb_chptr[v]; c < sb_chptr[v + 1]; c++) { int ch = sb_chidx[c]; acc -= mm[ch] * r[ch]; }
+            r[v] = acc;
+        }
+        __syncwarp();
+    }
+    for (int bb = lane; bb < SB_NBLOCKS; bb += SB_WARP) {
+        int nb = sb_bptr[bb + 1] - sb_bptr[bb];
+        const double* A = blk + sb_boff[bb];
+        const int* pv = bpiv + sb_bptr[bb];
+        const short* vert = sb_bvert + sb_bptr[bb];
+        double x[SB_MAXBLOCK];
+        for (int i = 0; i < nb; i++) x[i] = r[vert[i]];
+        for (int kx = 0; kx < nb; kx++) { int p = pv[kx]; if (p != kx) { double tt = x[kx]; x[kx] = x[p]; x[p] = tt; } }
+        for (int i = 1; i < nb; i++) for (int j = 0; j < i; j++) x[i] -= A[i * nb + j] * x[j];
+        for (int i = nb - 1; i >= 0; i--) { for (int j = i + 1; j < nb; j++) x[i] -= A[i * nb + j] * x[j]; x[i] /= A[i * nb + i]; }
+        for (int i = 0; i < nb; i++) r[vert[i]] = x[i];
+    }
+    __syncwarp();
+    for (int lv = SB_NLEVELS - 1; lv >= 0; lv--) {
+        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
+            int v = sb_lvorder[q], p = sb_parent[v];
+            if (p >= 0) r[v] = (r[v] - up[v] * r[p]) / d[v];
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void sb_hub_dots(const double* b, const double* r, double& s1, double& s2, int lane) {
+    double a = 0, c = 0;
+    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) a += sb_hcoef[t] * b[sb_hb[t]] * r[sb_hidx[t]];
+    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) c += sb_hcoef[t] * b[sb_hb[t]] * r[sb_hidx[t]];
+    s1 = warp_sum(a); s2 = warp_sum(c);
+}
+
+// Persistent kernel: one warp (= one CTA) per k-mode, modes pulled from an atomic work queue in the given order
+// (host sorts by descending k, i.e. descending cost).  FP64 throughout.
+__global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x;
+    double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *d = sm + SB_SM_D, *up = sm + SB_SM_UP,
+           *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
+    int* bpiv = (int*)(sm + SB_SM_DOUBLES);
+    const double reltol = A.reltol, abstol = A.abstol;
+
+    while (true) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(A.queue, 1);
+        qi = __shfl_sync(SB_FULL, qi, 0);
+        if (qi >= A.nk) break;
+        const int mode = A.order ? A.order[qi] : qi;
+        const double k = A.ks[mode];
+        double t = A.tini[mode];
+        const double tend = A.tend;
+        long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
+        int rc = SB_RC_SUCCESS, isave = 0;
+        double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
+
+        if (!(k > 0) || !isfinite(k)) { // reference: solve fails for k = 0 / NaN (test "Success checking", runtests.jl:358-361)
+            for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = NAN;
+            if (usave) for (int i = lane; i < A.nsave * SB_N; i += SB_WARP) usave[i] = NAN;
+            if (lane == 0) { A.retcode[mode] = SB_RC_UNSTABLE; for (int j = 0; j < 4; j++) A.stats[4 * mode + j] = 0; }
+            continue;
+        }
+        if (lane < 7) kp[lane] = pow(k, (double)(lane - 3));
+        if (lane == 0) { double y[5]; sb_spl_eval(A.spl, t, y, nullptr); sb_initial(t, k, y, A.P, u); }
+        __syncwarp();
+        while (isave < A.nsave && A.saveat[isave] <= t) { // save points at (or before) the start
+            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = (A.saveat[isave] == t) ? u[i] : NAN;
+            isave++;
+        }
+        SbController ctl; ctl.init();
+        double dt = 0;
+        if (tend > t) {
+            sb_basis_at(A.tb, t, kp, bs, bdv, lane);
+            __syncwarp();
+            sb_eval_f(bs, u, f0, lane); nf++;
+            sb_eval_dT(bs, bdv, u, dT, lane);
+            { // automatic initial step (Hairer), order 5
+                double d0 = 0, d1 = 0;
+                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; d0 += (u[i] / sk) * (u[i] / sk); d1 += (f0[i] / sk) * (f0[i] / sk); }
+                d0 = sqrt(warp_sum(d0) / SB_N); d1 = sqrt(warp_sum(d1) / SB_N);
+                double dtmax = tend - t;
+                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                dt0 = fmin(dt0, dtmax);
+                for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
+                sb_basis_at(A.tb, t + dt0, kp, bs + SB_NB, nullptr, lane);
+                __syncwarp();
+                sb_eval_f(bs + SB_NB, U, K, lane); nf++;
+                double d2 = 0;
+                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; double r = (K[i] - f0[i]) / sk; d2 += r * r; }
+                d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
+                double dm = fmax(d1, d2);
+                double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 5.0);
+                dt = fmin(fmin(100 * dt0, dt1), dtmax);
+                __syncwarp();
+            }
+            for (int it = 0;; it++) {
+                if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
+                bool last = false;
+                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
+                // basis at the 5 later stage times
+                for (int s = 1; s < 6; s++) sb_basis_at(A.tb, t + ((s == 5) ? 1.0 : cc[s]) * dt, kp, bs + s * SB_NB, nullptr, lane);
+                __syncwarp();
+                // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
+                sb_factor(1.0 / (SB_R5_GAMMA * dt), bs, d, up, mm, blk, bpiv, lane);
+                for (int i = lane; i < SB_N; i += SB_WARP) { Zp[i] = 0; Zq[i] = 0; }
+                __syncwarp();
+                for (int tt = sb_hptr[0] + lane; tt < sb_hptr[1]; tt += SB_WARP) Zp[sb_hidx[tt]] += sb_hcoef[tt] * bs[sb_hb[tt]];
+                for (int tt = sb_hptr[1] + lane; tt < sb_hptr[2]; tt += SB_WARP) Zq[sb_hidx[tt]] += sb_hcoef[tt] * bs[sb_hb[tt]];
+                __syncwarp();
+                sb_bsolve(Zp, d, up, mm, blk, bpiv, lane);
+                sb_bsolve(Zq, d, up, mm, blk, bpiv, lane);
+                nsolve += 2;
+                double m11, m12, m21, m22;
+                sb_hub_dots(bs, Zp, m11, m21, lane);
+                sb_hub_dots(bs, Zq, m12, m22, lane);
+                m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
+                const double idet = 1.0 / (m11 * m22 - m12 * m21);
+                // 8 stages
+                for (int s = 0; s < 8; s++) {
+                    double* ks = K + s * SB_N;
+                    const double* fs = f0;
+                    if (s > 0) {
+                        if (s <= 5) { for (int i = lane; i < SB_N; i += SB_WARP) { double v = u[i]; for (int j = 0; j < s; j++) v += cA[s][j] * K[j * SB_N + i]; U[i] = v; } }
+                        else { for (int i = lane; i < SB_N; i += SB_WARP) U[i] += K[(s - 1) * SB_N + i]; }
+                        __syncwarp();
+                        sb_eval_f(bs + cslot[s] * SB_NB, U, ks, lane); nf++;
+                        fs = ks;
+                    }
+                    const double hd_ = dt * cd[s], idt = 1.0 / dt;
+                    for (int i = lane; i < SB_N; i += SB_WARP) { double v = fs[i] + hd_ * dT[i]; for (int j = 0; j < s; j++) v += (cC[s][j] * idt) * K[j * SB_N + i]; ks[i] = v; }
+                    __syncwarp();
+                    sb_bsolve(ks, d, up, mm, blk, bpiv, lane); nsolve++;
+                    double s1, s2;
+                    sb_hub_dots(bs, ks, s1, s2, lane);
+                    const double c1 = (m22 * s1 - m12 * s2) * idet, c2 = (-m21 * s1 + m11 * s2) * idet;
+                    for (int i = lane; i < SB_N; i += SB_WARP) ks[i] += Zp[i] * c1 + Zq[i] * c2;
+                    __syncwarp();
+                }
+                // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
+                double es = 0; bool bad = false;
+                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
+                double EEst = sqrt(warp_sum(es) / SB_N);
+                if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
+                double q = ctl.q_of(EEst);
+                if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                naccept++;
+                const double dtnew = ctl.accept(dt, q, EEst);
+                const double tn = last ? tend : t + dt;
+                if (isave < A.nsave && A.saveat[isave] <= tn) { // dense output (4th order), vectors stored over dT, f0, Zp
+                    for (int i = lane; i < SB_N; i += SB_WARP) {
+                        double a1 = 0, a2 = 0, a3 = 0;
+                        for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
+                        dT[i] = a1; f0[i] = a2; Zp[i] = a3;
+                    }
+                    while (isave < A.nsave && A.saveat[isave] <= tn) {
+                        double ts = A.saveat[isave];
+                        if (ts == tn) { for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = U[i] + K[7 * SB_N + i]; }
+                        else {
+                            double th = (ts - t) / dt, t1 = 1 - th;
+                            for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; usave[(size_t)isave * SB_N + i] = t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i]))); }
+                        }
+                        isave++;
+                    }
+                }
+                for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; if (isnan(un)) bad = true; u[i] = un; }
+                t = tn;
+                bad = __any_sync(SB_FULL, bad);
+                __syncwarp();
+                if (bad) { rc = SB_RC_UNSTABLE; break; }
+                if (last) break;
+                dt = dtnew;
+                sb_basis_at(A.tb, t, kp, bs, bdv, lane);
+                __syncwarp();
+                sb_eval_f(bs, u, f0, lane); nf++;
+                sb_eval_dT(bs, bdv, u, dT, lane);
+            }
+        }
+        for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = u[i];
+        if (usave) for (; isave < A.nsave; isave++) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
+        if (lane == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
+        __syncwarp();
+    }
+}
+
+// Δm(τ,k) for P(k): one thread per mode
+__global__ void sb_deltam_kernel(const double* __restrict__ P, SbSpline spl, double tau, int nk, const double* __restrict__ ks, const double* __restrict__ u, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nk) return;
+    double y[5]; sb_spl_eval(spl, tau, y, nullptr);
+    out[i] = sb_delta_m(tau, ks[i], y, P, u + (size_t)i * SB_N);
+}
+
+// Per-τ background quantities for the CMB sources: one thread per saved time.
+// srcbg[it][0..5] = κ̇, κ̈, κ⃛, exp(−κ), τ0 − τ, spare;  then β_m (NBETA) and flow-derivative dβ_m/dτ (NBETA)
+#define SB_SRCBG_STRIDE (8 + 2 * SB_NBETA)
+__global__ void sb_srcbg_kernel(const double* __restrict__ P, SbSpline spl, int nt, const double* __restrict__ taus, double* __restrict__ srcbg) {
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= nt) return;
+    double tau = taus[it], y[5], g[5], kd[3];
+    sb_spl_eval(spl, tau, y, nullptr);
+    sb_kappa_derivs(y, P, g, kd);
+    double* o = srcbg + (size_t)it * SB_SRCBG_STRIDE;
+    o[0] = kd[0]; o[1] = kd[1]; o[2] = kd[2]; o[3] = exp(-(y[1] - P[SB_P_KAPPA0])); o[4] = P[SB_P_TAU0] - tau; o[5] = 0; o[6] = 0; o[7] = 0;
+    sb_beta(tau, y, g, P, o + 8, o + 8 + SB_NBETA); // time derivatives along the background flow: dy/dτ = g(y)
+}
+
+// CMB source functions ST, SE (reference src/models/cosmologies.jl:99-104) at every saved (k, τ): one thread per point.
+// Derivatives of unknowns are expanded through the ODE itself (u̇ = J u, ü = J̇ u + J u̇), as MTK does symbolically.
+// out layout: S[ik][iS][it], iS = 0: ST, 1: SE
+__global__ void sb_source_kernel(int nt, const double* __restrict__ taus, const double* __restrict__ srcbg, int nk, const double* __restrict__ ks,
+                                 const double* __restrict__ usave, double* __restrict__ S, int scale_k) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nk * nt) return;
+    int ik = idx / nt, it = idx % nt;
+    const double k = ks[ik];
+    const double* sb = srcbg + (size_t)it * SB_SRCBG_STRIDE;
+    const double* u = usave + ((size_t)ik * nt + it) * SB_N;
+    double kpw[7];
+    for (int e = 0; e < 7; e++) kpw[e] = pow(k, (double)(e - 3));
+    double b[SB_NB], bd[SB_NB];
+    for (int m = 0; m < SB_NB; m++) { double kk = kpw[sb_basis_kpow[m] + 3]; b[m] = kk * sb[8 + sb_basis_beta[m]]; bd[m] = kk * sb[8 + SB_NBETA + sb_basis_beta[m]]; }
+    // hubs and their time derivatives
+    double Phd = 0, Psi = 0;
+    for (int t = sb_hptr[2]; t < sb_hptr[3]; t++) Phd += sb_hcoef[t] * b[sb_hb[t]] * u[sb_hidx[t]];
+    for (int t = sb_hptr[3]; t < sb_hptr[4]; t++) Psi += sb_hcoef[t] * b[sb_hb[t]] * u[sb_hidx[t]];
+    double ud[SB_N];
+    for (int i = 0; i < SB_N; i++) { double acc = 0; for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * b[sb_bidx[e]] * u[sb_col[e]]; ud[i] = acc; }
+    for (int t = sb_hptr[0]; t < sb_hptr[1]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Phd;
+    for (int t = sb_hptr[1]; t < sb_hptr[2]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Psi;
+    double Psid = 0;
+    for (int t = sb_hptr[3]; t < sb_hptr[4]; t++) Psid += sb_hcoef[t] * (bd[sb_hb[t]] * u[sb_hidx[t]] + b[sb_hb[t]] * ud[sb_hidx[t]]);
+    // second derivatives of F2, G0, G2 (rows without hub terms): ü_i = J_i(ḃ) u + J_i(b) u̇
+    const int rows3[3] = {SB_I_F2, SB_I_G0, SB_I_G2};
+    double Pig = 0, Pigd = 0, Pigdd = 0;
+    for (int r = 0; r < 3; r++) {
+        int i = rows3[r];
+        double acc = 0;
+        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * (bd[sb_bidx[e]] * u[sb_col[e]] + b[sb_bidx[e]] * ud[sb_col[e]]);
+        Pig += u[i]; Pigd += ud[i]; Pigdd += acc;
+    }
+    const double kd = sb[0], kdd = sb[1], kddd = sb[2], ek = sb[3], chi = sb[4];
+    const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
+    const double thb = u[SB_I_TB], thbd = ud[SB_I_TB];
+    double ST = v * (u[SB_I_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
+    double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
+    if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
+    S[((size_t)ik * 2 + 0) * nt + it] = ST;
+    S[((size_t)ik * 2 + 1) * nt + it] = SE;
+}
+
+// ================================================================================================ C ABI (device pointers)
+#define SB_CUDA_CHECK(x)                                             \
+    do {                                                             \
+        cudaError_t e_ = (x);                                        \
+        if (e_ != cudaSuccess) { fprintf(stderr, "symboltz_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)e_ - 1000; } \
+    } while (0)
+
+extern "C" {
+
+int sbm_smem_bytes(void) { return SB_SM_BYTES; }
+int sbm_srcbg_stride(void) { return SB_SRCBG_STRIDE; }
+
+int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nT, double s0, double ds, double* dtab, void* stream) {
+    SbSpline spl{nb, dt, dy, ddy};
+    sb_table_kernel<<<(nT + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dP, spl, nT, s0, ds, dtab);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Perturbation solve over nk modes (reference solvept, src/solve.jl:543-569).  All array arguments are DEVICE pointers.
+// dorder may be NULL (natural order).  dqueue: one int, zeroed by this call.  nctas <= 0: fill the GPU.
+int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nT, double s0, double ds, const double* dtab, int nk,
+                const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream) {
+    if (nk <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SbSolveArgs A;
+    A.P = dP; A.spl = SbSpline{nb, dt, dy, ddy}; A.tb = SbTable{nT, s0, ds, 1.0 / ds, dtab};
+    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.tend = tend; A.nsave = dusave ? nsave : 0; A.saveat = dsaveat;
+    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
+    SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
+    static int occ = 0, nsm = 0;
+    if (!occ) {
+        int dev; SB_CUDA_CHECK(cudaGetDevice(&dev));
+        SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP, SB_SM_BYTES));
+        if (occ < 1) occ = 1;
+    }
+    int grid = nctas > 0 ? nctas : std::min(nk, nsm * occ);
+    sb_integrate_kernel<<<grid, SB_WARP, SB_SM_BYTES, st>>>(A);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return grid;
+}
+
+int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, double tau, int nk, const double* dks, const double* du, double* dout, void* stream) {
+    if (nk <= 0) return 0;
+    sb_deltam_kernel<<<(nk + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dP, SbSpline{nb, dt, dy, ddy}, tau, nk, dks, du, dout);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// sources: dsrcbg is scratch of nt·sbm_srcbg_stride() doubles; dS: [nk][2][nt]
+int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, int nk, const double* dks,
+                const double* dusave, double* dS, int scale_k, void* stream) {
+    if (nk <= 0 || nt <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    sb_srcbg_kernel<<<(nt + 63) / 64, 64, 0, st>>>(dP, SbSpline{nb, dt, dy, ddy}, nt, dtaus, dsrcbg);
+    SB_CUDA_CHECK(cudaGetLastError());
+    int n = nk * nt;
+    sb_source_kernel<<<(n + 127) / 128, 128, 0, st>>>(nt, dtaus, dsrcbg, nk, dks, dusave, dS, scale_k);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+} // extern "C"

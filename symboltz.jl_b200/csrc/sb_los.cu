@@ -1,0 +1,193 @@
+// symboltz.jl_b200 -- model-independent line-of-sight / C_l kernels for sm_100a + C ABI (device pointers).
+//
+// Replaces, for the hot path (file:line relative to the reference tree):
+//   SphericalBesselCache           src/observables/angular.jl:9-48, 59-60   -> sbl_bessel_table (table built on the GPU)
+//   source_kinterp (Chebyshev)     src/observables/fourier.jl:232-247, 524-547 -> fused into sbl_los (B·S_coarse in shared memory)
+//   los_integrate                  src/observables/angular.jl:109-152       -> sbl_los (one CTA per fine k, threads over l × τ-slices)
+//   Θ rescale                      src/observables/angular.jl:301-306       -> epilogue of sbl_los
+//   spectrum_cmb(ΘA,ΘB,P0,ls,ks)   src/observables/angular.jl:198-223       -> sbl_cl (natural-spline k-integral as a weighted dot product;
+//                                                                              the integral is linear in the data, weights from the host)
+// FP64 throughout; no tensor cores (this is table interpolation + reductions, not a contraction worth reshaping).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+
+#define SBL_CUDA_CHECK(x)                                            \
+    do {                                                             \
+        cudaError_t e_ = (x);                                        \
+        if (e_ != cudaSuccess) { fprintf(stderr, "symboltz_b200(los): CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -(int)e_ - 1000; } \
+    } while (0)
+
+#define SBL_MAXNL 1024
+
+// j_l(x) and j_l'(x) = l/(2l+1) j_{l-1} − (l+1)/(2l+1) j_{l+1} for the requested (sorted, integer) l at x = ix·step.
+// Upward recurrence where it is stable (l < x), Miller's downward recurrence with rescaling otherwise.
+// Output layout: y[ix*nl + il] (l contiguous, as the reference's `y[il, ix]` column-major matrix).
+__global__ void sbl_bessel_kernel(int nl, const int* __restrict__ ls, int nxp, double step, double* __restrict__ y, double* __restrict__ dy) {
+    int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ix >= nxp) return;
+    const double x = ix * step;
+    double* yo = y + (size_t)ix * nl;
+    double* dyo = dy + (size_t)ix * nl;
+    const int lmax = ls[nl - 1];
+    if (x == 0.0) {
+        for (int i = 0; i < nl; i++) { yo[i] = (ls[i] == 0) ? 1.0 : 0.0; dyo[i] = (ls[i] == 1) ? 1.0 / 3.0 : 0.0; }
+        return;
+    }
+    double sx, cx;
+    sincos(x, &sx, &cx);
+    const double j0 = sx / x, j1 = sx / (x * x) - cx / x;
+    if (x > lmax + 1.5) { // upward, stable for n < x
+        double jm = j0, jn = j1; // j_{n-1}, j_n with n = 1
+        int ip = 0;
+        if (ls[0] == 0) { yo[0] = j0; dyo[0] = -j1; ip = 1; }
+        for (int n = 1; n <= lmax; n++) {
+            double jp = (2 * n + 1) / x * jn - jm; // j_{n+1}
+            if (ip < nl && ls[ip] == n) { yo[ip] = jn; dyo[ip] = (n * jm - (n + 1) * jp) / (2 * n + 1); ip++; }
+            jm = jn; jn = jp;
+        }
+        return;
+    }
+    // downward (Miller).  Start far enough above max(lmax+1, x) that the seed error has decayed below 1e-17.
+    const double big = 1e200, small = 1e-200;
+    int Lm = lmax + 1;
+    int nstart = Lm + 25 + (int)ceil(pow(60.0 * sqrt(0.5 * Lm + 1.0), 2.0 / 3.0));
+    double jp = 0.0, jn = 1e-250; // j_{n+1}, j_n at n = nstart (unnormalised)
+    int nres = 0;                 // number of rescalings applied so far
+    short cnt[SBL_MAXNL];
+    int ip = nl - 1;
+    for (int n = nstart; n >= 1; n--) {
+        double jm = (2 * n + 1) / x * jn - jp; // j_{n-1}
+        if (ip >= 0 && ls[ip] == n) { yo[ip] = jn; dyo[ip] = (n * jm - (n + 1) * jp) / (2 * n + 1); cnt[ip] = (short)nres; ip--; }
+        jp = jn; jn = jm;
+        if (fabs(jn) > big) { jn *= small; jp *= small; nres++; }
+    }
+    // now jn = j_0, jp = j_1 (unnormalised)
+    if (ip >= 0 && ls[ip] == 0) { yo[ip] = jn; dyo[ip] = -jp; cnt[ip] = (short)nres; ip--; }
+    const double scale = (fabs(j0) >= fabs(j1)) ? j0 / jn : j1 / jp;
+    for (int i = 0; i < nl; i++) {
+        int m = nres - cnt[i];
+        double f = scale;
+        // values recorded before m later rescalings are too large by big^m relative to the final scale
+        if (m >= 2) f = 0.0; else if (m == 1) f *= small;
+        yo[i] *= f; dyo[i] *= f;
+    }
+}
+
+// One CTA per fine k: optional barycentric k-interpolation of the coarse sources (in shared memory), trapezoid-weighted
+// line-of-sight sum against the Hermite-interpolated j_l table, Θ rescaling.  Threads: x → l, y → τ slice.
+// Sc layout [nc][2][nt] (coarse k, source, time);  Bw [nk][nc] barycentric weights (NULL: direct, nc == nk);
+// jy/jdy [nx][nl];  Theta out [2][nl][nk].
+__global__ void sbl_los_kernel(int nk, int k0, const double* __restrict__ ks, int nc, const double* __restrict__ Bw, const double* __restrict__ Sc, int nt,
+                               const double* __restrict__ chi, const double* __restrict__ wt, int nl, const int* __restrict__ ls, const double* __restrict__ jy,
+                               const double* __restrict__ jdy, double invdx, double dxc, int nxp, double* __restrict__ Theta, int nk_total) {
+    extern __shared__ double sh[];
+    double* SwT = sh;            // [nt] weighted temperature source
+    double* SwE = sh + nt;       // [nt]
+    double* red = sh + 2 * nt;   // [TS][LT][2] reduction scratch
+    const int ik = blockIdx.x;   // local index in [0, nk)
+    const int LT = blockDim.x, TS = blockDim.y;
+    const int tid = threadIdx.y * LT + threadIdx.x, nthr = LT * TS;
+    const double k = ks[k0 + ik];
+    for (int o = tid; o < 2 * nt; o += nthr) {
+        int s = o / nt, it = o % nt;
+        double v;
+        if (Bw) {
+            const double* bw = Bw + (size_t)(k0 + ik) * nc;
+            v = 0;
+            for (int j = 0; j < nc; j++) v += bw[j] * Sc[((size_t)j * 2 + s) * nt + it];
+        } else v = Sc[((size_t)(k0 + ik) * 2 + s) * nt + it];
+        v *= wt[it];
+        if (it == nt - 1) v = 0.0; // reference zeroes the last row (χ = 0), angular.jl:296
+        sh[o] = v;
+    }
+    __syncthreads();
+    const int il = threadIdx.x;
+    double aT = 0, aE = 0;
+    if (il < nl) {
+        for (int it = threadIdx.y; it < nt; it += TS) {
+            double w = k * chi[it] * invdx;
+            int i = (int)w; // trunc, x >= 0
+            w -= i;
+            if (i > nxp - 2) { i = nxp - 2; w = 1.0; }
+            const double wm1 = w - 1.0;
+            const size_t o0 = (size_t)i * nl + il, o1 = o0 + nl;
+            const double ym = __ldg(jy + o0), yp = __ldg(jy + o1), dm = __ldg(jdy + o0), dp = __ldg(jdy + o1);
+            const double j = (1 + 2 * w) * wm1 * wm1 * ym + w * w * (3 - 2 * w) * yp + w * wm1 * (wm1 * dm + w * dp) * dxc; // angular.jl:38-48
+            aT += SwT[it] * j;
+            aE += SwE[it] * j;
+        }
+    }
+    red[(threadIdx.y * LT + threadIdx.x) * 2] = aT;
+    red[(threadIdx.y * LT + threadIdx.x) * 2 + 1] = aE;
+    __syncthreads();
+    if (threadIdx.y == 0 && il < nl) {
+        for (int s = 1; s < TS; s++) { aT += red[(s * LT + il) * 2]; aE += red[(s * LT + il) * 2 + 1]; }
+        const double l = (double)ls[il];
+        Theta[((size_t)0 * nl + il) * nk_total + k0 + ik] = aT / k;                                                   // angular.jl:302
+        Theta[((size_t)1 * nl + il) * nk_total + k0 + ik] = aE * sqrt((l + 2) * (l + 1) * l * (l - 1)) / (k * k);     // angular.jl:305
+    }
+}
+
+// C_l^{AB} = Σ_k c_k Θ^A_l(k) Θ^B_l(k) with c_k = w_k (2/π) k² P0(k), w_k = natural-cubic-spline integration weights.
+// grid (nl, nmodes); modes: pairs (A,B) of source indices.  Cl out [nmodes][nl].  Deterministic tree reduction.
+__global__ void sbl_cl_kernel(int nl, int nk, int k0, int k1, const double* __restrict__ ck, const double* __restrict__ Theta, const int* __restrict__ modeA,
+                              const int* __restrict__ modeB, double* __restrict__ Cl) {
+    __shared__ double red[256];
+    const int il = blockIdx.x, im = blockIdx.y;
+    const double* TA = Theta + ((size_t)modeA[im] * nl + il) * nk;
+    const double* TB = Theta + ((size_t)modeB[im] * nl + il) * nk;
+    double acc = 0;
+    for (int ik = k0 + threadIdx.x; ik < k1; ik += blockDim.x) acc += ck[ik] * TA[ik] * TB[ik];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) Cl[(size_t)im * nl + il] = red[0];
+}
+
+// Standalone barycentric k-interpolation (reference source_kinterp, fourier.jl:232-247): Sf[nk][2][nt] = Σ_j Bw[k][j] Sc[j][2][nt]
+__global__ void sbl_kinterp_kernel(int nk, int nc, const double* __restrict__ Bw, const double* __restrict__ Sc, int n2t, double* __restrict__ Sf) {
+    int ik = blockIdx.x;
+    for (int o = threadIdx.x; o < n2t; o += blockDim.x) {
+        double v = 0;
+        for (int j = 0; j < nc; j++) v += Bw[(size_t)ik * nc + j] * Sc[(size_t)j * n2t + o];
+        Sf[(size_t)ik * n2t + o] = v;
+    }
+}
+
+extern "C" {
+
+int sbl_bessel_table(int nl, const int* dls, int nxp, double step, double* dy_, double* ddy_, void* stream) {
+    if (nl > SBL_MAXNL) return -2;
+    sbl_bessel_kernel<<<(nxp + 63) / 64, 64, 0, (cudaStream_t)stream>>>(nl, dls, nxp, step, dy_, ddy_);
+    SBL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// Line-of-sight integration for fine-k indices [k0, k0+nk) of a grid with nk_total points (multi-GPU: each rank its slice).
+int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nt, const double* dchi, const double* dwt, int nl,
+            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, void* stream) {
+    if (nk <= 0) return 0;
+    int LT = ((nl + 31) / 32) * 32;
+    if (LT > 1024) return -2;
+    int TS = 512 / LT; if (TS > 8) TS = 8; if (TS < 1) TS = 1;
+    size_t smem = (size_t)(2 * nt + 2 * LT * TS) * sizeof(double);
+    if (smem > 48 * 1024) SBL_CUDA_CHECK(cudaFuncSetAttribute(sbl_los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sbl_los_kernel<<<nk, dim3(LT, TS), smem, (cudaStream_t)stream>>>(nk, k0, dks, nc, dBw, dSc, nt, dchi, dwt, nl, dls, djy, djdy, invdx, dx, nxp, dTheta, nk_total);
+    SBL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sbl_cl(int nl, int nk, int k0, int k1, const double* dck, const double* dTheta, int nmodes, const int* dmodeA, const int* dmodeB, double* dCl, void* stream) {
+    sbl_cl_kernel<<<dim3(nl, nmodes), 256, 0, (cudaStream_t)stream>>>(nl, nk, k0, k1, dck, dTheta, dmodeA, dmodeB, dCl);
+    SBL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, double* dSf, void* stream) {
+    if (nk <= 0) return 0;
+    sbl_kinterp_kernel<<<nk, 256, 0, (cudaStream_t)stream>>>(nk, nc, dBw, dSc, n2t, dSf);
+    SBL_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+} // extern "C"
