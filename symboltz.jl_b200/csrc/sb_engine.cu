@@ -274,8 +274,8 @@ struct SbSolveArgs {
 #define SB_SM_K (SB_SM_UU + SB_N)
 #define SB_SM_DT (SB_SM_K + 8 * SB_N)
 #define SB_SM_F0 (SB_SM_DT + SB_N)
-#define SB_SM_D (SB_SM_F0 + SB_N)
-#define SB_SM_UP (SB_SM_D + SB_N)
+#define SB_SM_DI (SB_SM_F0 + SB_N)
+#define SB_SM_UP (SB_SM_DI + SB_N)
 #define SB_SM_MM (SB_SM_UP + SB_N)
 #define SB_SM_ZP (SB_SM_MM + SB_N)
 #define SB_SM_ZQ (SB_SM_ZP + SB_N)
@@ -284,7 +284,10 @@ struct SbSolveArgs {
 #define SB_SM_BLK (SB_SM_BD + SB_NB)
 #define SB_SM_KP (SB_SM_BLK + SB_BLKSTORE)
 #define SB_SM_DOUBLES (SB_SM_KP + 8)
-#define SB_SM_BYTES (SB_SM_DOUBLES * 8 + SB_N * 4)
+#define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
+#define SB_WARPS_PER_CTA 1
+#define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
+#define SB_NBR ((SB_NB + 31) / 32)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -292,152 +295,290 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Per-lane schedules produced by the code generator, kept in registers for the lifetime of the kernel
+// (every loop over them is fully unrolled so that the arrays never become addressable local memory).
+struct SbLane {
+    double ec[SB_R * SB_WD];   // J_local ELL coefficients of the rows owned by this lane
+    unsigned ei[SB_R * SB_WD]; // col | basis<<8 | role<<16 | target<<20
+    double pqc[SB_R * 2];      // hub vectors p, q at the owned rows
+    unsigned pqi[SB_R];
+    double phc[SB_TPH], psc[SB_TPS]; // hub functionals φ, ψ: one term per lane and slot
+    unsigned phi[SB_TPH], psi[SB_TPS];
+    unsigned ph[SB_NPH * SB_PR], pk[SB_NPH * SB_PR], pv[SB_NPH * SB_PR * SB_PLW]; // owned elimination paths: len|parent, first-vertex children, vertices
+    unsigned dk;               // dense-block member owned by this lane (lane = block*8+row): its forest children
+    unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
+    __device__ __forceinline__ void load(int lane) {
+#pragma unroll
+        for (int e = 0; e < SB_R * SB_WD; e++) { ec[e] = sb_ell_coef[e * 32 + lane]; ei[e] = sb_ell_idx[e * 32 + lane]; }
+#pragma unroll
+        for (int r = 0; r < SB_R; r++) { pqc[2 * r] = sb_pq_coef[(2 * r) * 32 + lane]; pqc[2 * r + 1] = sb_pq_coef[(2 * r + 1) * 32 + lane]; pqi[r] = sb_pq_idx[r * 32 + lane]; }
+#pragma unroll
+        for (int t = 0; t < SB_TPH; t++) { phc[t] = sb_phi_coef[t * 32 + lane]; phi[t] = sb_phi_idx[t * 32 + lane]; }
+#pragma unroll
+        for (int t = 0; t < SB_TPS; t++) { psc[t] = sb_psi_coef[t * 32 + lane]; psi[t] = sb_psi_idx[t * 32 + lane]; }
+#pragma unroll
+        for (int q = 0; q < SB_NPH * SB_PR; q++) { ph[q] = sb_path_head[q * 32 + lane]; pk[q] = sb_path_kids[q * 32 + lane]; }
+#pragma unroll
+        for (int q = 0; q < SB_NPH * SB_PR * SB_PLW; q++) pv[q] = sb_path_vert[q * 32 + lane];
+        dk = sb_dense_kids[lane];
+#pragma unroll
+        for (int r = 0; r < SB_NBR; r++) { int m = r * 32 + lane; bp[r] = (m < SB_NB) ? sb_basis_pack[m] : 0u; }
+    }
+};
+
 // basis functions b_m = k^e β_m(τ) (and optionally ḃ_m) from the β-table; lanes over m
-__device__ __forceinline__ void sb_basis_at(const SbTable& tb, double tau, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
+__device__ __forceinline__ void sb_basis_at(const SbLane& S, const SbTable& tb, double tau, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
     double s = log(tau);
     double fi = (s - tb.s0) * tb.inv_ds;
     int i = (int)floor(fi);
     i = max(0, min(i, tb.nT - 2));
     double w = fi - i, w1 = w - 1.0;
     double h00 = (1 + 2 * w) * w1 * w1, h10 = w * w1 * w1, h01 = w * w * (3 - 2 * w), h11 = w * w * w1;
-    double g00 = 6 * w * w1, g10 = (3 * w - 1) * w1, g11 = w * (3 * w - 2); // derivatives wrt w (g01 = -g00)
     const double* n0 = tb.tab + (size_t)i * 2 * SB_NBETA;
     const double* n1 = n0 + 2 * SB_NBETA;
-    for (int m = lane; m < SB_NB; m += SB_WARP) {
-        int be = sb_basis_beta[m];
-        double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n1 + be), d1 = __ldg(n1 + SB_NBETA + be);
-        double kk = kp[sb_basis_kpow[m] + 3];
-        b[m] = kk * (h00 * v0 + h10 * d0 + h01 * v1 + h11 * d1);
-        if (bd) bd[m] = kk * (g00 * (v0 - v1) + g10 * d0 + g11 * d1) * tb.inv_ds / tau; // dβ/dτ = (dβ/dw)/(ds·τ)
+#pragma unroll
+    for (int r = 0; r < SB_NBR; r++) {
+        int m = r * 32 + lane;
+        if (m < SB_NB) {
+            int be = S.bp[r] & 255;
+            double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n1 + be), d1 = __ldg(n1 + SB_NBETA + be);
+            double kk = kp[(S.bp[r] >> 8) & 255];
+            b[m] = kk * (h00 * v0 + h10 * d0 + h01 * v1 + h11 * d1);
+            if (bd) {
+                double g00 = 6 * w * w1, g10 = (3 * w - 1) * w1, g11 = w * (3 * w - 2); // d/dw of the Hermite basis (g01 = -g00)
+                bd[m] = kk * (g00 * (v0 - v1) + g10 * d0 + g11 * d1) * tb.inv_ds / tau; // dβ/dτ = (dβ/dw)/(ds·τ)
+            }
+        }
     }
 }
 
-// out = J(b)·U  (table-driven: local CSR rows + the two hub functionals)
-__device__ __forceinline__ void sb_eval_f(const double* b, const double* U, double* out, int lane) {
+// out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU
+__device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane) {
     double sphi = 0, spsi = 0;
-    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) sphi += sb_hcoef[t] * b[sb_hb[t]] * U[sb_hidx[t]];
-    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) spsi += sb_hcoef[t] * b[sb_hb[t]] * U[sb_hidx[t]];
+#pragma unroll
+    for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[(S.phi[t] >> 8) & 255] * U[S.phi[t] & 255];
+#pragma unroll
+    for (int t = 0; t < SB_TPS; t++) spsi += S.psc[t] * b[(S.psi[t] >> 8) & 255] * U[S.psi[t] & 255];
     sphi = warp_sum(sphi); spsi = warp_sum(spsi);
-    for (int i = lane; i < SB_N; i += SB_WARP) {
-        double acc = 0;
-        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * b[sb_bidx[e]] * U[sb_col[e]];
-        out[i] = acc;
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) {
+        double acc = S.pqc[2 * r] * b[S.pqi[r] & 255] * sphi + S.pqc[2 * r + 1] * b[(S.pqi[r] >> 8) & 255] * spsi;
+#pragma unroll
+        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * b[(S.ei[e] >> 8) & 255] * U[S.ei[e] & 255]; }
+        const int i = r * 32 + lane;
+        if (i < SB_N) out[i] = acc;
     }
-    __syncwarp();
-    for (int t = sb_hptr[0] + lane; t < sb_hptr[1]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * sphi;
-    __syncwarp();
-    for (int t = sb_hptr[1] + lane; t < sb_hptr[2]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * spsi;
     __syncwarp();
 }
-// product rule for ∂f/∂τ = J'u:  J' = J_local(ḃ) + ṗ φᵀ + p φ̇ᵀ + q̇ ψᵀ + q ψ̇ᵀ
-__device__ __forceinline__ void sb_eval_dT(const double* b, const double* bd, const double* U, double* out, int lane) {
+// ∂f/∂τ = J'u with J' = J_local(ḃ) + ṗ φᵀ + p φ̇ᵀ + q̇ ψᵀ + q ψ̇ᵀ
+__device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, const double* bd, const double* U, double* out, int lane) {
     double sphi = 0, spsi = 0, sphid = 0, spsid = 0;
-    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) { double cu = sb_hcoef[t] * U[sb_hidx[t]]; sphi += cu * b[sb_hb[t]]; sphid += cu * bd[sb_hb[t]]; }
-    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) { double cu = sb_hcoef[t] * U[sb_hidx[t]]; spsi += cu * b[sb_hb[t]]; spsid += cu * bd[sb_hb[t]]; }
+#pragma unroll
+    for (int t = 0; t < SB_TPH; t++) { double cu = S.phc[t] * U[S.phi[t] & 255]; sphi += cu * b[(S.phi[t] >> 8) & 255]; sphid += cu * bd[(S.phi[t] >> 8) & 255]; }
+#pragma unroll
+    for (int t = 0; t < SB_TPS; t++) { double cu = S.psc[t] * U[S.psi[t] & 255]; spsi += cu * b[(S.psi[t] >> 8) & 255]; spsid += cu * bd[(S.psi[t] >> 8) & 255]; }
     sphi = warp_sum(sphi); spsi = warp_sum(spsi); sphid = warp_sum(sphid); spsid = warp_sum(spsid);
-    for (int i = lane; i < SB_N; i += SB_WARP) {
-        double acc = 0;
-        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * bd[sb_bidx[e]] * U[sb_col[e]];
-        out[i] = acc;
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) {
+        const int pb = S.pqi[r] & 255, qb = (S.pqi[r] >> 8) & 255;
+        double acc = S.pqc[2 * r] * (bd[pb] * sphi + b[pb] * sphid) + S.pqc[2 * r + 1] * (bd[qb] * spsi + b[qb] * spsid);
+#pragma unroll
+        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * bd[(S.ei[e] >> 8) & 255] * U[S.ei[e] & 255]; }
+        const int i = r * 32 + lane;
+        if (i < SB_N) out[i] = acc;
     }
-    __syncwarp();
-    for (int t = sb_hptr[0] + lane; t < sb_hptr[1]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * (bd[sb_hb[t]] * sphi + b[sb_hb[t]] * sphid);
-    __syncwarp();
-    for (int t = sb_hptr[1] + lane; t < sb_hptr[2]; t += SB_WARP) out[sb_hidx[t]] += sb_hcoef[t] * (bd[sb_hb[t]] * spsi + b[sb_hb[t]] * spsid);
     __syncwarp();
 }
 
-// Factor B = x·I − J_local(b) with the generated elimination forest (no fill) + pivoted dense 2-core blocks.
-__device__ __forceinline__ void sb_factor(double x, const double* b, double* d, double* up, double* mm, double* blk, int* bpiv, int lane) {
-    for (int i = lane; i < SB_N; i += SB_WARP) { d[i] = x; up[i] = 0; mm[i] = 0; }
+#define SB_PVERT(S, q, pos) (((S).pv[(q) * SB_PLW + ((pos) >> 2)] >> (8 * ((pos) & 3))) & 255)
+
+// Factor B = x·I − J_local(b) along the generated elimination paths (zero fill, no pivoting: the chains have sign-skew
+// off-diagonals and non-negative damping, so pivots only grow) + explicit pivoted inverse of the dense 2-core blocks.
+// Leaves 1/pivot in di (raw diagonal for dense members), multipliers in mm, entries towards the parent in up, block inverses in blk.
+__device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane) {
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) mm[i] = 0; }
     for (int i = lane; i < SB_BLKSTORE; i += SB_WARP) blk[i] = 0;
     __syncwarp();
-    for (int i = lane; i < SB_N; i += SB_WARP) {
-        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) {
-            double v = -sb_coef[e] * b[sb_bidx[e]];
-            int kind = sb_rkind[e], r = sb_ridx[e];
-            if (kind == 0) d[i] += v;
-            else if (kind == 1) up[i] += v;
-            else if (kind == 2) mm[r] += v;
-            else { int bb = sb_blkid[i]; int nb = sb_bptr[bb + 1] - sb_bptr[bb]; blk[sb_boff[bb] + sb_blkpos[i] * nb + r] += v; }
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) {
+        const int i = r * 32 + lane;
+        double dacc = x, uacc = 0;
+#pragma unroll
+        for (int w = 0; w < SB_WD; w++) {
+            const int e = r * SB_WD + w;
+            const unsigned ix = S.ei[e];
+            const double v = -S.ec[e] * b[(ix >> 8) & 255];
+            const int kind = (ix >> 16) & 15, tgt = ix >> 20;
+            if (kind == 0) dacc += v;
+            else if (kind == 1) uacc += v;
+            else if (S.ec[e] != 0.0) { if (kind == 2) mm[tgt] += v; else blk[tgt] += v; }
         }
+        if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
     __syncwarp();
-    for (int lv = 1; lv < SB_NLEVELS; lv++) {
-        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
-            int v = sb_lvorder[q];
-            double dj = d[v];
-            for (int c = sb_chptr[v]; c < sb_chptr[v + 1]; c++) { int ch = sb_chidx[c]; double m = mm[ch] / d[ch]; mm[ch] = m; dj -= m * up[ch]; }
-            d[v] = dj;
+#pragma unroll
+    for (int ph = 0; ph < SB_NPH; ph++) {
+#pragma unroll
+        for (int rd = 0; rd < SB_PR; rd++) {
+            const int q = ph * SB_PR + rd;
+            const int len = S.ph[q] & 255;
+            if (len > 0) {
+                int prev = SB_PVERT(S, q, 0);
+                double dj = di[prev];
+                if (ph > 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
+                }
+                double dinv = 1.0 / dj;
+                di[prev] = dinv;
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) {
+                    if (pos < len) {
+                        const int v = SB_PVERT(S, q, pos);
+                        const double m = mm[prev] * dinv;
+                        mm[prev] = m;
+                        dj = di[v] - m * up[prev];
+                        dinv = 1.0 / dj;
+                        di[v] = dinv;
+                        prev = v;
+                    }
+                }
+            }
         }
         __syncwarp();
     }
-    for (int bb = lane; bb < SB_NBLOCKS; bb += SB_WARP) { // dense LU with partial pivoting, one lane per block
-        int nb = sb_bptr[bb + 1] - sb_bptr[bb];
-        double* A = blk + sb_boff[bb];
-        int* pv = bpiv + sb_bptr[bb];
-        for (int i = 0; i < nb; i++) A[i * nb + i] = d[sb_bvert[sb_bptr[bb] + i]];
-        for (int kx = 0; kx < nb; kx++) {
-            int p = kx; double mx = fabs(A[kx * nb + kx]);
-            for (int i = kx + 1; i < nb; i++) { double a = fabs(A[i * nb + kx]); if (a > mx) { mx = a; p = i; } }
-            pv[kx] = p;
-            if (p != kx) for (int j = 0; j < nb; j++) { double tt = A[kx * nb + j]; A[kx * nb + j] = A[p * nb + j]; A[p * nb + j] = tt; }
-            double inv = 1.0 / A[kx * nb + kx];
-            for (int i = kx + 1; i < nb; i++) { double l = A[i * nb + kx] * inv; A[i * nb + kx] = l; for (int j = kx + 1; j < nb; j++) A[i * nb + j] -= l * A[kx * nb + j]; }
+    if (SB_NDENSE > 0) {
+        const int bb = lane >> 3, i = lane & 7;
+        if (bb < SB_NDENSE && i < sb_dense_n[bb]) { // gather the children's Schur contributions into the block diagonal
+            const unsigned vv = (i < 4) ? sb_dense_v0[bb] : sb_dense_v1[bb];
+            const int v = (vv >> (8 * (i & 3))) & 255;
+            double dj = di[v];
+#pragma unroll
+            for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
+            di[v] = dj;
         }
+        __syncwarp();
+        // Gauss-Jordan with partial pivoting, one matrix row [A | I] per lane (lane = block*8 + row), rows exchanged by
+        // warp shuffles within the 8-lane group -> explicit inverse (block solves become mat-vecs)
+        {
+            int nb = 0, off = 0; unsigned v0 = 0, v1 = 0;
+            if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; v0 = sb_dense_v0[bb]; v1 = sb_dense_v1[bb]; }
+            double Ar[SB_MAXBLOCK], Ir[SB_MAXBLOCK];
+#pragma unroll
+            for (int j = 0; j < SB_MAXBLOCK; j++) {
+                const int vi = (i < 4) ? ((v0 >> (8 * i)) & 255) : ((v1 >> (8 * (i - 4))) & 255);
+                Ar[j] = (i < nb && j < nb) ? ((i == j) ? di[vi] : blk[off + i * nb + j]) : ((i == j) ? 1.0 : 0.0);
+                Ir[j] = (i == j) ? 1.0 : 0.0;
+            }
+            int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
+            const int base = lane & ~7;
+#pragma unroll
+            for (int kx = 0; kx < SB_MAXBLOCK; kx++) {
+                // pivot search among rows not used yet
+                double best = (myrow < 0 && i < SB_MAXBLOCK) ? fabs(Ar[kx]) : -1.0; int who = i;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
+                if (i == who) myrow = kx;
+                const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
+                const double inv = 1.0 / piv;
+                const double l = (i == who) ? 0.0 : Ar[kx];
+#pragma unroll
+                for (int j = 0; j < SB_MAXBLOCK; j++) {
+                    const double pa = __shfl_sync(SB_FULL, Ar[j], base + who) * inv, pi_ = __shfl_sync(SB_FULL, Ir[j], base + who) * inv;
+                    if (i == who) { Ar[j] = pa; Ir[j] = pi_; } else { Ar[j] -= l * pa; Ir[j] -= l * pi_; }
+                }
+            }
+            if (bb < SB_NDENSE && myrow >= 0 && myrow < nb) {
+#pragma unroll
+                for (int j = 0; j < SB_MAXBLOCK; j++) if (j < nb) blk[off + myrow * nb + j] = Ir[j];
+            }
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
-// r <- B^{-1} r
-__device__ __forceinline__ void sb_bsolve(double* r, const double* d, const double* up, const double* mm, const double* blk, const int* bpiv, int lane) {
-    for (int lv = 1; lv < SB_NLEVELS; lv++) {
-        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
-            int v = sb_lvorder[q];
-            double acc = r[v];
-            for (int c = sb_chptr[v]; c < sb_chptr[v + 1]; c++) { int ch = sb_chidx[c]; acc -= mm[ch] * r[ch]; }
-            r[v] = acc;
+// r <- B^{-1} r : forward along the paths (registers), dense blocks (mat-vec with the explicit inverse), backward along the paths
+__device__ __forceinline__ void sb_bsolve(const SbLane& S, double* r, const double* di, const double* up, const double* mm, const double* blk, int lane) {
+#pragma unroll
+    for (int ph = 0; ph < SB_NPH; ph++) {
+#pragma unroll
+        for (int rd = 0; rd < SB_PR; rd++) {
+            const int q = ph * SB_PR + rd;
+            const int len = S.ph[q] & 255;
+            if (len > 0) {
+                double av[SB_PL];
+                double acc = r[SB_PVERT(S, q, 0)];
+                if (ph > 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * r[ch]; }
+                }
+                av[0] = acc;
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = r[SB_PVERT(S, q, pos)] - mm[SB_PVERT(S, q, pos - 1)] * acc; av[pos] = acc; }
+#pragma unroll
+                for (int pos = (0); pos < SB_PL; pos++) if (pos < len && (pos > 0 || ph > 0)) r[SB_PVERT(S, q, pos)] = av[pos];
+            }
         }
         __syncwarp();
     }
-    for (int bb = lane; bb < SB_NBLOCKS; bb += SB_WARP) {
-        int nb = sb_bptr[bb + 1] - sb_bptr[bb];
-        const double* A = blk + sb_boff[bb];
-        const int* pv = bpiv + sb_bptr[bb];
-        const short* vert = sb_bvert + sb_bptr[bb];
-        double x[SB_MAXBLOCK];
-        for (int i = 0; i < nb; i++) x[i] = r[vert[i]];
-        for (int kx = 0; kx < nb; kx++) { int p = pv[kx]; if (p != kx) { double tt = x[kx]; x[kx] = x[p]; x[p] = tt; } }
-        for (int i = 1; i < nb; i++) for (int j = 0; j < i; j++) x[i] -= A[i * nb + j] * x[j];
-        for (int i = nb - 1; i >= 0; i--) { for (int j = i + 1; j < nb; j++) x[i] -= A[i * nb + j] * x[j]; x[i] /= A[i * nb + i]; }
-        for (int i = 0; i < nb; i++) r[vert[i]] = x[i];
+    if (SB_NDENSE > 0) { // dense blocks: lane = block*8 + row
+        const int bb = lane >> 3, i = lane & 7;
+        int vi = 255, nb = 0, off = 0; unsigned v0 = 0, v1 = 0;
+        if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; v0 = sb_dense_v0[bb]; v1 = sb_dense_v1[bb]; }
+        if (i < nb) {
+            vi = (i < 4) ? ((v0 >> (8 * i)) & 255) : ((v1 >> (8 * (i - 4))) & 255);
+            double acc = r[vi];
+#pragma unroll
+            for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * r[ch]; }
+            r[vi] = acc;
+        }
+        __syncwarp();
+        double xi = 0;
+        if (i < nb) for (int j = 0; j < nb; j++) { const int vj = (j < 4) ? ((v0 >> (8 * j)) & 255) : ((v1 >> (8 * (j - 4))) & 255); xi += blk[off + i * nb + j] * r[vj]; }
+        __syncwarp();
+        if (i < nb) r[vi] = xi;
+        __syncwarp();
     }
-    __syncwarp();
-    for (int lv = SB_NLEVELS - 1; lv >= 0; lv--) {
-        for (int q = sb_lvptr[lv] + lane; q < sb_lvptr[lv + 1]; q += SB_WARP) {
-            int v = sb_lvorder[q], p = sb_parent[v];
-            if (p >= 0) r[v] = (r[v] - up[v] * r[p]) / d[v];
+#pragma unroll
+    for (int ph = SB_NPH - 1; ph >= 0; ph--) {
+#pragma unroll
+        for (int rd = 0; rd < SB_PR; rd++) {
+            const int q = ph * SB_PR + rd;
+            const int len = S.ph[q] & 255, par = (S.ph[q] >> 8) & 255;
+            if (len > 0) {
+                double xs[SB_PL];
+                double xv = (par == 255) ? 0.0 : r[par];
+#pragma unroll
+                for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { const int v = SB_PVERT(S, q, pos); xv = (r[v] - up[v] * xv) * di[v]; xs[pos] = xv; }
+#pragma unroll
+                for (int pos = 0; pos < SB_PL; pos++) if (pos < len) r[SB_PVERT(S, q, pos)] = xs[pos];
+            }
         }
         __syncwarp();
     }
 }
 
-__device__ __forceinline__ void sb_hub_dots(const double* b, const double* r, double& s1, double& s2, int lane) {
+__device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, const double* r, double& s1, double& s2, int lane) {
     double a = 0, c = 0;
-    for (int t = sb_hptr[2] + lane; t < sb_hptr[3]; t += SB_WARP) a += sb_hcoef[t] * b[sb_hb[t]] * r[sb_hidx[t]];
-    for (int t = sb_hptr[3] + lane; t < sb_hptr[4]; t += SB_WARP) c += sb_hcoef[t] * b[sb_hb[t]] * r[sb_hidx[t]];
+#pragma unroll
+    for (int t = 0; t < SB_TPH; t++) a += S.phc[t] * b[(S.phi[t] >> 8) & 255] * r[S.phi[t] & 255];
+#pragma unroll
+    for (int t = 0; t < SB_TPS; t++) c += S.psc[t] * b[(S.psi[t] >> 8) & 255] * r[S.psi[t] & 255];
     s1 = warp_sum(a); s2 = warp_sum(c);
 }
 
-// Persistent kernel: one warp (= one CTA) per k-mode, modes pulled from an atomic work queue in the given order
-// (host sorts by descending k, i.e. descending cost).  FP64 throughout.
-__global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x;
-    double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *d = sm + SB_SM_D, *up = sm + SB_SM_UP,
+// Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
+// queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
+__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel(SbSolveArgs A) {
+    extern __shared__ double sm_all[];
+    const int lane = threadIdx.x & 31;
+    double* sm = sm_all + (threadIdx.x >> 5) * SB_SM_DOUBLES;
+    double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
            *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
-    int* bpiv = (int*)(sm + SB_SM_DOUBLES);
     const double reltol = A.reltol, abstol = A.abstol;
+    SbLane S;
+    S.load(lane);
 
     while (true) {
         int qi = 0;
@@ -468,10 +609,10 @@ __global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
         SbController ctl; ctl.init();
         double dt = 0;
         if (tend > t) {
-            sb_basis_at(A.tb, t, kp, bs, bdv, lane);
+            sb_basis_at(S, A.tb, t, kp, bs, bdv, lane);
             __syncwarp();
-            sb_eval_f(bs, u, f0, lane); nf++;
-            sb_eval_dT(bs, bdv, u, dT, lane);
+            sb_eval_f(S, bs, u, f0, lane); nf++;
+            sb_eval_dT(S, bs, bdv, u, dT, lane);
             { // automatic initial step (Hairer), order 5
                 double d0 = 0, d1 = 0;
                 for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; d0 += (u[i] / sk) * (u[i] / sk); d1 += (f0[i] / sk) * (f0[i] / sk); }
@@ -480,9 +621,9 @@ __global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
                 double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
                 dt0 = fmin(dt0, dtmax);
                 for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
-                sb_basis_at(A.tb, t + dt0, kp, bs + SB_NB, nullptr, lane);
+                sb_basis_at(S, A.tb, t + dt0, kp, bs + SB_NB, nullptr, lane);
                 __syncwarp();
-                sb_eval_f(bs + SB_NB, U, K, lane); nf++;
+                sb_eval_f(S, bs + SB_NB, U, K, lane); nf++;
                 double d2 = 0;
                 for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; double r = (K[i] - f0[i]) / sk; d2 += r * r; }
                 d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
@@ -496,21 +637,23 @@ __global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
                 // basis at the 5 later stage times
-                for (int s = 1; s < 6; s++) sb_basis_at(A.tb, t + ((s == 5) ? 1.0 : cc[s]) * dt, kp, bs + s * SB_NB, nullptr, lane);
+#pragma unroll
+                for (int s = 1; s < 6; s++) sb_basis_at(S, A.tb, t + cc[s] * dt, kp, bs + s * SB_NB, nullptr, lane);
                 __syncwarp();
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
-                sb_factor(1.0 / (SB_R5_GAMMA * dt), bs, d, up, mm, blk, bpiv, lane);
-                for (int i = lane; i < SB_N; i += SB_WARP) { Zp[i] = 0; Zq[i] = 0; }
+                sb_factor(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane);
+#pragma unroll
+                for (int r = 0; r < SB_R; r++) {
+                    const int i = r * 32 + lane;
+                    if (i < SB_N) { Zp[i] = S.pqc[2 * r] * bs[S.pqi[r] & 255]; Zq[i] = S.pqc[2 * r + 1] * bs[(S.pqi[r] >> 8) & 255]; }
+                }
                 __syncwarp();
-                for (int tt = sb_hptr[0] + lane; tt < sb_hptr[1]; tt += SB_WARP) Zp[sb_hidx[tt]] += sb_hcoef[tt] * bs[sb_hb[tt]];
-                for (int tt = sb_hptr[1] + lane; tt < sb_hptr[2]; tt += SB_WARP) Zq[sb_hidx[tt]] += sb_hcoef[tt] * bs[sb_hb[tt]];
-                __syncwarp();
-                sb_bsolve(Zp, d, up, mm, blk, bpiv, lane);
-                sb_bsolve(Zq, d, up, mm, blk, bpiv, lane);
+                sb_bsolve(S, Zp, di, up, mm, blk, lane);
+                sb_bsolve(S, Zq, di, up, mm, blk, lane);
                 nsolve += 2;
                 double m11, m12, m21, m22;
-                sb_hub_dots(bs, Zp, m11, m21, lane);
-                sb_hub_dots(bs, Zq, m12, m22, lane);
+                sb_hub_dots(S, bs, Zp, m11, m21, lane);
+                sb_hub_dots(S, bs, Zq, m12, m22, lane);
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
                 const double idet = 1.0 / (m11 * m22 - m12 * m21);
                 // 8 stages
@@ -521,15 +664,15 @@ __global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
                         if (s <= 5) { for (int i = lane; i < SB_N; i += SB_WARP) { double v = u[i]; for (int j = 0; j < s; j++) v += cA[s][j] * K[j * SB_N + i]; U[i] = v; } }
                         else { for (int i = lane; i < SB_N; i += SB_WARP) U[i] += K[(s - 1) * SB_N + i]; }
                         __syncwarp();
-                        sb_eval_f(bs + cslot[s] * SB_NB, U, ks, lane); nf++;
+                        sb_eval_f(S, bs + cslot[s] * SB_NB, U, ks, lane); nf++;
                         fs = ks;
                     }
                     const double hd_ = dt * cd[s], idt = 1.0 / dt;
                     for (int i = lane; i < SB_N; i += SB_WARP) { double v = fs[i] + hd_ * dT[i]; for (int j = 0; j < s; j++) v += (cC[s][j] * idt) * K[j * SB_N + i]; ks[i] = v; }
                     __syncwarp();
-                    sb_bsolve(ks, d, up, mm, blk, bpiv, lane); nsolve++;
+                    sb_bsolve(S, ks, di, up, mm, blk, lane); nsolve++;
                     double s1, s2;
-                    sb_hub_dots(bs, ks, s1, s2, lane);
+                    sb_hub_dots(S, bs, ks, s1, s2, lane);
                     const double c1 = (m22 * s1 - m12 * s2) * idet, c2 = (-m21 * s1 + m11 * s2) * idet;
                     for (int i = lane; i < SB_N; i += SB_WARP) ks[i] += Zp[i] * c1 + Zq[i] * c2;
                     __syncwarp();
@@ -567,10 +710,10 @@ __global__ void __launch_bounds__(SB_WARP) sb_integrate_kernel(SbSolveArgs A) {
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
                 if (last) break;
                 dt = dtnew;
-                sb_basis_at(A.tb, t, kp, bs, bdv, lane);
+                sb_basis_at(S, A.tb, t, kp, bs, bdv, lane);
                 __syncwarp();
-                sb_eval_f(bs, u, f0, lane); nf++;
-                sb_eval_dT(bs, bdv, u, dT, lane);
+                sb_eval_f(S, bs, u, f0, lane); nf++;
+                sb_eval_dT(S, bs, bdv, u, dT, lane);
             }
         }
         for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = u[i];
@@ -682,11 +825,11 @@ int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, co
         int dev; SB_CUDA_CHECK(cudaGetDevice(&dev));
         SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
         SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
-        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP, SB_SM_BYTES));
+        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
         if (occ < 1) occ = 1;
     }
-    int grid = nctas > 0 ? nctas : std::min(nk, nsm * occ);
-    sb_integrate_kernel<<<grid, SB_WARP, SB_SM_BYTES, st>>>(A);
+    int grid = nctas > 0 ? nctas : std::min((nk + SB_WARPS_PER_CTA - 1) / SB_WARPS_PER_CTA, nsm * occ);
+    sb_integrate_kernel<<<grid, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
 }
