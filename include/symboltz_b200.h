@@ -1,0 +1,107 @@
+/* symboltz_b200.h -- C ABI of the B200-native SymBoltz hot path.
+ *
+ * Two shared libraries export these symbols:
+ *   libsbm_<model>.so  (one per model structure lmax/nx/w0wa; built at problem-build time by symboltz.jl_b200/build.py,
+ *                       sources: symboltz.jl_b200/csrc/sb_engine.cu + sb_debug.cpp + generated sb_model_gen.h)   -> sbm_*
+ *   libsbl.so          (model independent; symboltz.jl_b200/csrc/sb_los.cu)                                       -> sbl_*
+ *
+ * Conventions: plain pointers and sizes only; doubles are IEEE binary64; τ in 1/H0, k in H0/c (reference
+ * docs/src/conventions.md:14-18).  Pointers named d* are DEVICE pointers (cudaMalloc / torch / CUDA.jl memory), all others
+ * are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points are
+ * asynchronous on that stream.  Return value: 0 (or a non-negative count where stated) on success, negative on error
+ * (-1000 - cudaError for CUDA failures).  There is no CPU fallback: without a GPU every device entry point fails.
+ *
+ * Each entry point names the reference interface it replaces (file:line relative to hersle/SymBoltz.jl v1.6.0).
+ */
+#ifndef SYMBOLTZ_B200_H
+#define SYMBOLTZ_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ model library (libsbm_<model>.so) */
+
+/* Model constants.  out[16] = N, NPAR, NBETA, NB, LMAX, NX, W0WA, NNZ(W), FLOPS_F, FLOPS_LU, FLOPS_SOLVE, NLEVELS,
+ * NBLOCKS, index of kappa0 in P, index of tau0 in P, NSLOT.   (replaces: `length(unknowns(prob.pt.f.sys))`,
+ * sparsity summary of Base.show(::CosmologyProblem), src/solve.jl:40-60) */
+int sbm_info(int* out);
+const char* sbm_key(void);
+
+/* Parameter vector P[NPAR] (all entry points): h, Omega_c, Omega_b, Omega_g, Omega_nu, C_h = 3/(8π) Omega_h/Iρ0, Omega_L,
+ * T0, YHe, fHe, y0, w0, wa, cs2X, kappa0, tau0, then x_i[NX], W_i[NX], dlnf0_i[NX] (momentum quadrature,
+ * src/models/neutrinos.jl:55-60,73).  kappa0 and tau0 are filled from sbm_solvebg's info (callback of src/solve.jl:183-189). */
+
+/* Background + thermodynamics solve on the host (replaces solvebg, src/solve.jl:427-435, with the "today" callback of
+ * src/solve.jl:158-202 and the spline construction of src/utils.jl:118-127).  Writes the nb Hermite-spline knots
+ * t[nb], y[nb][5] = (a, _κ, XH+, XHe+, ΔT), dy[nb][5]; info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
+ * Returns nb, or -1 if cap is too small. */
+int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info);
+
+/* Build the β-table (Jacobian basis functions on the knot-aligned grid) on the device from the uploaded knots.
+ * dtab must hold ((nb-1)*msub + 1) * 2 * NBETA doubles.  (replaces the in-RHS spline evaluation `splvalue`,
+ * src/utils.jl:135-140, 203-209) */
+int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, double* dtab, void* stream);
+
+/* Perturbation solve over nk independent k-modes (replaces solvept(ptprob, bgsol, ks, ptivini; reltol, abstol, saveat, ...),
+ * src/solve.jl:543-569, i.e. Rodas5P + KLU per mode, src/solve.jl:327-341).
+ *   dlut[nlut]: interval look-up (knot interval containing exp(s0 + q*dsl));  dks[nk], dtini[nk] (already clamped to the
+ *   background span, src/solve.jl:527); dorder[nk]: processing order (NULL = natural; pass descending k);
+ *   dsaveat[nsave] ascending (dense output); dusave[nk][nsave][N] or NULL; duend[nk][N]; dretcode[nk]
+ *   (0 Success, 1 MaxIters, 2 DtLessThanMin, 3 Unstable -- SciML retcodes, src/solve.jl:407-419);
+ *   dstats[nk][4] = naccept, nreject, nf, nsolve; dqueue: one int of scratch; nctas <= 0: fill the GPU;
+ *   dtrace/ntrace: optional (t, dt, EEst) trace of mode 0 (NULL/0 to disable).
+ * Returns the launched grid size (>= 0) or a negative error. */
+int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas,
+                void* stream, double* dtrace, int ntrace);
+
+/* Total-matter gauge-invariant overdensity Δm(τ, k_i) from states du[nk][N] (replaces the observed-function evaluation
+ * inside spectrum_matter(sol, k), src/observables/fourier.jl:39-52, 90-97). */
+int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, double tau, int nk, const double* dks, const double* du, double* dout, void* stream);
+
+/* CMB source functions at every saved (k, τ) (replaces getsym(prob.pt, Ss) in source_grid's output_func,
+ * src/observables/fourier.jl:267-281, with ST and SE of src/models/cosmologies.jl:99-104).
+ * dsrcbg: scratch of nt * sbm_srcbg_stride() doubles.  dS[nk][2][nt]; scale_k != 0 returns (k·ST, k²·SE) as fed to the
+ * line-of-sight integrator (src/observables/angular.jl:293). */
+int sbm_srcbg_stride(void);
+int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, int nk,
+                const double* dks, const double* dusave, double* dS, int scale_k, void* stream);
+int sbm_smem_bytes(void);
+
+/* Host-side diagnostics of the generated code (unit tests of the generator; not a solve path). */
+int sbm_debug_fjt(const double* P, const double* y, const double* yp, double tau, double k, const double* u, double* f, double* J, double* dT);
+int sbm_debug_split(const double* P, const double* y, const double* yp, double tau, double k, double* Jloc, double* hubs);
+int sbm_debug_initial(const double* P, const double* y, double tau, double k, double* u);
+int sbm_debug_bg(const double* P, const double* y, double* g, double* J, double* kder, double* obs);
+int sbm_debug_delta_m(const double* P, const double* y, double tau, double k, const double* u, double* out);
+int sbm_debug_spline(int nb, const double* t, const double* y, const double* dy, double tau, double* yo, double* ypo);
+int sbm_debug_beta(const double* P, const double* y, const double* yp, double tau, double* beta, double* betad);
+
+/* ------------------------------------------------------------------ line-of-sight library (libsbl.so) */
+
+/* j_l(x), j_l'(x) table on x = ix*step, ix < nxp, for sorted integer dls[nl]; output dy_[nxp][nl], ddy_[nxp][nl]
+ * (l contiguous, = the reference's y[il, ix]).  (replaces SphericalBesselCache, src/observables/angular.jl:18-26, 59-60) */
+int sbl_bessel_table(int nl, const int* dls, int nxp, double step, double* dy_, double* ddy_, void* stream);
+
+/* Θ_l(k) for fine-k indices [k0, k0+nk) of dks[nk_total]: optional barycentric interpolation from nc coarse nodes
+ * (dBw[nk_total][nc], NULL = sources already on the fine grid), trapezoid weights dwt[nt], χ = dchi[nt], Hermite j_l table,
+ * Θ_T/k and Θ_E √((l+2)!/(l−2)!)/k² rescaling.  dSc[nc or nk_total][2][nt]; dTheta[2][nl][nk_total].
+ * (replaces source_kinterp, src/observables/fourier.jl:232-247; los_integrate, src/observables/angular.jl:109-152;
+ * the rescaling of src/observables/angular.jl:301-306) */
+int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nt, const double* dchi, const double* dwt, int nl,
+            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, void* stream);
+
+/* C_l^{AB} = Σ_{k in [k0,k1)} c_k Θ^A_l(k) Θ^B_l(k), c_k = w_k (2/π) k² P0(k) with w_k the natural-cubic-spline integration
+ * weights through (0,0) + ks (host-computed).  dCl[nmodes][nl].
+ * (replaces spectrum_cmb(ΘlAs, ΘlBs, P0s, ls, ks), src/observables/angular.jl:198-223) */
+int sbl_cl(int nl, int nk, int k0, int k1, const double* dck, const double* dTheta, int nmodes, const int* dmodeA, const int* dmodeB, double* dCl, void* stream);
+
+/* Standalone barycentric k-interpolation dSf[nk][n2t] = Σ_j dBw[k][j] dSc[j][n2t] (replaces source_kinterp,
+ * src/observables/fourier.jl:232-247) */
+int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, double* dSf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

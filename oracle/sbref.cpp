@@ -660,6 +660,7 @@ static int solve_mode(const Derived& D, const Spline& spl, double k, double tini
             if (t + dt >= tend - 100 * 2.2e-16 * std::fabs(tend)) { dt = tend - t; last = true; }
             if (!R.step(t, u.data(), dt)) { rc = RC_UNSTABLE; break; }
             double EEst = R.errnorm(u.data(), abstol, reltol);
+            if (getenv("SBO_TRACE")) fprintf(stderr, "TRACE %ld %.17g %.17g %.17g\n", it, t, dt, EEst);
             if (!std::isfinite(EEst)) { R.st.nreject++; dt /= 5; if (dt < 1e-15 * std::fabs(t)) { rc = RC_UNSTABLE; break; } continue; }
             double q = ctl.q_of(EEst);
             if (EEst > 1) { R.st.nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * std::fabs(t)) { rc = RC_DTMIN; break; } continue; }

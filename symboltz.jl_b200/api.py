@@ -230,17 +230,22 @@ class BackgroundSolution:
     def success(self):
         return self.retcode == 0
 
-    def device(self, ntable=16384):
-        """Upload spline knots and parameters, build the β-table on the GPU (once)."""
-        if self._dev is None or self._dev["nT"] != ntable:
+    def device(self, msub=16):
+        """Upload spline knots and parameters, build the β-table on the GPU (once).
+        msub: sub-intervals per background knot interval (see sb_table_kernel)."""
+        if self._dev is None or self._dev["msub"] != msub:
             _require_cuda()
             dev = torch.device("cuda")
             d = dict(P=torch.from_numpy(self.P).to(dev), t=torch.from_numpy(self.t).to(dev), y=torch.from_numpy(self.y).to(dev), dy=torch.from_numpy(self.dy).to(dev))
+            nb = len(self.t)
+            nnode = (nb - 1) * msub + 1
+            d["tab"] = torch.empty((nnode, 2, self.prob.NBETA), dtype=torch.float64, device=dev)
+            nlut = 4096
             s0 = math.log(self.t[0])
-            ds = (math.log(self.t[-1]) - s0) / (ntable - 1)
-            d["tab"] = torch.empty((ntable, 2, self.prob.NBETA), dtype=torch.float64, device=dev)
-            d.update(nT=ntable, s0=s0, ds=ds)
-            rc = self.prob.lib.sbm_build_table(_cptr(d["P"]), C.c_int(len(self.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(ntable), C.c_double(s0), C.c_double(ds), _cptr(d["tab"]), _stream())
+            dsl = (math.log(self.t[-1]) - s0) / nlut
+            lut = np.clip(np.searchsorted(self.t, np.exp(s0 + dsl * np.arange(nlut)), side="right") - 1, 0, nb - 2).astype(np.int32)
+            d.update(msub=msub, nlut=nlut, s0=s0, dsl=dsl, lut=torch.from_numpy(lut).to(dev))
+            rc = self.prob.lib.sbm_build_table(_cptr(d["P"]), C.c_int(nb), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(msub), _cptr(d["tab"]), _stream())
             if rc != 0:
                 raise RuntimeError(f"sbm_build_table failed with code {rc}")
             self._dev = d
@@ -295,7 +300,7 @@ class PerturbationSolution:
         return bool((self.retcode == 0).all())
 
 
-def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, ntable=16384, nctas=0, warn=True, sync=True):
+def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0):
     """Perturbation solve over independent k-modes on the GPU (reference solvept, src/solve.jl:543-569).
     ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527)."""
     _require_cuda()
@@ -305,7 +310,7 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     with np.errstate(divide="ignore", invalid="ignore"):
         tini = np.array([min(max(f(k), bgsol.t[0]), bgsol.t[-1]) if k == k else bgsol.t[0] for k in ks], dtype=np.float64)
     order = np.argsort(-np.nan_to_num(ks, nan=0.0), kind="stable").astype(np.int32)  # most expensive (largest k) first
-    d = bgsol.device(ntable)
+    d = bgsol.device(msub)
     dev = d["P"].device
     host = torch.from_numpy(np.concatenate([ks, tini])).pin_memory()
     dkt = host.to(dev, non_blocking=True)
@@ -323,13 +328,15 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         ns = len(saveat)
     else:
         dsave, usave, ns = None, None, 0
-    rc = prob.lib.sbm_solvept(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["nT"]), C.c_double(d["s0"]), C.c_double(d["ds"]), _cptr(d["tab"]),
+    dtrace = torch.zeros((trace, 3), dtype=torch.float64, device=dev) if trace else None  # debug: (t, dt, EEst) of mode 0
+    rc = prob.lib.sbm_solvept(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
                               C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
-                              _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), C.c_int(nctas), _stream())
+                              _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), C.c_int(nctas), _stream(), _cptr(dtrace), C.c_int(trace))
     if rc < 0:
         raise RuntimeError(f"sbm_solvept failed with code {rc}")
     sol = PerturbationSolution(prob, bgsol, ks, tini, saveat, uend, usave, retcode, stats, dks)
     sol.grid = rc
+    sol.trace = dtrace.cpu().numpy() if trace else None
     if sync and warn:
         for i in np.nonzero(sol.retcode != 0)[0]:  # warn, don't throw (src/solve.jl:557-560)
             warnings.warn(f"Perturbation (mode k = {ks[i]}) solution failed with return code {RETCODES.get(int(sol.retcode[i]))}.\nCheck the parameters and precision settings!")
@@ -680,3 +687,137 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
     if return_all:
         return out, dict(ks_fine=ks_fine, taus=taus, S=S, theta=theta, bg=bg)
     return out
+
+
+class CMBPlan:
+    """Preallocated, allocation-free execution plan for the C_l hot path of one cosmology:
+    (H2D knots) -> β-table -> perturbation solve (saveat) -> sources -> [k-interp +] LOS -> C_l -> (D2H C_l).
+    Used by bench.py for the device-resident number (`run`) and the end-to-end number (`run_e2e`), and handy for sweeps:
+    every launch goes to torch's current stream, so a sequence of plans can be captured in a CUDA graph."""
+
+    def __init__(self, prob, bg, jl, modes=("TT", "EE", "TE"), direct=True, kinterp=None, dkt0=math.pi, ntau=300, taucut=1e-2,
+                 reltol=1e-5, abstol=1e-5, maxiters=100000, msub=16, normalization="Cl"):
+        _require_cuda()
+        self.prob, self.jl, self.modes, self.direct = prob, jl, list(modes), direct
+        self.reltol, self.abstol, self.maxiters, self.msub, self.normalization = reltol, abstol, maxiters, msub, normalization
+        self.kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
+        dev = torch.device("cuda")
+        self.dev = dev
+        self.ks_fine, self.taus = cmb_grids(bg, self.kinterp.minimum(), self.kinterp.maximum(), dkt0, ntau, taucut)
+        self.ks_solve = self.ks_fine if direct else self.kinterp.xs
+        nk, nkf, nt, N, nl = len(self.ks_solve), len(self.ks_fine), len(self.taus), prob.N, len(jl.l)
+        self.nk, self.nkf, self.nt, self.nl = nk, nkf, nt, nl
+        self.nb = len(bg.t)
+        # pinned host staging for the per-cosmology inputs: knots (t, y, dy) and parameters
+        self.h_in = torch.empty(self.nb * 11 + prob.npar, dtype=torch.float64).pin_memory()
+        self.d_in = torch.empty_like(self.h_in, device=dev)
+        self.stage(bg)
+        tini = np.full(nk, bg.t[0])
+        order = np.argsort(-self.ks_solve, kind="stable").astype(np.int32)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.d_ks, self.d_tini, self.d_order = torch.from_numpy(self.ks_solve.copy()).to(dev), torch.from_numpy(tini).to(dev), torch.from_numpy(order).to(dev)
+        self.d_ksf = torch.from_numpy(self.ks_fine).to(dev)
+        self.d_taus = torch.from_numpy(self.taus).to(dev)
+        self.d_chi = torch.from_numpy(self.taus[-1] - self.taus).to(dev)
+        self.d_wt = torch.from_numpy(_trapz_weights(self.taus)).to(dev)
+        self.d_usave = torch.empty((nk, nt, N), **f64)
+        self.d_uend = torch.empty((nk, N), **f64)
+        self.d_ret = torch.empty(nk, dtype=torch.int32, device=dev)
+        self.d_stats = torch.empty((nk, 4), dtype=torch.int64, device=dev)
+        self.d_queue = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.d_S = torch.empty((nk, 2, nt), **f64)
+        self.d_srcbg = torch.empty(nt * prob.lib.sbm_srcbg_stride(), **f64)
+        self.d_theta = torch.zeros((2, nl, nkf), **f64)
+        self.d_Bw = None if direct else torch.from_numpy(self.kinterp.matrix(self.ks_fine)).to(dev)
+        w = natural_spline_weights(np.concatenate([[0.0], self.ks_fine]))[1:]
+        self.d_ck = torch.from_numpy(w * (2 / math.pi) * self.ks_fine**2 * spectrum_primordial(self.ks_fine, prob)).to(dev)
+        self.d_mA = torch.tensor([_MODE_IDX[m[0]] for m in self.modes], dtype=torch.int32, device=dev)
+        self.d_mB = torch.tensor([_MODE_IDX[m[1]] for m in self.modes], dtype=torch.int32, device=dev)
+        self.d_Cl = torch.empty((len(self.modes), nl), **f64)
+        self.h_Cl = torch.empty((len(self.modes), nl), dtype=torch.float64).pin_memory()
+        nnode = (self.nb - 1) * msub + 1
+        self.d_tab = torch.empty((nnode, 2, prob.NBETA), **f64)
+        self.nlut = 4096
+        self.h_lut = torch.empty(self.nlut, dtype=torch.int32).pin_memory()
+        self.d_lut = torch.empty(self.nlut, dtype=torch.int32, device=dev)
+        self._lut(bg)
+        self.h2d_bytes = self.h_in.numel() * 8 + self.h_lut.numel() * 4
+        self.d2h_bytes = self.h_Cl.numel() * 8
+        self.launches_resident, self.launches_e2e = 5, 6
+
+    def stage(self, bg):
+        """Copy a background solution (same number of knots) into the pinned staging buffer."""
+        if len(bg.t) != self.nb:
+            raise ValueError("plan was built for a different number of background knots")
+        nb = self.nb
+        h = self.h_in.numpy()
+        h[:nb] = bg.t
+        h[nb:6 * nb] = bg.y.ravel()
+        h[6 * nb:11 * nb] = bg.dy.ravel()
+        h[11 * nb:] = bg.P
+        self.tau0, self.s0, self.dsl = bg.tau0, math.log(bg.t[0]), (math.log(bg.t[-1]) - math.log(bg.t[0])) / 4096
+        self._bg = bg
+
+    def _lut(self, bg):
+        lut = np.clip(np.searchsorted(bg.t, np.exp(self.s0 + self.dsl * np.arange(self.nlut)), side="right") - 1, 0, self.nb - 2).astype(np.int32)
+        self.h_lut.numpy()[:] = lut
+
+    def _views(self):
+        nb = self.nb
+        d = self.d_in
+        return d[11 * nb:], d[:nb], d[nb:6 * nb], d[6 * nb:11 * nb]
+
+    def upload(self):
+        """H2D of the staged inputs + β-table build."""
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self.d_lut.copy_(self.h_lut, non_blocking=True)
+        P, t, y, dy = self._views()
+        rc = self.prob.lib.sbm_build_table(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), _cptr(self.d_tab), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbm_build_table failed with code {rc}")
+
+    def solve(self):
+        P, t, y, dy = self._views()
+        lib = self.prob.lib
+        rc = lib.sbm_solvept(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
+                             C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), _cptr(self.d_order), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
+                             C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), C.c_int(0), _stream(), None, C.c_int(0))
+        if rc < 0:
+            raise RuntimeError(f"sbm_solvept failed with code {rc}")
+
+    def sources(self):
+        P, t, y, dy = self._views()
+        rc = self.prob.lib.sbm_sources(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.nt), _cptr(self.d_taus), _cptr(self.d_srcbg), C.c_int(self.nk), _cptr(self.d_ks),
+                                       _cptr(self.d_usave), _cptr(self.d_S), C.c_int(1), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbm_sources failed with code {rc}")
+
+    def los_cl(self):
+        jl, L = self.jl, los_lib()
+        rc = L.sbl_los(C.c_int(self.nkf), C.c_int(0), C.c_int(self.nkf), _cptr(self.d_ksf), C.c_int(self.nk), _cptr(self.d_Bw), _cptr(self.d_S), C.c_int(self.nt), _cptr(self.d_chi), _cptr(self.d_wt),
+                       C.c_int(self.nl), _cptr(jl.d_l), _cptr(jl.y), _cptr(jl.dy), C.c_double(jl.invdx), C.c_double(jl.dx), C.c_int(jl.nx), _cptr(self.d_theta), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbl_los failed with code {rc}")
+        rc = L.sbl_cl(C.c_int(self.nl), C.c_int(self.nkf), C.c_int(0), C.c_int(self.nkf), _cptr(self.d_ck), _cptr(self.d_theta), C.c_int(len(self.modes)), _cptr(self.d_mA), _cptr(self.d_mB), _cptr(self.d_Cl), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbl_cl failed with code {rc}")
+
+    def run(self):
+        """Device-resident pass: solve -> sources -> LOS -> C_l (inputs and β-table already in HBM)."""
+        self.solve()
+        self.sources()
+        self.los_cl()
+
+    def download(self):
+        self.h_Cl.copy_(self.d_Cl, non_blocking=False)
+        out = self.h_Cl.numpy().T.copy()
+        if self.normalization == "Dl":
+            ls = np.asarray(self.jl.l, dtype=np.float64)
+            out = out * (ls * (ls + 1) / (2 * math.pi))[:, None]
+        return out
+
+    def run_e2e(self):
+        """End-to-end pass from host buffers: H2D (pinned) -> table -> solve -> sources -> LOS -> C_l -> D2H."""
+        self.upload()
+        self.run()
+        return self.download()

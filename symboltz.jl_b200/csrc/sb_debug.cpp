@@ -44,6 +44,17 @@ int sbm_debug_fjt(const double* P, const double* y, const double* yp, double tau
     }
     return 0;
 }
+// dense J_local and the hub vectors p, q, phi, psi (each N) at (τ,k): for conditioning studies of the Woodbury split
+int sbm_debug_split(const double* P, const double* y, const double* yp, double tau, double k, double* Jloc, double* hubs) {
+    double beta[SB_NBETA], betad[SB_NBETA], b[SB_NB];
+    sb_beta(tau, y, yp, P, beta, betad);
+    for (int m = 0; m < SB_NB; m++) b[m] = pow(k, (double)sb_basis_kpow[m]) * beta[sb_basis_beta[m]];
+    for (int i = 0; i < SB_N * SB_N; i++) Jloc[i] = 0;
+    for (int i = 0; i < SB_N; i++) for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) Jloc[i * SB_N + sb_col[e]] += sb_coef[e] * b[sb_bidx[e]];
+    for (int i = 0; i < 4 * SB_N; i++) hubs[i] = 0;
+    for (int v = 0; v < 4; v++) for (int t = sb_hptr[v]; t < sb_hptr[v + 1]; t++) hubs[v * SB_N + sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]];
+    return 0;
+}
 int sbm_debug_initial(const double* P, const double* y, double tau, double k, double* u) { sb_initial(tau, k, y, P, u); return 0; }
 int sbm_debug_bg(const double* P, const double* y, double* g, double* J, double* kder, double* obs) {
     double g2[5];

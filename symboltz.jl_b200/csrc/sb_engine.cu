@@ -230,24 +230,38 @@ int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double
 } // extern "C"
 
 // ================================================================================================ DEVICE
-// β-table: node j at s_j = s0 + j·ds (s = ln τ): tab[j][0][m] = β_m(τ_j), tab[j][1][m] = ds·dβ_m/ds = ds·τ_j·dβ_m/dτ.
-// Cubic Hermite in s between nodes.  The table replaces per-stage re-evaluation of the thermodynamics
-// (exp/tanh/pow chains) inside the integrator; its interpolation error is measured by tests (≤ 1e-9 relative).
-__global__ void sb_table_kernel(const double* __restrict__ P, SbSpline spl, int nT, double s0, double ds, double* __restrict__ tab) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nT) return;
-    double tau = exp(s0 + j * ds);
+// β-table.  The background spline is piecewise cubic on the solver's knots, so β_m(y(τ)) is smooth only *between* knots:
+// every knot interval [t_j, t_{j+1}] is subdivided uniformly into msub sub-intervals; node n = j·msub + s sits at
+// τ = t_j + s·(t_{j+1} − t_j)/msub and stores β_m and dβ_m/dτ (exact, chain rule through the spline derivative).
+// Cubic Hermite in τ between nodes.  The table replaces per-stage re-evaluation of the thermodynamics (exp/tanh/pow chains)
+// inside the integrator; its interpolation error (≈1e-12 relative, tests/test_gpu_parity.py) is far below the solver tolerance.
+__global__ void sb_table_kernel(const double* __restrict__ P, SbSpline spl, int msub, double* __restrict__ tab) {
+    const int nnode = (spl.nb - 1) * msub + 1;
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nnode) return;
+    int j = n / msub, sidx = n % msub;
+    if (j > spl.nb - 2) { j = spl.nb - 2; sidx = msub; }
+    const double h = spl.t[j + 1] - spl.t[j];
+    const double tau = (sidx == msub) ? spl.t[j + 1] : spl.t[j] + sidx * (h / msub);
     double y[5], yp[5], beta[SB_NBETA], betad[SB_NBETA];
-    sb_spl_eval(spl, tau, y, yp);
+    const double d0 = tau - spl.t[j], d1 = tau - spl.t[j + 1];
+    for (int q = 0; q < 5; q++) {
+        double u0 = spl.y[5 * j + q], u1 = spl.y[5 * j + 5 + q], v0 = spl.dy[5 * j + q], v1 = spl.dy[5 * j + 5 + q];
+        double c1 = (u1 - u0 - v0 * h) / (h * h), c2 = (v1 - v0 - 2 * c1 * h) / (h * h);
+        y[q] = u0 + d0 * v0 + d0 * d0 * (c1 + d1 * c2);
+        yp[q] = v0 + 2 * d0 * (c1 + d1 * c2) + d0 * d0 * c2;
+    }
     sb_beta(tau, y, yp, P, beta, betad);
-    double* o = tab + (size_t)j * 2 * SB_NBETA;
-    for (int m = 0; m < SB_NBETA; m++) { o[m] = beta[m]; o[SB_NBETA + m] = ds * tau * betad[m]; }
+    double* o = tab + (size_t)n * 2 * SB_NBETA;
+    for (int m = 0; m < SB_NBETA; m++) { o[m] = beta[m]; o[SB_NBETA + m] = betad[m]; }
 }
 
 struct SbTable {
-    int nT;
-    double s0, ds, inv_ds;
-    const double* tab;
+    int nb, msub, nlut;      // knots, sub-intervals per knot interval, size of the interval look-up table
+    double s0, inv_dsl;      // lut[q] = knot interval containing exp(s0 + q/inv_dsl)
+    const double* t;         // knots
+    const int* lut;
+    const double* tab;       // [(nb-1)·msub + 1][2][NBETA]
 };
 
 struct SbSolveArgs {
@@ -266,6 +280,8 @@ struct SbSolveArgs {
     int* retcode;
     long long* stats; // [nk][4] = naccept, nreject, nf, nsolve
     int* queue;
+    double* trace;    // optional debug trace of mode 0: (t, dt, EEst) per attempted step
+    int ntrace;
 };
 
 // shared-memory layout per warp (doubles)
@@ -328,13 +344,17 @@ struct SbLane {
 
 // basis functions b_m = k^e β_m(τ) (and optionally ḃ_m) from the β-table; lanes over m
 __device__ __forceinline__ void sb_basis_at(const SbLane& S, const SbTable& tb, double tau, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
-    double s = log(tau);
-    double fi = (s - tb.s0) * tb.inv_ds;
-    int i = (int)floor(fi);
-    i = max(0, min(i, tb.nT - 2));
-    double w = fi - i, w1 = w - 1.0;
-    double h00 = (1 + 2 * w) * w1 * w1, h10 = w * w1 * w1, h01 = w * w * (3 - 2 * w), h11 = w * w * w1;
-    const double* n0 = tb.tab + (size_t)i * 2 * SB_NBETA;
+    int q = (int)((log(tau) - tb.s0) * tb.inv_dsl);
+    q = max(0, min(q, tb.nlut - 1));
+    int j = __ldg(tb.lut + q);
+    while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
+    const double tj = __ldg(tb.t + j), hj = __ldg(tb.t + j + 1) - tj;
+    const double hs = hj / tb.msub;
+    double f = (tau - tj) / hs;
+    int sidx = max(0, min((int)f, tb.msub - 1));
+    const double w = f - sidx, w1 = w - 1.0;
+    const double h00 = (1 + 2 * w) * w1 * w1, h10 = w * w1 * w1 * hs, h01 = w * w * (3 - 2 * w), h11 = w * w * w1 * hs;
+    const double* n0 = tb.tab + ((size_t)j * tb.msub + sidx) * 2 * SB_NBETA;
     const double* n1 = n0 + 2 * SB_NBETA;
 #pragma unroll
     for (int r = 0; r < SB_NBR; r++) {
@@ -344,10 +364,7 @@ __device__ __forceinline__ void sb_basis_at(const SbLane& S, const SbTable& tb, 
             double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n1 + be), d1 = __ldg(n1 + SB_NBETA + be);
             double kk = kp[(S.bp[r] >> 8) & 255];
             b[m] = kk * (h00 * v0 + h10 * d0 + h01 * v1 + h11 * d1);
-            if (bd) {
-                double g00 = 6 * w * w1, g10 = (3 * w - 1) * w1, g11 = w * (3 * w - 2); // d/dw of the Hermite basis (g01 = -g00)
-                bd[m] = kk * (g00 * (v0 - v1) + g10 * d0 + g11 * d1) * tb.inv_ds / tau; // dβ/dτ = (dβ/dw)/(ds·τ)
-            }
+            if (bd) bd[m] = kk * (6 * w * w1 * (v0 - v1) / hs + (3 * w - 1) * w1 * d0 + w * (3 * w - 2) * d1); // derivative of the Hermite cubic
         }
     }
 }
@@ -681,6 +698,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 double es = 0; bool bad = false;
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
                 double EEst = sqrt(warp_sum(es) / SB_N);
+                if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
                 double q = ctl.q_of(EEst);
                 if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
@@ -801,24 +819,26 @@ extern "C" {
 int sbm_smem_bytes(void) { return SB_SM_BYTES; }
 int sbm_srcbg_stride(void) { return SB_SRCBG_STRIDE; }
 
-int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nT, double s0, double ds, double* dtab, void* stream) {
+// dtab: ((nb-1)·msub + 1)·2·NBETA doubles
+int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, double* dtab, void* stream) {
     SbSpline spl{nb, dt, dy, ddy};
-    sb_table_kernel<<<(nT + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dP, spl, nT, s0, ds, dtab);
+    int nnode = (nb - 1) * msub + 1;
+    sb_table_kernel<<<(nnode + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dP, spl, msub, dtab);
     SB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 // Perturbation solve over nk modes (reference solvept, src/solve.jl:543-569).  All array arguments are DEVICE pointers.
 // dorder may be NULL (natural order).  dqueue: one int, zeroed by this call.  nctas <= 0: fill the GPU.
-int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nT, double s0, double ds, const double* dtab, int nk,
+int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
                 const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
-                int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream) {
+                int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace) {
     if (nk <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SbSolveArgs A;
-    A.P = dP; A.spl = SbSpline{nb, dt, dy, ddy}; A.tb = SbTable{nT, s0, ds, 1.0 / ds, dtab};
+    A.P = dP; A.spl = SbSpline{nb, dt, dy, ddy}; A.tb = SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab};
     A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.tend = tend; A.nsave = dusave ? nsave : 0; A.saveat = dsaveat;
-    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
+    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue; A.trace = dtrace; A.ntrace = ntrace;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
     static int occ = 0, nsm = 0;
     if (!occ) {
