@@ -1,0 +1,202 @@
+"""CPU tests of the product's host side: code generator vs the independent oracle, host background solver, grids,
+interpolators, C-ABI loading.  No GPU compute is called here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_abi_exports_every_declared_symbol(sb, prob5):
+    """Every function declared in include/symboltz_b200.h is exported by the built libraries."""
+    hdr = open(os.path.join(ROOT, "include", "symboltz_b200.h")).read()
+    names = re.findall(r"\b(sb[ml]_\w+)\s*\(", hdr)
+    assert len(names) > 15
+    los = C.CDLL(sb.build.build_los())
+    for n in set(names):
+        lib = prob5.lib if n.startswith("sbm_") else los
+        assert hasattr(lib, n), f"{n} not exported"
+    inf = (C.c_int * 16)()
+    prob5.lib.sbm_info(inf)
+    assert inf[0] == 47 and inf[4] == 5 and inf[5] == 4  # N = 5 + (lmax+1)(3+nx), reference test fixture lmax = 5
+
+
+def test_model_sizes_match_reference_counts(sb):
+    """N = 5 + (lmax+1)(3+nx); nnz(W) = 409 at lmax = 10, 124 unknowns at lmax = 16 (talk notebook)."""
+    p10 = sb.CosmologyProblem(sb.ΛCDM(lmax=10), sb.parameters_Planck18(sb.ΛCDM()))
+    assert p10.N == 82 and p10.info["nnz_full"] == 409
+    pw = sb.CosmologyProblem(sb.w0waCDM(lmax=10), sb.parameters_Planck18(sb.w0waCDM()))
+    assert pw.N == 84
+
+
+def test_gpu_path_fails_loudly_without_gpu(sb, prob5, bg5):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="GPU-only"):
+        sb.solvept(prob5, bg5, [1.0])
+    with pytest.raises(RuntimeError, match="GPU-only"):
+        sb.SphericalBesselCache(np.array([2, 3]))
+
+
+def test_derived_parameters_match_oracle(prob5, obg5):
+    for k in ("Omega_g", "Omega_nu", "Omega_h", "Omega_L", "fHe", "y0", "Irho0", "kpivot", "As"):
+        assert np.isclose(prob5.derived[k], obg5.derived[k], rtol=1e-12), k
+
+
+def test_momentum_quadrature(sb, oracle):
+    from scipy.special import factorial, zeta
+    for n in (4, 8, 16):
+        xs, Ws = sb.momentum_quadrature(n)
+        xo, Wo = oracle.momentum_quadrature(n)
+        assert np.allclose(xs, xo, rtol=1e-9) and np.allclose(Ws, Wo, rtol=1e-8)
+    xs, Ws = sb.momentum_quadrature(4)
+    for m in range(2, 7):
+        assert abs(np.sum(Ws * xs ** (m - 2)) / (factorial(m) * (1 - 1 / 2**m) * zeta(m + 1)) - 1) < 10.0 ** (-6 + m - 1)
+
+
+def test_generated_bg_rhs_and_jacobian_match_oracle(prob5, obg5, oracle):
+    """sympy program (forward-mode on the statement list) vs hand-written C++ with complex-step Jacobian."""
+    for i in (50, 300, 500, 700, 900):
+        y = obg5.y[i].copy()
+        g, J, kd, obs = np.zeros(5), np.zeros((5, 5)), np.zeros(3), np.zeros(6)
+        prob5.lib.sbm_debug_bg(_ptr(prob5.P), _ptr(y), _ptr(g), _ptr(J), _ptr(kd), _ptr(obs))
+        g2, J2 = np.zeros(5), np.zeros((5, 5))
+        oracle.lib().sbo_bg_rhs(C.byref(obg5.p), _ptr(y), _ptr(g2), _ptr(J2))
+        assert np.allclose(g[:4], g2[:4], rtol=1e-10, atol=1e-300)
+        assert np.isclose(g[4], g2[4], rtol=1e-3)  # D(ΔT): difference of large terms at early times (Compton coupling), roundoff-limited
+        m = J2 != 0
+        assert np.allclose(J[m], J2[m], rtol=1e-5, atol=1e-6 * np.abs(J2).max())
+
+
+def test_generated_f_J_dT_ic_match_oracle(sb, oracle):
+    """The generated tables (J = J_local + p φᵀ + q ψᵀ, basis functions, ICs, Δm) against the oracle's hand-typed RHS,
+    probed Jacobian and complex-step time gradient, for ΛCDM and w0waCDM."""
+    rng = np.random.default_rng(1)
+    for M, kw in ((sb.ΛCDM(lmax=5), dict(lmax=5)), (sb.ΛCDM(lmax=10), dict(lmax=10)), (sb.w0waCDM(lmax=10), dict(lmax=10, model=1, w0=-0.9, wa=0.1, cs2X=1.0))):
+        prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+        obg = oracle.Background(oracle.planck18(**kw))
+        P = prob.P.copy()
+        P[prob.iP_kappa0], P[prob.iP_tau0] = obg.kappa0, obg.tau0
+        N = prob.N
+        assert N == obg.N
+        for tau, k in ((1e-3, 50.0), (0.05, 300.0), (1.0, 5.0), (3.0, 1000.0)):
+            u = rng.standard_normal(N)
+            fo, Jo, dTo = np.zeros(N), np.zeros((N, N)), np.zeros(N)
+            oracle.lib().sbo_pt_fjt(C.byref(obg.p), *obg._spl(), C.c_double(tau), C.c_double(k), _ptr(u), _ptr(fo), _ptr(Jo), _ptr(dTo))
+            yo, ypo = np.zeros(5), np.zeros(5)
+            prob.lib.sbm_debug_spline(C.c_int(len(obg.t)), _ptr(obg.t), _ptr(obg.y), _ptr(obg.dy), C.c_double(tau), _ptr(yo), _ptr(ypo))
+            f, J, dT = np.zeros(N), np.zeros((N, N)), np.zeros(N)
+            prob.lib.sbm_debug_fjt(_ptr(P), _ptr(yo), _ptr(ypo), C.c_double(tau), C.c_double(k), _ptr(u), _ptr(f), _ptr(J), _ptr(dT))
+            assert np.abs(f - fo).max() <= 1e-11 * np.abs(fo).max()
+            assert np.abs(J - Jo).max() <= 1e-11 * np.abs(Jo).max()
+            assert np.abs(dT - dTo).max() <= 1e-9 * np.abs(dTo).max()
+            assert ((J != 0) == (Jo != 0)).all()  # identical sparsity pattern
+            u0, u0o = np.zeros(N), np.zeros(N)
+            prob.lib.sbm_debug_initial(_ptr(P), _ptr(yo), C.c_double(tau), C.c_double(k), _ptr(u0))
+            oracle.lib().sbo_pt_initial(C.byref(obg.p), *obg._spl(), C.c_double(tau), C.c_double(k), _ptr(u0o))
+            assert np.abs(u0 - u0o).max() <= 1e-12 * np.abs(u0o).max()
+            dm = C.c_double()
+            prob.lib.sbm_debug_delta_m(_ptr(P), _ptr(yo), C.c_double(tau), C.c_double(k), _ptr(u), C.byref(dm))
+            dmo = np.zeros(1)
+            oracle.lib().sbo_delta_m(C.byref(obg.p), *obg._spl(), C.c_double(tau), C.c_int(1), _ptr(np.array([k])), _ptr(u), _ptr(dmo))
+            assert np.isclose(dm.value, dmo[0], rtol=1e-11)
+
+
+def test_woodbury_split_is_well_conditioned(sb, prob5, bg5):
+    """W = B − pφᵀ − qψᵀ solved through B and a 2x2 capacitance matrix reproduces a dense solve to ~1e-12."""
+    N = prob5.N
+    rng = np.random.default_rng(0)
+    for tau, k, h in ((1e-4, 1000.0, 1e-5), (0.05, 1000.0, 2e-3), (2.0, 1000.0, 2e-2), (3.0, 2000.0, 3e-3), (1.0, 10.0, 0.2)):
+        y, yp = bg5.spline(tau)
+        Jl, hubs = np.zeros((N, N)), np.zeros((4, N))
+        prob5.lib.sbm_debug_split(_ptr(bg5.P), _ptr(y), _ptr(yp), C.c_double(tau), C.c_double(k), _ptr(Jl), _ptr(hubs))
+        p, q, phi, psi = hubs
+        B = np.eye(N) / (0.21193756319429014 * h) - Jl
+        W = B - np.outer(p, phi) - np.outer(q, psi)
+        r = rng.standard_normal(N)
+        U, V = np.stack([p, q], 1), np.stack([phi, psi], 1)
+        Z, yb = np.linalg.solve(B, U), np.linalg.solve(B, r)
+        xw = yb + Z @ np.linalg.solve(np.eye(2) - V.T @ Z, V.T @ yb)
+        xd = np.linalg.solve(W, r)  # dense pivoted LU; cond(W) reaches 1e12 in the tightly-coupled era, so compare solutions
+        assert np.abs(xw - xd).max() <= 1e-8 * np.abs(xd).max()
+
+
+def test_host_background_matches_oracle(bg5, obg5):
+    """Host Rodas5P background (analytic generated Jacobian) vs the oracle (complex-step Jacobian): same τ0, a(τ), X_e within tolerance."""
+    assert bg5.success and abs(bg5.tau0 / obg5.tau0 - 1) < 1e-8
+    assert bg5.t[-1] == bg5.tau0 and bg5.y[-1, 0] >= 1.0 and abs(bg5.y[-1, 0] - 1) < 1e-10
+    ts = np.exp(np.linspace(np.log(2e-6), np.log(0.999 * bg5.tau0), 400))
+    Y = np.array([bg5.spline(t)[0] for t in ts])
+    o = obg5.observe(ts)
+    assert np.abs(Y[:, 0] / o["a"] - 1).max() < 1e-6          # runtests.jl:289 checkvar(a, 1e-6)
+    assert np.abs(Y[:, 2] - o["XH"]).max() < 1e-5 and np.abs(Y[:, 3] - o["XHe"]).max() < 1e-5
+    late = ts > 1e-2
+    assert np.abs((Y[late, 1] - bg5.kappa0) - o["kappa"][late]).max() < 1e-4 * (1 + np.abs(o["kappa"][late]).max())
+
+
+def test_grids(sb):
+    """src/utils.jl:269-292"""
+    g = sb.loggrid(1e-4, 1.0, length=100)
+    assert g[0] == 1e-4 and g[-1] == 1.0 and len(g) == 100 and (np.diff(g) > 0).all()
+    assert len(sb.lingrid(0.0, 1.0, step=0.3)) == 5 and sb.lingrid(0.0, 1.0, step=0.3)[-1] == 1.0
+    c = sb.cosgrid(0.0, 1.0, length=300)
+    assert c[0] == 0.0 and abs(c[-1] - 1.0) < 1e-15 and len(c) == 300
+    ch = sb.chebgrid(1.0, 3.0, order=4)
+    assert np.allclose(ch, 2 + np.cos(np.pi * np.arange(4, -1, -1) / 4))
+    with pytest.raises(ValueError):
+        sb.lingrid(1.0, 0.0, length=3)
+
+
+def test_chebyshev_interpolator_known_answers(sb):
+    """runtests.jl:216-229: S = τ + k and τ·k through the Chebyshev interpolator (order 1 is exact for linear functions)."""
+    ks = np.array([1.0, 10.0, 100.0])
+    kint = sb.ChebyshevInterpolator(ks.min(), ks.max(), 1)
+    assert kint.xs[0] == 100.0 and kint.xs[-1] == 1.0  # stored descending
+    B = kint.matrix(ks)
+    taus = np.array([1.0, 2.0])
+    Sc = taus[:, None] + kint.xs[None, :]
+    assert np.allclose(Sc @ B.T, taus[:, None] + ks[None, :])
+    k60 = sb.ChebyshevInterpolator(1e-2, 2e3, 60)
+    assert len(k60.xs) == 61 and np.isclose(k60.matrix(k60.xs), np.eye(61)).all()
+    f = np.cos(k60.xs / 300.0)
+    kf = np.linspace(1e-2, 2e3, 777)
+    assert np.abs(k60.matrix(kf) @ f - np.cos(kf / 300.0)).max() < 1e-10
+
+
+def test_natural_spline_weights_and_l_spline(sb):
+    """The C_l k-integral is linear in the data: weights reproduce scipy's natural cubic spline integral / evaluation."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(3)
+    x = np.concatenate([[0.0], np.sort(rng.random(40)) * 10 + 0.01])
+    f = rng.standard_normal(len(x))
+    w = sb.natural_spline_weights(x)
+    assert np.isclose(w @ f, CubicSpline(x, f, bc_type="natural").integrate(x[0], x[-1]), rtol=1e-12)
+    ls = np.array([2, 3, 5, 10, 20, 40, 80.0])
+    y = np.stack([np.log(ls), ls**0.5], 1)
+    lf = np.arange(2, 81)
+    ref = np.stack([CubicSpline(ls, y[:, i], bc_type="natural")(lf) for i in range(2)], 1)
+    assert np.allclose(sb.spline_ls(y, ls, lf), ref, rtol=1e-12)
+
+
+def test_spectrum_primordial(sb, prob5):
+    """src/observables/fourier.jl:14-23: P0 = 2π² As k⁻³ (k/kp)^(ns−1); kp = 0.05/Mpc in H0/c units."""
+    k = np.array([1.0, 222.530031175772])
+    P0 = sb.spectrum_primordial(k, prob5)
+    assert np.isclose(P0[1], 2 * np.pi**2 * 2.099e-9 / k[1] ** 3, rtol=1e-9)
+    assert np.isclose(prob5.derived["kpivot"], 0.05 / sb.k0 / 0.6736, rtol=1e-12)
+
+
+def test_parameter_updater(sb, prob5):
+    upd = sb.parameter_updater(prob5, ["Omega_c", "ns"])
+    p2 = upd([0.3, 0.97])
+    assert p2.pars["Omega_c"] == 0.3 and p2.pars["ns"] == 0.97 and p2.pars["h"] == prob5.pars["h"]
+    assert p2.lib is prob5.lib  # the compiled engine is reused
+    assert abs(p2.derived["Omega_L"] - (prob5.derived["Omega_L"] - (0.3 - prob5.pars["Omega_c"]))) < 1e-12
