@@ -374,46 +374,13 @@ def generate(m: Model):
     W(_arr("short", "sb_blkid", blkid))
     W(_arr("short", "sb_blkpos", blkpos))
 
-    # ---------------- per-lane schedules (warp = 32 lanes).  Layout [item][lane] so that a warp reads one coalesced line;
-    # the integrator keeps them in registers.  Row i is owned by lane i % 32 (slot r = i / 32).
-    R = (N + 31) // 32
-    WD = max(len(r) for r in L.rows)
-    assert N <= 255 and NB <= 255 and sum(len(b) ** 2 for b in L.blocks) <= 255
-    ell_coef = [0.0] * (R * WD * 32)
-    ell_idx = [0] * (R * WD * 32)
-    for i in range(N):
-        lane, r = i % 32, i // 32
-        for w, ((j, c, b), (rk, ri)) in enumerate(zip(L.rows[i], L.roles[i])):
-            tgt = ri
-            if rk == 3:
-                bb, pos = L.blk_of[i]
-                tgt = boff[bb] + pos * len(L.blocks[bb]) + ri
-            ell_coef[(r * WD + w) * 32 + lane] = c
-            ell_idx[(r * WD + w) * 32 + lane] = j | (b << 8) | (rk << 16) | (tgt << 20)
-    # hub vectors p, q by row (one term each, asserted above)
-    pq_coef = [0.0] * (R * 2 * 32)
-    pq_idx = [0] * (R * 32)
-    for (i, c, b) in L.hub["p"]:
-        pq_coef[((i // 32) * 2 + 0) * 32 + i % 32] = c
-        pq_idx[(i // 32) * 32 + i % 32] |= b
-    for (i, c, b) in L.hub["q"]:
-        pq_coef[((i // 32) * 2 + 1) * 32 + i % 32] = c
-        pq_idx[(i // 32) * 32 + i % 32] |= b << 8
-    # hub functionals phi, psi: term t handled by lane t % 32, slot t / 32
-    TPH = (len(L.hub["phi"]) + 31) // 32
-    TPS = (len(L.hub["psi"]) + 31) // 32
-    def _terms(lst, T):
-        cf, ix = [0.0] * (T * 32), [0] * (T * 32)
-        for t, (i, c, b) in enumerate(lst):
-            cf[(t // 32) * 32 + t % 32] = c
-            ix[(t // 32) * 32 + t % 32] = i | (b << 8)
-        return cf, ix
-    phc, phi_ = _terms(L.hub["phi"], TPH)
-    psc, psi_ = _terms(L.hub["psi"], TPS)
-    # Path decomposition of the elimination forest: a path is a maximal chain v0 -> v1 -> ... in which every vertex after
-    # the first has exactly one child (the previous one).  One lane owns one path per phase and runs the elimination /
-    # substitution recurrences along it in registers; phase(path) = 0 for paths starting at a leaf, else 1 + max phase of
-    # the paths feeding its first vertex.  Dense 2-core members are not on paths (handled by the block step).
+    # ---------------- per-lane schedules for the integrator (warp = 32 lanes), layout [item][lane] (one coalesced line per item).
+    # Path decomposition of the elimination forest: a path is a maximal chain v0 -> v1 -> ... in which every vertex after the
+    # first has exactly one child (the previous one).  One lane owns one path per phase and runs the elimination / substitution
+    # recurrences along it in registers; phase(path) = 0 for paths starting at a leaf, else 1 + max phase of the paths feeding
+    # its first vertex.  Dense 2-core members are not on paths (block step).  The integrator works in a RELABELLED state order
+    # in which every path is a contiguous index range (phase by phase, dense members last), so that the recurrences address
+    # shared memory as base + compile-time offset; sb_nat / sb_newidx convert at the kernel boundary (ICs, saved states).
     dense_blocks = [b for b in L.blocks if len(b) > 1]
     in_dense = {v for b in dense_blocks for v in b}
     path_of, paths, pphase = {}, [], []
@@ -431,52 +398,90 @@ def generate(m: Model):
         path_of[v] = pid
     NPH = max(pphase) + 1
     PL = max(len(p) for p in paths)
-    PLW = (PL + 3) // 4
     PR = max((sum(1 for q in pphase if q == ph) + 31) // 32 for ph in range(NPH))
-    # descriptors [phase][round][lane]: head = len | parent_of_last<<8 (255: root) ; kids = children of the first vertex ; verts packed 4 per word
+    nat = []  # new index -> natural index
+    for ph in range(NPH):
+        for pid, q in enumerate(pphase):
+            if q == ph:
+                nat += paths[pid]
+    for b in dense_blocks:
+        nat += b
+    assert sorted(nat) == list(range(N)) and N <= 254
+    inv = [0] * N
+    for new_i, old_i in enumerate(nat):
+        inv[old_i] = new_i
+    R = (N + 31) // 32
+    WD = max(len(r) for r in L.rows)
+    assert NB <= 255 and sum(len(b) ** 2 for b in L.blocks) <= 255
+    ell_coef = [0.0] * (R * WD * 32)
+    ell_idx = [0] * (R * WD * 32)
+    for i in range(N):
+        ni = inv[i]
+        lane, r = ni % 32, ni // 32
+        for w, ((j, c, b), (rk, ri)) in enumerate(zip(L.rows[i], L.roles[i])):
+            tgt = 0
+            if rk == 2:
+                tgt = inv[ri]
+            elif rk == 3:
+                bb, pos = L.blk_of[i]
+                tgt = boff[bb] + pos * len(L.blocks[bb]) + ri
+            ell_coef[(r * WD + w) * 32 + lane] = c
+            ell_idx[(r * WD + w) * 32 + lane] = inv[j] | (b << 8) | (rk << 16) | (tgt << 20)
+    pq_coef = [0.0] * (R * 2 * 32)
+    pq_idx = [0] * (R * 32)
+    for (i, c, b) in L.hub["p"]:
+        ni = inv[i]
+        pq_coef[((ni // 32) * 2 + 0) * 32 + ni % 32] = c
+        pq_idx[(ni // 32) * 32 + ni % 32] |= b
+    for (i, c, b) in L.hub["q"]:
+        ni = inv[i]
+        pq_coef[((ni // 32) * 2 + 1) * 32 + ni % 32] = c
+        pq_idx[(ni // 32) * 32 + ni % 32] |= b << 8
+    TPH = (len(L.hub["phi"]) + 31) // 32
+    TPS = (len(L.hub["psi"]) + 31) // 32
+
+    def _terms(lst, T):
+        cf, ix = [0.0] * (T * 32), [0] * (T * 32)
+        for t, (i, c, b) in enumerate(lst):
+            cf[(t // 32) * 32 + t % 32] = c
+            ix[(t // 32) * 32 + t % 32] = inv[i] | (b << 8)
+        return cf, ix
+    phc, phi_ = _terms(L.hub["phi"], TPH)
+    psc, psi_ = _terms(L.hub["psi"], TPS)
+    # path descriptors [phase][round][lane]: head = start | len<<8 | parent_of_last<<16 (255: root); kids = children of the first vertex
     p_head = [0] * (NPH * PR * 32)
     p_kids = [0xFFFFFFFF] * (NPH * PR * 32)
-    p_vert = [0xFFFFFFFF] * (NPH * PR * PLW * 32)
     for ph in range(NPH):
         mine = [i for i, q in enumerate(pphase) if q == ph]
         for q, pid in enumerate(mine):
             rd, lane = q // 32, q % 32
             p = paths[pid]
+            start = inv[p[0]]
+            assert [inv[v] for v in p] == list(range(start, start + len(p)))
             par = L.parent[p[-1]]
-            par = 255 if par < 0 else par
-            p_head[(ph * PR + rd) * 32 + lane] = len(p) | (par << 8)
-            kids = list(L.children[p[0]]) + [255] * (4 - len(L.children[p[0]]))
-            assert len(L.children[p[0]]) <= 4
+            par = 255 if par < 0 else inv[par]
+            p_head[(ph * PR + rd) * 32 + lane] = start | (len(p) << 8) | (par << 16)
+            kids = [inv[c] for c in L.children[p[0]]]
+            assert len(kids) <= 4
+            kids += [255] * (4 - len(kids))
             p_kids[(ph * PR + rd) * 32 + lane] = kids[0] | (kids[1] << 8) | (kids[2] << 16) | (kids[3] << 24)
-            for w in range(PLW):
-                word = 0
-                for j in range(4):
-                    idx = 4 * w + j
-                    word |= (p[idx] if idx < len(p) else 255) << (8 * j)
-                p_vert[((ph * PR + rd) * PLW + w) * 32 + lane] = word
-    # dense members: children lists (contributions gathered before the block step); lane = block*8 + row
     d_kids = [0xFFFFFFFF] * 32
     for bi, b in enumerate(dense_blocks):
         for pos, v in enumerate(b):
-            kids = list(L.children[v]) + [255] * (4 - len(L.children[v]))
-            assert len(L.children[v]) <= 4
+            kids = [inv[c] for c in L.children[v]]
+            assert len(kids) <= 4
+            kids += [255] * (4 - len(kids))
             d_kids[bi * 8 + pos] = kids[0] | (kids[1] << 8) | (kids[2] << 16) | (kids[3] << 24)
-    assert len(dense_blocks) <= 4
-    for name, val in [("SB_NPH", NPH), ("SB_PL", PL), ("SB_PLW", PLW), ("SB_PR", PR)]:
-        W(f"#define {name} {val}")
-    W(_arr("unsigned int", "sb_path_head", p_head, "{}u"))
-    W(_arr("unsigned int", "sb_path_kids", p_kids, "{}u"))
-    W(_arr("unsigned int", "sb_path_vert", p_vert, "{}u"))
-    W(_arr("unsigned int", "sb_dense_kids", d_kids, "{}u"))
-    LVR = 1
-    tree_a, tree_c = [0], [0]
-    assert len(dense_blocks) <= 32 and all(len(b) <= 8 for b in dense_blocks)
+    assert len(dense_blocks) <= 4 and all(len(b) <= 8 for b in dense_blocks)
     dbn = [len(b) for b in dense_blocks]
     dboff = [boff[L.blocks.index(b)] for b in dense_blocks]
-    dbv0 = [sum((b[i] if i < len(b) else 255) << (8 * i) for i in range(4)) for b in dense_blocks]
-    dbv1 = [sum((b[i + 4] if i + 4 < len(b) else 255) << (8 * i) for i in range(4)) for b in dense_blocks]
-    for name, val in [("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_LVR", LVR), ("SB_NDENSE", len(dense_blocks))]:
+    dbstart = [inv[b[0]] for b in dense_blocks]
+    for b in dense_blocks:
+        assert [inv[v] for v in b] == list(range(inv[b[0]], inv[b[0]] + len(b)))
+    for name, val in [("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NDENSE", len(dense_blocks)), ("SB_NPH", NPH), ("SB_PL", PL), ("SB_PR", PR)]:
         W(f"#define {name} {val}")
+    W(_arr("short", "sb_nat", nat))
+    W(_arr("short", "sb_newidx", inv))
     W(_arr("double", "sb_ell_coef", ell_coef, "{!r}"))
     W(_arr("unsigned int", "sb_ell_idx", ell_idx, "{}u"))
     W(_arr("double", "sb_pq_coef", pq_coef, "{!r}"))
@@ -485,12 +490,12 @@ def generate(m: Model):
     W(_arr("unsigned int", "sb_phi_idx", phi_, "{}u"))
     W(_arr("double", "sb_psi_coef", psc, "{!r}"))
     W(_arr("unsigned int", "sb_psi_idx", psi_, "{}u"))
-    W(_arr("unsigned int", "sb_tree_a", tree_a, "{}u"))
-    W(_arr("unsigned int", "sb_tree_c", tree_c, "{}u"))
+    W(_arr("unsigned int", "sb_path_head", p_head, "{}u"))
+    W(_arr("unsigned int", "sb_path_kids", p_kids, "{}u"))
+    W(_arr("unsigned int", "sb_dense_kids", d_kids, "{}u"))
     W(_arr("int", "sb_dense_n", dbn))
     W(_arr("int", "sb_dense_off", dboff))
-    W(_arr("unsigned int", "sb_dense_v0", dbv0, "{}u"))
-    W(_arr("unsigned int", "sb_dense_v1", dbv1, "{}u"))
+    W(_arr("int", "sb_dense_start", dbstart))
     W(_arr("unsigned int", "sb_basis_pack", [(b[0] | ((b[1] + 3) << 8)) for b in L.basis], "{}u"))
 
     flops = {}

@@ -320,7 +320,7 @@ struct SbLane {
     unsigned pqi[SB_R];
     double phc[SB_TPH], psc[SB_TPS]; // hub functionals φ, ψ: one term per lane and slot
     unsigned phi[SB_TPH], psi[SB_TPS];
-    unsigned ph[SB_NPH * SB_PR], pk[SB_NPH * SB_PR], pv[SB_NPH * SB_PR * SB_PLW]; // owned elimination paths: len|parent, first-vertex children, vertices
+    unsigned ph[SB_NPH * SB_PR], pk[SB_NPH * SB_PR]; // owned elimination paths (contiguous index ranges): start|len<<8|parent<<16, first-vertex children
     unsigned dk;               // dense-block member owned by this lane (lane = block*8+row): its forest children
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
     __device__ __forceinline__ void load(int lane) {
@@ -334,8 +334,6 @@ struct SbLane {
         for (int t = 0; t < SB_TPS; t++) { psc[t] = sb_psi_coef[t * 32 + lane]; psi[t] = sb_psi_idx[t * 32 + lane]; }
 #pragma unroll
         for (int q = 0; q < SB_NPH * SB_PR; q++) { ph[q] = sb_path_head[q * 32 + lane]; pk[q] = sb_path_kids[q * 32 + lane]; }
-#pragma unroll
-        for (int q = 0; q < SB_NPH * SB_PR * SB_PLW; q++) pv[q] = sb_path_vert[q * 32 + lane];
         dk = sb_dense_kids[lane];
 #pragma unroll
         for (int r = 0; r < SB_NBR; r++) { int m = r * 32 + lane; bp[r] = (m < SB_NB) ? sb_basis_pack[m] : 0u; }
@@ -343,10 +341,16 @@ struct SbLane {
 };
 
 // basis functions b_m = k^e β_m(τ) (and optionally ḃ_m) from the β-table; lanes over m
-__device__ __forceinline__ void sb_basis_at(const SbLane& S, const SbTable& tb, double tau, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
+__device__ __forceinline__ int sb_interval(const SbTable& tb, double tau) { // knot interval containing tau (log look-up + scan)
     int q = (int)((log(tau) - tb.s0) * tb.inv_dsl);
     q = max(0, min(q, tb.nlut - 1));
     int j = __ldg(tb.lut + q);
+    while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
+    return j;
+}
+// jhint: an interval index known to be <= the interval of tau (times only move forward inside a mode)
+__device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, double tau, int jhint, const double* kp /*smem: k^-3..k^3 at [0..6]*/, double* b, double* bd, int lane) {
+    int j = jhint;
     while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
     const double tj = __ldg(tb.t + j), hj = __ldg(tb.t + j + 1) - tj;
     const double hs = hj / tb.msub;
@@ -367,6 +371,7 @@ __device__ __forceinline__ void sb_basis_at(const SbLane& S, const SbTable& tb, 
             if (bd) bd[m] = kk * (6 * w * w1 * (v0 - v1) / hs + (3 * w - 1) * w1 * d0 + w * (3 * w - 2) * d1); // derivative of the Hermite cubic
         }
     }
+    return j;
 }
 
 // out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU
@@ -407,7 +412,6 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
     __syncwarp();
 }
 
-#define SB_PVERT(S, q, pos) (((S).pv[(q) * SB_PLW + ((pos) >> 2)] >> (8 * ((pos) & 3))) & 255)
 
 // Factor B = x·I − J_local(b) along the generated elimination paths (zero fill, no pivoting: the chains have sign-skew
 // off-diagonals and non-negative damping, so pivots only grow) + explicit pivoted inverse of the dense 2-core blocks.
@@ -439,26 +443,24 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int len = S.ph[q] & 255;
+            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255;
             if (len > 0) {
-                int prev = SB_PVERT(S, q, 0);
-                double dj = di[prev];
+                double* dip = di + start; double* mmp = mm + start; const double* upp = up + start;
+                double dj = dip[0];
                 if (ph > 0) {
 #pragma unroll
                     for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
                 }
                 double dinv = 1.0 / dj;
-                di[prev] = dinv;
+                dip[0] = dinv;
 #pragma unroll
                 for (int pos = 1; pos < SB_PL; pos++) {
                     if (pos < len) {
-                        const int v = SB_PVERT(S, q, pos);
-                        const double m = mm[prev] * dinv;
-                        mm[prev] = m;
-                        dj = di[v] - m * up[prev];
+                        const double m = mmp[pos - 1] * dinv;
+                        mmp[pos - 1] = m;
+                        dj = dip[pos] - m * upp[pos - 1];
                         dinv = 1.0 / dj;
-                        di[v] = dinv;
-                        prev = v;
+                        dip[pos] = dinv;
                     }
                 }
             }
@@ -468,8 +470,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
     if (SB_NDENSE > 0) {
         const int bb = lane >> 3, i = lane & 7;
         if (bb < SB_NDENSE && i < sb_dense_n[bb]) { // gather the children's Schur contributions into the block diagonal
-            const unsigned vv = (i < 4) ? sb_dense_v0[bb] : sb_dense_v1[bb];
-            const int v = (vv >> (8 * (i & 3))) & 255;
+            const int v = sb_dense_start[bb] + i;
             double dj = di[v];
 #pragma unroll
             for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
@@ -479,13 +480,12 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         // Gauss-Jordan with partial pivoting, one matrix row [A | I] per lane (lane = block*8 + row), rows exchanged by
         // warp shuffles within the 8-lane group -> explicit inverse (block solves become mat-vecs)
         {
-            int nb = 0, off = 0; unsigned v0 = 0, v1 = 0;
-            if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; v0 = sb_dense_v0[bb]; v1 = sb_dense_v1[bb]; }
+            int nb = 0, off = 0, vstart = 0;
+            if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; vstart = sb_dense_start[bb]; }
             double Ar[SB_MAXBLOCK], Ir[SB_MAXBLOCK];
 #pragma unroll
             for (int j = 0; j < SB_MAXBLOCK; j++) {
-                const int vi = (i < 4) ? ((v0 >> (8 * i)) & 255) : ((v1 >> (8 * (i - 4))) & 255);
-                Ar[j] = (i < nb && j < nb) ? ((i == j) ? di[vi] : blk[off + i * nb + j]) : ((i == j) ? 1.0 : 0.0);
+                Ar[j] = (i < nb && j < nb) ? ((i == j) ? di[vstart + i] : blk[off + i * nb + j]) : ((i == j) ? 1.0 : 0.0);
                 Ir[j] = (i == j) ? 1.0 : 0.0;
             }
             int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
@@ -513,48 +513,65 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         }
         __syncwarp();
     }
+    // all Schur updates are done: scale the parent couplings by the inverse pivots (backward substitution = 1 fma per vertex)
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) up[i] *= di[i]; }
+    __syncwarp();
 }
 
-// r <- B^{-1} r : forward along the paths (registers), dense blocks (mat-vec with the explicit inverse), backward along the paths
-__device__ __forceinline__ void sb_bsolve(const SbLane& S, double* r, const double* di, const double* up, const double* mm, const double* blk, int lane) {
+// r <- B^{-1} r for NR right-hand sides at once (independent recurrences interleave: the solve is latency-bound):
+// forward along the owned paths (registers), dense blocks (mat-vec with the explicit inverse), backward along the paths.
+template <int NR>
+__device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[NR], const double* di, const double* up, const double* mm, const double* blk, int lane) {
 #pragma unroll
     for (int ph = 0; ph < SB_NPH; ph++) {
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int len = S.ph[q] & 255;
+            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255;
             if (len > 0) {
-                double av[SB_PL];
-                double acc = r[SB_PVERT(S, q, 0)];
-                if (ph > 0) {
+                const double* mmp = mm + start;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * r[ch]; }
+                for (int a = 0; a < NR; a++) {
+                    double* rp = rr[a] + start;
+                    double av[SB_PL];
+                    double acc = rp[0];
+                    if (ph > 0) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * rr[a][ch]; }
+                    }
+                    av[0] = acc;
+#pragma unroll
+                    for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; }
+#pragma unroll
+                    for (int pos = 0; pos < SB_PL; pos++) if (pos < len && (pos > 0 || ph > 0)) rp[pos] = av[pos];
                 }
-                av[0] = acc;
-#pragma unroll
-                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = r[SB_PVERT(S, q, pos)] - mm[SB_PVERT(S, q, pos - 1)] * acc; av[pos] = acc; }
-#pragma unroll
-                for (int pos = (0); pos < SB_PL; pos++) if (pos < len && (pos > 0 || ph > 0)) r[SB_PVERT(S, q, pos)] = av[pos];
             }
         }
         __syncwarp();
     }
     if (SB_NDENSE > 0) { // dense blocks: lane = block*8 + row
         const int bb = lane >> 3, i = lane & 7;
-        int vi = 255, nb = 0, off = 0; unsigned v0 = 0, v1 = 0;
-        if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; v0 = sb_dense_v0[bb]; v1 = sb_dense_v1[bb]; }
+        int nb = 0, off = 0, vstart = 0;
+        if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; vstart = sb_dense_start[bb]; }
         if (i < nb) {
-            vi = (i < 4) ? ((v0 >> (8 * i)) & 255) : ((v1 >> (8 * (i - 4))) & 255);
-            double acc = r[vi];
 #pragma unroll
-            for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * r[ch]; }
-            r[vi] = acc;
+            for (int a = 0; a < NR; a++) {
+                double acc = rr[a][vstart + i];
+#pragma unroll
+                for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * rr[a][ch]; }
+                rr[a][vstart + i] = acc;
+            }
         }
         __syncwarp();
-        double xi = 0;
-        if (i < nb) for (int j = 0; j < nb; j++) { const int vj = (j < 4) ? ((v0 >> (8 * j)) & 255) : ((v1 >> (8 * (j - 4))) & 255); xi += blk[off + i * nb + j] * r[vj]; }
+        double xi[NR];
+#pragma unroll
+        for (int a = 0; a < NR; a++) { xi[a] = 0; if (i < nb) for (int j = 0; j < nb; j++) xi[a] = fma(blk[off + i * nb + j], rr[a][vstart + j], xi[a]); }
         __syncwarp();
-        if (i < nb) r[vi] = xi;
+        if (i < nb) {
+#pragma unroll
+            for (int a = 0; a < NR; a++) rr[a][vstart + i] = xi[a];
+        }
         __syncwarp();
     }
 #pragma unroll
@@ -562,14 +579,19 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* r, const doub
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int len = S.ph[q] & 255, par = (S.ph[q] >> 8) & 255;
+            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255, par = (S.ph[q] >> 16) & 255;
             if (len > 0) {
-                double xs[SB_PL];
-                double xv = (par == 255) ? 0.0 : r[par];
+                const double *upp = up + start, *dip = di + start;
 #pragma unroll
-                for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { const int v = SB_PVERT(S, q, pos); xv = (r[v] - up[v] * xv) * di[v]; xs[pos] = xv; }
+                for (int a = 0; a < NR; a++) {
+                    double* rp = rr[a] + start;
+                    double xs[SB_PL];
+                    double xv = (par == 255) ? 0.0 : rr[a][par];
 #pragma unroll
-                for (int pos = 0; pos < SB_PL; pos++) if (pos < len) r[SB_PVERT(S, q, pos)] = xs[pos];
+                    for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, rp[pos] * dip[pos]); xs[pos] = xv; }
+#pragma unroll
+                    for (int pos = 0; pos < SB_PL; pos++) if (pos < len) rp[pos] = xs[pos];
+                }
             }
         }
         __syncwarp();
@@ -617,16 +639,19 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
             continue;
         }
         if (lane < 7) kp[lane] = pow(k, (double)(lane - 3));
-        if (lane == 0) { double y[5]; sb_spl_eval(A.spl, t, y, nullptr); sb_initial(t, k, y, A.P, u); }
+        if (lane == 0) { double y[5]; sb_spl_eval(A.spl, t, y, nullptr); sb_initial(t, k, y, A.P, U); } // natural order
+        __syncwarp();
+        for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
         __syncwarp();
         while (isave < A.nsave && A.saveat[isave] <= t) { // save points at (or before) the start
-            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = (A.saveat[isave] == t) ? u[i] : NAN;
+            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = (A.saveat[isave] == t) ? u[i] : NAN;
             isave++;
         }
         SbController ctl; ctl.init();
         double dt = 0;
         if (tend > t) {
-            sb_basis_at(S, A.tb, t, kp, bs, bdv, lane);
+            int jt = sb_interval(A.tb, t); // knot interval of the current time
+            jt = sb_basis_at(S, A.tb, t, jt, kp, bs, bdv, lane);
             __syncwarp();
             sb_eval_f(S, bs, u, f0, lane); nf++;
             sb_eval_dT(S, bs, bdv, u, dT, lane);
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
                 dt0 = fmin(dt0, dtmax);
                 for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
-                sb_basis_at(S, A.tb, t + dt0, kp, bs + SB_NB, nullptr, lane);
+                sb_basis_at(S, A.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
                 __syncwarp();
                 sb_eval_f(S, bs + SB_NB, U, K, lane); nf++;
                 double d2 = 0;
@@ -649,13 +674,14 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
                 __syncwarp();
             }
+            int jend = jt; // interval of t + dt after the step (becomes jt on accept)
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
                 // basis at the 5 later stage times
 #pragma unroll
-                for (int s = 1; s < 6; s++) sb_basis_at(S, A.tb, t + cc[s] * dt, kp, bs + s * SB_NB, nullptr, lane);
+                for (int s = 1; s < 6; s++) { const int js = sb_basis_at(S, A.tb, t + cc[s] * dt, jt, kp, bs + s * SB_NB, nullptr, lane); if (s == 5) jend = js; }
                 __syncwarp();
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
                 sb_factor(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane);
@@ -665,33 +691,48 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                     if (i < SB_N) { Zp[i] = S.pqc[2 * r] * bs[S.pqi[r] & 255]; Zq[i] = S.pqc[2 * r + 1] * bs[(S.pqi[r] >> 8) & 255]; }
                 }
                 __syncwarp();
-                sb_bsolve(S, Zp, di, up, mm, blk, lane);
-                sb_bsolve(S, Zq, di, up, mm, blk, lane);
+                { double* const zz[2] = {Zp, Zq}; sb_bsolve<2>(S, zz, di, up, mm, blk, lane); }
                 nsolve += 2;
                 double m11, m12, m21, m22;
                 sb_hub_dots(S, bs, Zp, m11, m21, lane);
                 sb_hub_dots(S, bs, Zq, m12, m22, lane);
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
                 const double idet = 1.0 / (m11 * m22 - m12 * m21);
-                // 8 stages
+                const double idt = 1.0 / dt;
+                // 8 stages.  U_s = u + Σ_j a_sj k_j and R_s = Σ_j (C_sj/dt) k_j are accumulated together (each k_j is read once per
+                // stage; coefficients padded with zeros so that the 7-term loops are branch-free and the owned rows interleave)
                 for (int s = 0; s < 8; s++) {
                     double* ks = K + s * SB_N;
-                    const double* fs = f0;
+                    double Racc[SB_R];
                     if (s > 0) {
-                        if (s <= 5) { for (int i = lane; i < SB_N; i += SB_WARP) { double v = u[i]; for (int j = 0; j < s; j++) v += cA[s][j] * K[j * SB_N + i]; U[i] = v; } }
-                        else { for (int i = lane; i < SB_N; i += SB_WARP) U[i] += K[(s - 1) * SB_N + i]; }
+                        double ca[7], cq[7];
+#pragma unroll
+                        for (int j = 0; j < 7; j++) { ca[j] = cA[s][j]; cq[j] = cC[s][j] * idt; }
+#pragma unroll
+                        for (int r = 0; r < SB_R; r++) {
+                            const int i = min(r * 32 + lane, SB_N - 1);
+                            double ua = u[i], ra = 0;
+#pragma unroll
+                            for (int j = 0; j < 7; j++) { const double kj = (j < s) ? K[j * SB_N + i] : 0.0; ua = fma(ca[j], kj, ua); ra = fma(cq[j], kj, ra); }
+                            Racc[r] = ra;
+                            if (r * 32 + lane < SB_N) U[i] = ua;
+                        }
                         __syncwarp();
                         sb_eval_f(S, bs + cslot[s] * SB_NB, U, ks, lane); nf++;
-                        fs = ks;
                     }
-                    const double hd_ = dt * cd[s], idt = 1.0 / dt;
-                    for (int i = lane; i < SB_N; i += SB_WARP) { double v = fs[i] + hd_ * dT[i]; for (int j = 0; j < s; j++) v += (cC[s][j] * idt) * K[j * SB_N + i]; ks[i] = v; }
+                    const double hd_ = dt * cd[s];
+#pragma unroll
+                    for (int r = 0; r < SB_R; r++) {
+                        const int i = r * 32 + lane;
+                        if (i < SB_N) ks[i] = ((s > 0) ? ks[i] + Racc[r] : f0[i]) + hd_ * dT[i];
+                    }
                     __syncwarp();
-                    sb_bsolve(S, ks, di, up, mm, blk, lane); nsolve++;
+                    { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); } nsolve++;
                     double s1, s2;
                     sb_hub_dots(S, bs, ks, s1, s2, lane);
                     const double c1 = (m22 * s1 - m12 * s2) * idet, c2 = (-m21 * s1 + m11 * s2) * idet;
-                    for (int i = lane; i < SB_N; i += SB_WARP) ks[i] += Zp[i] * c1 + Zq[i] * c2;
+#pragma unroll
+                    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) ks[i] += Zp[i] * c1 + Zq[i] * c2; }
                     __syncwarp();
                 }
                 // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
@@ -713,10 +754,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                     }
                     while (isave < A.nsave && A.saveat[isave] <= tn) {
                         double ts = A.saveat[isave];
-                        if (ts == tn) { for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = U[i] + K[7 * SB_N + i]; }
+                        if (ts == tn) { for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = U[i] + K[7 * SB_N + i]; }
                         else {
                             double th = (ts - t) / dt, t1 = 1 - th;
-                            for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; usave[(size_t)isave * SB_N + i] = t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i]))); }
+                            for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; usave[(size_t)isave * SB_N + sb_nat[i]] = t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i]))); }
                         }
                         isave++;
                     }
@@ -728,13 +769,13 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
                 if (last) break;
                 dt = dtnew;
-                sb_basis_at(S, A.tb, t, kp, bs, bdv, lane);
+                jt = sb_basis_at(S, A.tb, t, jend, kp, bs, bdv, lane);
                 __syncwarp();
                 sb_eval_f(S, bs, u, f0, lane); nf++;
                 sb_eval_dT(S, bs, bdv, u, dT, lane);
             }
         }
-        for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = u[i];
+        for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
         if (usave) for (; isave < A.nsave; isave++) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
         if (lane == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
         __syncwarp();
