@@ -220,7 +220,7 @@ def main():
                 op = sbref.planck18(lmax=10, Omega_c=pars["Omega_c"], Omega_b=pars["Omega_b"], ns=pars["ns"])
                 tc = oracle_sample(op, (bg.t, bg.y, bg.dy, bg.tau0, bg.kappa0), plan.ks_fine[idx], plan.taus, ls)
                 out["cpu_baseline"] = {"value": nsamp / tc, "unit": "k-modes/s", "cores": os.cpu_count(), "kind": "port",
-                                       "sample": f"{nsamp} of {len(plan.ks_fine)} k-modes evenly spaced over the k-range: perturbation solve + sources with the CPU oracle (OpenMP over modes, dense LU)"}
+                                       "sample": f"{nsamp} of {len(plan.ks_fine)} k-modes evenly spaced over the k-range: perturbation solve + sources with the CPU oracle (OpenMP over modes; zero-skipping LU in a fill-reducing order, compressed Jacobian probing)"}
             except Exception as e:  # the oracle is optional at bench time
                 out["cpu_baseline"] = {"value": None, "unit": "k-modes/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(out))

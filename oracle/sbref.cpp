@@ -19,8 +19,9 @@
 //
 // It is deliberately independent of the product's sympy code generator: equations are typed by
 // hand as C++ templates and differentiated by complex-step (time gradient) and by truncated
-// Taylor "jets" (source-function time derivatives); the Jacobian is probed column by column
-// (the system is linear in u).  Linear algebra is dense LU with partial pivoting.
+// Taylor "jets" (source-function time derivatives); the Jacobian is probed (the system is linear in u; columns with
+// disjoint row patterns are probed together).  Linear algebra is Gaussian elimination with threshold partial pivoting and zero
+// skipping in a fill-reducing order (stand-in for KLU, src/solve.jl:329).
 //
 // PARITY PINNING: Julia is not available, so the reference itself cannot be run.  This oracle is
 // pinned against the reference's own golden vectors test/class_Pk.dat and test/class_Cl.dat
@@ -311,16 +312,67 @@ static void lu_solve(int n, const double* A, const int* piv, double* b) {
     for (int i = n - 1; i >= 0; i--) { double s = b[i]; const double* Ai = A + i * n; for (int j = i + 1; j < n; j++) s -= Ai[j] * b[j]; b[i] = s / Ai[i]; }
 }
 
+// Sparse-aware LU on a dense array: threshold partial pivoting (keep the diagonal unless it is < 1e-3 of the column maximum --
+// KLU's default pivot tolerance, the linear solver the reference selects at src/solve.jl:329), zero skipping in the elimination
+// and index lists for the triangular solves.  With the fill-reducing ordering used by PtSys (hierarchy tails first) the cost is
+// O(nnz(L+U)) instead of O(n^3); the arithmetic is ordinary Gaussian elimination.
+struct SparseLU {
+    int n = 0;
+    std::vector<double> A;
+    std::vector<int> piv, Lptr, Lidx, Uptr, Uidx, cols;
+    bool factor(int n_, const double* W) {
+        n = n_; A.assign(W, W + (size_t)n * n); piv.resize(n); cols.resize(n);
+        for (int k = 0; k < n; k++) {
+            int p = k; double m = std::fabs(A[(size_t)k * n + k]), mx = m;
+            for (int i = k + 1; i < n; i++) { double v = std::fabs(A[(size_t)i * n + k]); if (v > mx) { mx = v; p = i; } }
+            if (!(mx > 0)) return false;
+            if (m >= 1e-3 * mx) p = k; // diagonal preference
+            piv[k] = p;
+            if (p != k) for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)p * n + j]);
+            int nc = 0; const double* Ak = &A[(size_t)k * n];
+            for (int j = k + 1; j < n; j++) if (Ak[j] != 0) cols[nc++] = j;
+            const double inv = 1 / Ak[k];
+            for (int i = k + 1; i < n; i++) {
+                double* Ai = &A[(size_t)i * n];
+                if (Ai[k] != 0) { const double l = Ai[k] * inv; Ai[k] = l; for (int c = 0; c < nc; c++) Ai[cols[c]] -= l * Ak[cols[c]]; }
+            }
+        }
+        Lptr.assign(n + 1, 0); Uptr.assign(n + 1, 0); Lidx.clear(); Uidx.clear();
+        for (int i = 0; i < n; i++) {
+            const double* Ai = &A[(size_t)i * n];
+            for (int j = 0; j < i; j++) if (Ai[j] != 0) Lidx.push_back(j);
+            Lptr[i + 1] = (int)Lidx.size();
+            for (int j = i + 1; j < n; j++) if (Ai[j] != 0) Uidx.push_back(j);
+            Uptr[i + 1] = (int)Uidx.size();
+        }
+        return true;
+    }
+    void solve(double* b) const {
+        for (int k = 0; k < n; k++) if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+        for (int i = 0; i < n; i++) { double s = b[i]; const double* Ai = &A[(size_t)i * n]; for (int q = Lptr[i]; q < Lptr[i + 1]; q++) s -= Ai[Lidx[q]] * b[Lidx[q]]; b[i] = s; }
+        for (int i = n - 1; i >= 0; i--) { double s = b[i]; const double* Ai = &A[(size_t)i * n]; for (int q = Uptr[i]; q < Uptr[i + 1]; q++) s -= Ai[Uidx[q]] * b[Uidx[q]]; b[i] = s / Ai[i]; }
+    }
+};
+
 enum { RC_SUCCESS = 0, RC_MAXITERS = 1, RC_DTMIN = 2, RC_UNSTABLE = 3, RC_TERMINATED = 4 };
 struct Stats { long naccept = 0, nreject = 0, nf = 0, njac = 0; };
 
 // One Rosenbrock step workspace + adaptive driver.  Sys provides n, f(t,u,du), jac(t,u,J), tgrad(t,u,dT).
 template <class Sys> struct Rodas5P {
     Sys& sys; int n;
-    std::vector<double> W, ks, U, du, dT, rhs, f0, K1, K2, K3, unew;
-    std::vector<int> piv;
+    std::vector<double> W, Wp, ks, U, du, dT, rhs, f0, K1, K2, K3, unew, tmp;
+    std::vector<int> perm; // elimination order (fill-reducing), identity if the system provides none
+    SparseLU lu;
     Stats st;
-    explicit Rodas5P(Sys& s) : sys(s), n(s.n), W(n * n), ks(8 * n), U(n), du(n), dT(n), rhs(n), f0(n), K1(n), K2(n), K3(n), unew(n), piv(n) {}
+    explicit Rodas5P(Sys& s) : sys(s), n(s.n), W(n * n), Wp(n * n), ks(8 * n), U(n), du(n), dT(n), rhs(n), f0(n), K1(n), K2(n), K3(n), unew(n), tmp(n), perm(n) {
+        for (int i = 0; i < n; i++) perm[i] = i;
+        sys.ordering(perm.data());
+    }
+    void solve_inplace(double* b) { // W x = b with the symmetrically permuted factorisation
+        for (int i = 0; i < n; i++) tmp[i] = b[perm[i]];
+        lu.solve(tmp.data());
+        for (int i = 0; i < n; i++) b[perm[i]] = tmp[i];
+    }
 
     // one step of size dt from (t,u); fills unew, ks, K1..K3. returns false if LU singular.
     bool step(double t, const double* u, double dt) {
@@ -329,9 +381,8 @@ template <class Sys> struct Rodas5P {
         sys.tgrad(t, u, dT.data());
         sys.jac(t, u, W.data()); st.njac++;
         double dg = 1 / (R5::gamma * dt);
-        for (int i = 0; i < n * n; i++) W[i] = -W[i];
-        for (int i = 0; i < n; i++) W[i * n + i] += dg;
-        if (!lu_factor(n, W.data(), piv.data())) return false;
+        for (int i = 0; i < n; i++) { const double* Wi = &W[(size_t)perm[i] * n]; double* Pi = &Wp[(size_t)i * n]; for (int j = 0; j < n; j++) Pi[j] = -Wi[perm[j]]; Pi[i] += dg; }
+        if (!lu.factor(n, Wp.data())) return false;
         for (int s = 0; s < 8; s++) {
             double* k = ks.data() + s * n;
             const double* fs;
@@ -343,7 +394,7 @@ template <class Sys> struct Rodas5P {
                 fs = du.data();
             }
             for (int i = 0; i < n; i++) { double v = fs[i] + dt * dd[s] * dT[i]; for (int j = 0; j < s; j++) v += (C[s][j] / dt) * ks[j * n + i]; k[i] = v; }
-            lu_solve(n, W.data(), piv.data(), k);
+            solve_inplace(k);
         }
         for (int i = 0; i < n; i++) unew[i] = U[i] + ks[7 * n + i];
         for (int i = 0; i < n; i++) {
@@ -403,6 +454,7 @@ struct Controller { // PI controller, OrdinaryDiffEq defaults for an order-5 ada
 struct BgSys {
     const Derived& D; int n = 5;
     explicit BgSys(const Derived& d) : D(d) {}
+    void ordering(int*) {}
     void f(double, const double* u, double* du) { bg_rhs<double>(D, u, du); }
     void tgrad(double, const double*, double* dT) { for (int i = 0; i < 5; i++) dT[i] = 0; } // autonomous
     void jac(double, const double* u, double* J) { // complex-step columns (exact to rounding)
@@ -612,19 +664,57 @@ static void pt_initial(const Derived& D, const Spline& spl, double tau, double k
 struct PtSys {
     const Derived& D; const Spline& spl; double k; int n;
     std::vector<double> e, col;
+    std::vector<int> color, rowsptr, rowsidx; // column colouring for compressed Jacobian probing + per-column row pattern
+    int ncolors = 0;
     PtSys(const Derived& d, const Spline& s, double kk) : D(d), spl(s), k(kk), n(d.N), e(d.N), col(d.N) {}
+    // fill-reducing elimination order: hierarchy tails (l = lmax ... 3 of every hierarchy) first, the coupled core last
+    void ordering(int* perm) {
+        const int L = D.p.lmax, nh = L + 1; int q = 0;
+        std::vector<char> used(n, 0);
+        auto tail = [&](int base) { for (int l = L; l >= 3; l--) { perm[q++] = base + l; used[base + l] = 1; } };
+        tail(D.iF); tail(D.iG); tail(D.iN);
+        for (int i = 0; i < D.p.nx; i++) tail(D.ipsi + i * nh);
+        for (int i = 0; i < n; i++) if (!used[i]) perm[q++] = i;
+    }
     void f(double t, const double* u, double* du) {
         double y[5]; spl.eval(t, y);
         Bg<double> c; bg_chain(D, y, c, false);
         pt_rhs<double>(D, c, t, k, u, du);
     }
-    void jac(double t, const double*, double* J) { // system is linear in u: column j = f(e_j)
+    // The system is linear in u: column j of J is f(e_j).  The sparsity pattern is fixed, so it is discovered once by full
+    // probing (at two times) and afterwards columns with disjoint row patterns are probed together (greedy colouring).
+    void discover(double t) {
+        std::vector<std::vector<int>> rows(n);
+        double ts[2] = {t, 0.5 * (t + D.tau0)};
+        for (int it = 0; it < 2; it++) {
+            double y[5]; spl.eval(ts[it], y);
+            Bg<double> c; bg_chain(D, y, c, false);
+            for (int j = 0; j < n; j++) {
+                std::fill(e.begin(), e.end(), 0.0); e[j] = 1;
+                pt_rhs<double>(D, c, ts[it], k, e.data(), col.data());
+                for (int i = 0; i < n; i++) if (col[i] != 0 && std::find(rows[j].begin(), rows[j].end(), i) == rows[j].end()) rows[j].push_back(i);
+            }
+        }
+        color.assign(n, -1); ncolors = 0;
+        std::vector<std::vector<char>> occ; // occ[color][row]
+        for (int j = 0; j < n; j++) {
+            int cidx = -1;
+            for (int cc2 = 0; cc2 < ncolors && cidx < 0; cc2++) { bool ok = true; for (int i : rows[j]) if (occ[cc2][i]) { ok = false; break; } if (ok) cidx = cc2; }
+            if (cidx < 0) { cidx = ncolors++; occ.emplace_back(n, 0); }
+            color[j] = cidx; for (int i : rows[j]) occ[cidx][i] = 1;
+        }
+        rowsptr.assign(n + 1, 0); rowsidx.clear();
+        for (int j = 0; j < n; j++) { for (int i : rows[j]) rowsidx.push_back(i); rowsptr[j + 1] = (int)rowsidx.size(); }
+    }
+    void jac(double t, const double*, double* J) {
+        if (ncolors == 0) discover(t);
         double y[5]; spl.eval(t, y);
         Bg<double> c; bg_chain(D, y, c, false);
-        for (int j = 0; j < n; j++) {
-            std::fill(e.begin(), e.end(), 0.0); e[j] = 1;
+        std::fill(J, J + (size_t)n * n, 0.0);
+        for (int cc2 = 0; cc2 < ncolors; cc2++) {
+            for (int j = 0; j < n; j++) e[j] = (color[j] == cc2) ? 1.0 : 0.0;
             pt_rhs<double>(D, c, t, k, e.data(), col.data());
-            for (int i = 0; i < n; i++) J[i * n + j] = col[i];
+            for (int j = 0; j < n; j++) if (color[j] == cc2) for (int q = rowsptr[j]; q < rowsptr[j + 1]; q++) J[(size_t)rowsidx[q] * n + j] = col[rowsidx[q]];
         }
     }
     void tgrad(double t, const double* u, double* dT) { // ∂f/∂τ at fixed u through the spline (complex step == ForwardDiff dual)
@@ -824,10 +914,34 @@ void sbo_sources(const SboParams* p, int nb, const double* t, const double* y, c
         for (int j = 0; j < nt; j++) cmb_sources(D, spl, taus[j], ks[i], u + ((size_t)i * nt + j) * D.N, out + ((size_t)i * nt + j) * 6);
 }
 
+// Timing of the per-step building blocks of the CPU path (diagnostic for the reported CPU baseline): out[0..5] = µs per call of
+// f, jac, tgrad, LU factor, solve, and the number of colours used by the compressed Jacobian probing.
+void sbo_bench_parts(const SboParams* p, int nb, const double* t, const double* y, const double* dy, double tau, double k, double h, int reps, double* out) {
+    Derived D; derive(*p, D); Spline spl{nb, t, y, dy}; PtSys sys(D, spl, k);
+    int n = sys.n; Rodas5P<PtSys> R(sys);
+    std::vector<double> u(n, 0.1), du(n), J((size_t)n * n), b(n, 1.0);
+    auto now = [] { return omp_get_wtime(); };
+    sys.jac(tau, u.data(), J.data());
+    double t0 = now(); for (int i = 0; i < reps; i++) sys.f(tau, u.data(), du.data()); out[0] = (now() - t0) / reps * 1e6;
+    t0 = now(); for (int i = 0; i < reps; i++) sys.jac(tau, u.data(), J.data()); out[1] = (now() - t0) / reps * 1e6;
+    t0 = now(); for (int i = 0; i < reps; i++) sys.tgrad(tau, u.data(), du.data()); out[2] = (now() - t0) / reps * 1e6;
+    double dg = 1 / (R5::gamma * h);
+    t0 = now();
+    for (int r = 0; r < reps; r++) {
+        for (int i = 0; i < n; i++) { const double* Wi = &J[(size_t)R.perm[i] * n]; double* Pi = &R.Wp[(size_t)i * n]; for (int j = 0; j < n; j++) Pi[j] = -Wi[R.perm[j]]; Pi[i] += dg; }
+        R.lu.factor(n, R.Wp.data());
+    }
+    out[3] = (now() - t0) / reps * 1e6;
+    t0 = now(); for (int i = 0; i < reps; i++) { R.solve_inplace(b.data()); b[0] = 1; } out[4] = (now() - t0) / reps * 1e6;
+    out[5] = sys.ncolors;
+    out[6] = (double)(R.lu.Lidx.size() + R.lu.Uidx.size() + n);
+}
+
 // Generic Rodas5P self-test hooks (used by tests to re-verify the recalled tableau):
 // integrates y' = f(t,y) for the 2-D nonlinear test problem with fixed steps and returns y(tend).
 struct TestSys {
     int n = 2; double lam;
+    void ordering(int*) {}
     void f(double t, const double* u, double* du) { du[0] = -lam * (u[0] - std::cos(t)) - std::sin(t) + 0.1 * u[1] * u[1] - 0.1 * std::sin(2 * t) * std::sin(2 * t); du[1] = 2 * std::cos(2 * t) + (u[0] - std::cos(t)); }
     void jac(double, const double* u, double* J) { J[0] = -lam; J[1] = 0.2 * u[1]; J[2] = 1; J[3] = 0; }
     void tgrad(double t, const double*, double* dT) { dT[0] = -lam * std::sin(t) - std::cos(t) - 0.4 * std::sin(2 * t) * std::cos(2 * t); dT[1] = -4 * std::sin(2 * t) + std::sin(t); }
