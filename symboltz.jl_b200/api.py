@@ -93,7 +93,18 @@ def parameters_Planck18(M):
     return p
 
 
+_quad_cache = {}
+
+
 def momentum_quadrature(N, L=100.0):
+    """Cached wrapper of _momentum_quadrature (the rule depends only on N)."""
+    if (N, L) not in _quad_cache:
+        _quad_cache[(N, L)] = _momentum_quadrature(N, L)
+    xs, Ws = _quad_cache[(N, L)]
+    return xs.copy(), Ws.copy()
+
+
+def _momentum_quadrature(N, L=100.0):
     """Gauss nodes/weights for ∫dx x² f0(x) g(x), f0 = 1/(eˣ+1), in u = 1/(1+x/L) (src/models/neutrinos.jl:55-60).
     Lanczos tridiagonalisation of the discretised measure + Golub-Welsch."""
     t, w = np.polynomial.legendre.leggauss(1500)
@@ -821,3 +832,50 @@ class CMBPlan:
         self.upload()
         self.run()
         return self.download()
+
+
+def spectrum_matter_sweep(prob, names, thetas, ks, nstreams=8, nthreads=None, kτini=1e-2, τinimax=1e-4, reltol=1e-5, abstol=1e-5, return_info=False):
+    """P(k) for a batch of cosmologies θ ↦ parameter_updater(prob, names)(θ) (BASELINE config 4: emulator / MCMC sweeps;
+    the reference runs a serial outer loop of `spectrum_matter(probgen(θ), ks)`, docs/src/forecasting.md:56-59).
+    Host background solves run on a thread pool (the ctypes calls release the GIL); every cosmology's perturbation solve is an
+    independent launch round-robined over `nstreams` CUDA streams, so several cosmologies share the GPU concurrently.
+    thetas: [ncosmo, len(names)].  Returns P[ncosmo, nk] (NaN rows where the background failed)."""
+    import concurrent.futures as cf
+    import os
+    _require_cuda()
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    ks = np.ascontiguousarray(ks, dtype=np.float64)
+    upd = parameter_updater(prob, names)
+    nthreads = nthreads or os.cpu_count()
+
+    def host(theta):
+        p = upd(theta)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return p, solvebg(p)
+
+    streams = [torch.cuda.Stream() for _ in range(nstreams)]
+    out = np.full((len(thetas), len(ks)), np.nan)
+    pending, nfail = [], 0
+    f = lambda k: min(kτini / k, τinimax) if k > 0 else τinimax
+    with cf.ThreadPoolExecutor(nthreads) as pool:
+        for i, (p, bg) in enumerate(pool.map(host, thetas)):
+            if not bg.success:
+                nfail += 1
+                continue
+            with torch.cuda.stream(streams[i % nstreams]):
+                sol = solvept(p, bg, ks, ptivini=f, reltol=reltol, abstol=abstol, warn=False, sync=False)
+                d = bg.device()
+                dm = torch.empty(len(ks), dtype=torch.float64, device=sol.d_uend.device)
+                rc = p.lib.sbm_delta_m(_cptr(d["P"]), C.c_int(len(bg.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_double(bg.tau0), C.c_int(len(ks)), _cptr(sol.d_ks), _cptr(sol.d_uend), _cptr(dm), _stream())
+                if rc != 0:
+                    raise RuntimeError(f"sbm_delta_m failed with code {rc}")
+            pending.append((i, p, sol, dm))
+    torch.cuda.synchronize()
+    nbad = 0
+    for i, p, sol, dm in pending:
+        out[i] = spectrum_primordial(ks, p) * dm.cpu().numpy() ** 2
+        nbad += int((sol.retcode != 0).sum())
+    if return_info:
+        return out, dict(background_failures=nfail, mode_failures=nbad)
+    return out
