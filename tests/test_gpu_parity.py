@@ -36,7 +36,7 @@ def test_native_library_is_loaded(sb, prob5):
 
 def test_pk_golden_and_oracle(sb, oracle, prob5, bg5, obg_same):
     """P(k) on the 516 CLASS wavenumbers (lmax = 5): reference criterion rtol 1e-3 in the 2-norm (runtests.jl:876);
-    vs oracle: median 1e-6, every mode within 2e-3 (default-tolerance chaos bound), step counts within 1%."""
+    vs oracle: median 1e-8 and every mode within 1e-4 (the north-star tolerance; measured 4e-7), step counts within 1%."""
     d = np.loadtxt(os.path.join(GOLDEN, "class_Pk.dat"))
     ks, Pc = d[:, 0], d[:, 1]
     P, sol = sb.spectrum_matter(prob5, ks, bgsol=bg5, return_solution=True)
@@ -44,7 +44,7 @@ def test_pk_golden_and_oracle(sb, oracle, prob5, bg5, obg_same):
     assert np.linalg.norm(P - Pc) <= 1e-3 * np.linalg.norm(Pc)
     Po, osol = oracle.spectrum_matter(obg_same, ks)
     rel = np.abs(P / Po - 1)
-    assert np.median(rel) < 1e-6 and rel.max() < 2e-3
+    assert np.median(rel) < 1e-8 and rel.max() < 1e-4
     assert np.abs(sol.stats[:, 0] - osol["stats"][:, 0]).max() <= 0.01 * osol["stats"][:, 0].max()
     assert (sol.stats[:200, 0] == osol["stats"][:200, 0]).mean() > 0.9  # smooth low-k modes: identical step sequences
 
@@ -164,7 +164,8 @@ def test_los_and_cl_match_oracle_given_same_sources(sb, oracle, prob5, bg5, jl12
 
 def test_cmb_spectra_vs_class_and_oracle(sb, oracle, prob5, bg5, obg_same):
     """Full pipeline at the reference's own test configuration (runtests.jl:879-885): D_l TT, EE vs CLASS at rtol 2e-3 (2-norm);
-    vs the oracle pipeline: 2-norm 1e-3, TE relative to its maximum 2e-3 (default-tolerance chaos bound)."""
+    vs the oracle pipeline at default tolerances: TT and EE element-wise within 3e-4 (measured 1.0e-4 / 7e-6), TE within 1e-4 of its
+    maximum (it crosses zero), 2-norms within 1e-4."""
     d = np.loadtxt(os.path.join(GOLDEN, "class_Cl.dat"))
     lc, TT, EE = d[:, 0], d[:, 1], d[:, 2]
     ls = np.unique(np.round(np.exp(np.linspace(np.log(lc[0]), np.log(lc[-1]), 200))).astype(int))
@@ -177,8 +178,9 @@ def test_cmb_spectra_vs_class_and_oracle(sb, oracle, prob5, bg5, obg_same):
     ojl = oracle.SphericalBesselCache(ls, xcut=2e3 * bg5.tau0 * 1.001)
     oDl = oracle.spectrum_cmb(["TT", "EE", "TE"], obg_same, ojl, normalization="Dl")
     for i in range(3):
-        assert np.linalg.norm(Dl[:, i] - oDl[:, i]) <= 1e-3 * np.linalg.norm(oDl[:, i])
-    assert np.abs(Dl[:, 2] - oDl[:, 2]).max() <= 2e-3 * np.abs(oDl[:, 2]).max()
+        assert np.linalg.norm(Dl[:, i] - oDl[:, i]) <= 1e-4 * np.linalg.norm(oDl[:, i])
+    assert np.abs(Dl[:, :2] / oDl[:, :2] - 1).max() < 3e-4
+    assert np.abs(Dl[:, 2] - oDl[:, 2]).max() <= 1e-4 * np.abs(oDl[:, 2]).max()
 
 
 def test_full_size_properties(sb):
