@@ -219,7 +219,20 @@ def test_w0wa_and_massive_neutrino_variants_run(sb, oracle):
     assert sol.success
     obg = oracle.Background.from_knots(oracle.planck18(lmax=10, model=1, w0=pars["w0"], wa=pars["wa"], cs2X=pars["cs2"]), bg.t, bg.y, bg.dy, bg.tau0, bg.kappa0)
     Po, _ = oracle.spectrum_matter(obg, ks)
-    assert np.abs(P / Po - 1).max() < 2e-3
+    assert np.abs(P / Po - 1).max() < 1e-4
+    # config 3: larger momentum grid (nx = 8 -> N = 126 unknowns, nnz(W) = 765 as the survey predicts), heavier neutrinos
+    M = sb.ΛCDM(lmax=10, nx=8)
+    pars = sb.parameters_Planck18(M)
+    pars["m_eV"] = 0.06
+    prob = sb.CosmologyProblem(M, pars)
+    assert prob.N == 126 and prob.info["nnz_full"] == 765
+    bg = sb.solvebg(prob)
+    ks = sb.loggrid(1e-4, 1.0, length=40) / sb.k0
+    P, sol = sb.spectrum_matter(prob, ks, bgsol=bg, return_solution=True)
+    assert sol.success
+    obg = oracle.Background.from_knots(oracle.planck18(lmax=10, nx=8, m_eV=0.06), bg.t, bg.y, bg.dy, bg.tau0, bg.kappa0)
+    Po, _ = oracle.spectrum_matter(obg, ks)
+    assert np.abs(P / Po - 1).max() < 1e-4
 
 
 def test_parameter_sweep_matches_single_calls(sb):
