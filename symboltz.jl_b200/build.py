@@ -72,8 +72,8 @@ def build_los(force=False, verbose=False):
     return so
 
 
-# BASELINE configs: 1/2 (ΛCDM lmax 10), the reference test fixture (lmax 5), 4 (w0waCDM), 3 (massive-ν momentum grids nx = 8)
-DEFAULT_MODELS = [dict(lmax=10, nx=4, w0wa=False), dict(lmax=5, nx=4, w0wa=False), dict(lmax=10, nx=4, w0wa=True), dict(lmax=10, nx=8, w0wa=False)]
+# BASELINE configs: 1/2 (ΛCDM lmax 10), the reference test fixture (lmax 5), 4 (w0waCDM), 3 (massive-ν momentum grids nx = 8), the reference's "High lmax" test (32)
+DEFAULT_MODELS = [dict(lmax=10, nx=4, w0wa=False), dict(lmax=5, nx=4, w0wa=False), dict(lmax=10, nx=4, w0wa=True), dict(lmax=10, nx=8, w0wa=False), dict(lmax=32, nx=4, w0wa=False)]
 
 
 def build_all(force=False, verbose=False):

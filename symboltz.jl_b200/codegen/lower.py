@@ -406,13 +406,18 @@ def generate(m: Model):
                 nat += paths[pid]
     for b in dense_blocks:
         nat += b
-    assert sorted(nat) == list(range(N)) and N <= 254
+    assert sorted(nat) == list(range(N)) and N <= 1022
+    # index width of the packed schedules: 8 bits when everything fits (cheaper byte extraction on the device), else 10
+    BITS = 8 if (N <= 254 and NB <= 255 and sum(len(b) ** 2 for b in L.blocks) <= 255) else 10
+    HB = 8 if BITS == 8 else 16          # width of the two-field words
+    KSH = 2 * BITS                       # role kind position in the ELL index word
+    TSH = 20 if BITS == 8 else 22        # role target position
     inv = [0] * N
     for new_i, old_i in enumerate(nat):
         inv[old_i] = new_i
     R = (N + 31) // 32
     WD = max(len(r) for r in L.rows)
-    assert NB <= 255 and sum(len(b) ** 2 for b in L.blocks) <= 255
+    assert NB <= 1023 and sum(len(b) ** 2 for b in L.blocks) <= 1023
     ell_coef = [0.0] * (R * WD * 32)
     ell_idx = [0] * (R * WD * 32)
     for i in range(N):
@@ -426,7 +431,7 @@ def generate(m: Model):
                 bb, pos = L.blk_of[i]
                 tgt = boff[bb] + pos * len(L.blocks[bb]) + ri
             ell_coef[(r * WD + w) * 32 + lane] = c
-            ell_idx[(r * WD + w) * 32 + lane] = inv[j] | (b << 8) | (rk << 16) | (tgt << 20)
+            ell_idx[(r * WD + w) * 32 + lane] = inv[j] | (b << BITS) | (rk << KSH) | (tgt << TSH)
     pq_coef = [0.0] * (R * 2 * 32)
     pq_idx = [0] * (R * 32)
     for (i, c, b) in L.hub["p"]:
@@ -436,7 +441,7 @@ def generate(m: Model):
     for (i, c, b) in L.hub["q"]:
         ni = inv[i]
         pq_coef[((ni // 32) * 2 + 1) * 32 + ni % 32] = c
-        pq_idx[(ni // 32) * 32 + ni % 32] |= b << 8
+        pq_idx[(ni // 32) * 32 + ni % 32] |= b << HB
     TPH = (len(L.hub["phi"]) + 31) // 32
     TPS = (len(L.hub["psi"]) + 31) // 32
 
@@ -444,13 +449,17 @@ def generate(m: Model):
         cf, ix = [0.0] * (T * 32), [0] * (T * 32)
         for t, (i, c, b) in enumerate(lst):
             cf[(t // 32) * 32 + t % 32] = c
-            ix[(t // 32) * 32 + t % 32] = inv[i] | (b << 8)
+            ix[(t // 32) * 32 + t % 32] = inv[i] | (b << HB)
         return cf, ix
     phc, phi_ = _terms(L.hub["phi"], TPH)
     psc, psi_ = _terms(L.hub["psi"], TPS)
     # path descriptors [phase][round][lane]: head = start | len<<8 | parent_of_last<<16 (255: root); kids = children of the first vertex
     p_head = [0] * (NPH * PR * 32)
-    p_kids = [0xFFFFFFFF] * (NPH * PR * 32)
+    NONE = (1 << BITS) - 1
+    NOKIDS = NONE | (NONE << BITS) | (NONE << (2 * BITS))
+    NOPAR = 255 if BITS == 8 else 4095
+    LSH, PSH = (8, 16) if BITS == 8 else (12, 20)
+    p_kids = [NOKIDS] * (NPH * PR * 32)
     for ph in range(NPH):
         mine = [i for i, q in enumerate(pphase) if q == ph]
         for q, pid in enumerate(mine):
@@ -459,26 +468,26 @@ def generate(m: Model):
             start = inv[p[0]]
             assert [inv[v] for v in p] == list(range(start, start + len(p)))
             par = L.parent[p[-1]]
-            par = 255 if par < 0 else inv[par]
-            p_head[(ph * PR + rd) * 32 + lane] = start | (len(p) << 8) | (par << 16)
+            par = NOPAR if par < 0 else inv[par]
+            p_head[(ph * PR + rd) * 32 + lane] = start | (len(p) << LSH) | (par << PSH)
             kids = [inv[c] for c in L.children[p[0]]]
-            assert len(kids) <= 4
-            kids += [255] * (4 - len(kids))
-            p_kids[(ph * PR + rd) * 32 + lane] = kids[0] | (kids[1] << 8) | (kids[2] << 16) | (kids[3] << 24)
-    d_kids = [0xFFFFFFFF] * 32
+            assert len(kids) <= 3
+            kids += [NONE] * (3 - len(kids))
+            p_kids[(ph * PR + rd) * 32 + lane] = kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
+    d_kids = [NOKIDS] * 32
     for bi, b in enumerate(dense_blocks):
         for pos, v in enumerate(b):
             kids = [inv[c] for c in L.children[v]]
-            assert len(kids) <= 4
-            kids += [255] * (4 - len(kids))
-            d_kids[bi * 8 + pos] = kids[0] | (kids[1] << 8) | (kids[2] << 16) | (kids[3] << 24)
+            assert len(kids) <= 3
+            kids += [NONE] * (3 - len(kids))
+            d_kids[bi * 8 + pos] = kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
     assert len(dense_blocks) <= 4 and all(len(b) <= 8 for b in dense_blocks)
     dbn = [len(b) for b in dense_blocks]
     dboff = [boff[L.blocks.index(b)] for b in dense_blocks]
     dbstart = [inv[b[0]] for b in dense_blocks]
     for b in dense_blocks:
         assert [inv[v] for v in b] == list(range(inv[b[0]], inv[b[0]] + len(b)))
-    for name, val in [("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NDENSE", len(dense_blocks)), ("SB_NPH", NPH), ("SB_PL", PL), ("SB_PR", PR)]:
+    for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NDENSE", len(dense_blocks)), ("SB_NPH", NPH), ("SB_PL", PL), ("SB_PR", PR)]:
         W(f"#define {name} {val}")
     W(_arr("short", "sb_nat", nat))
     W(_arr("short", "sb_newidx", inv))
@@ -496,7 +505,7 @@ def generate(m: Model):
     W(_arr("int", "sb_dense_n", dbn))
     W(_arr("int", "sb_dense_off", dboff))
     W(_arr("int", "sb_dense_start", dbstart))
-    W(_arr("unsigned int", "sb_basis_pack", [(b[0] | ((b[1] + 3) << 8)) for b in L.basis], "{}u"))
+    W(_arr("unsigned int", "sb_basis_pack", [(b[0] | ((b[1] + 3) << HB)) for b in L.basis], "{}u"))
 
     flops = {}
     # ---------------- β_m(τ) and dβ_m/dτ given dy/dτ = yp

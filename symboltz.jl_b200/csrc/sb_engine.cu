@@ -304,6 +304,34 @@ struct SbSolveArgs {
 #define SB_WARPS_PER_CTA 1
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
+// packed schedule fields (generator: lower.py).  SB_IDXBITS = 8 when N <= 254 and NB <= 255 (byte extraction), else 10 (N <= 1022).
+#if SB_IDXBITS == 8
+#define SB_E_COL(ix) ((ix) & 255u)
+#define SB_E_B(ix) (((ix) >> 8) & 255u)
+#define SB_E_KIND(ix) (((ix) >> 16) & 15u)
+#define SB_E_TGT(ix) ((ix) >> 20)
+#define SB_LO16(v) ((v) & 255u)
+#define SB_HI16(v) (((v) >> 8) & 255u)
+#define SB_P_START(v) ((int)((v) & 255u))
+#define SB_P_LEN(v) ((int)(((v) >> 8) & 255u))
+#define SB_P_PAR(v) ((int)(((v) >> 16) & 255u))
+#define SB_KID(v, c) ((int)(((v) >> (8 * (c))) & 255u))
+#define SB_NOKID 255
+#define SB_NOPAR 255
+#else
+#define SB_E_COL(ix) ((ix) & 1023u)
+#define SB_E_B(ix) (((ix) >> 10) & 1023u)
+#define SB_E_KIND(ix) (((ix) >> 20) & 3u)
+#define SB_E_TGT(ix) ((ix) >> 22)
+#define SB_LO16(v) ((v) & 0xFFFFu)
+#define SB_HI16(v) ((v) >> 16)
+#define SB_P_START(v) ((int)((v) & 4095u))
+#define SB_P_LEN(v) ((int)(((v) >> 12) & 255u))
+#define SB_P_PAR(v) ((int)((v) >> 20))
+#define SB_KID(v, c) ((int)(((v) >> (10 * (c))) & 1023u))
+#define SB_NOKID 1023
+#define SB_NOPAR 4095
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -364,9 +392,9 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
     for (int r = 0; r < SB_NBR; r++) {
         int m = r * 32 + lane;
         if (m < SB_NB) {
-            int be = S.bp[r] & 255;
+            int be = SB_LO16(S.bp[r]);
             double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n1 + be), d1 = __ldg(n1 + SB_NBETA + be);
-            double kk = kp[(S.bp[r] >> 8) & 255];
+            double kk = kp[SB_HI16(S.bp[r])];
             b[m] = kk * (h00 * v0 + h10 * d0 + h01 * v1 + h11 * d1);
             if (bd) bd[m] = kk * (6 * w * w1 * (v0 - v1) / hs + (3 * w - 1) * w1 * d0 + w * (3 * w - 2) * d1); // derivative of the Hermite cubic
         }
@@ -378,15 +406,15 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane) {
     double sphi = 0, spsi = 0;
 #pragma unroll
-    for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[(S.phi[t] >> 8) & 255] * U[S.phi[t] & 255];
+    for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[SB_HI16(S.phi[t])] * U[SB_LO16(S.phi[t])];
 #pragma unroll
-    for (int t = 0; t < SB_TPS; t++) spsi += S.psc[t] * b[(S.psi[t] >> 8) & 255] * U[S.psi[t] & 255];
+    for (int t = 0; t < SB_TPS; t++) spsi += S.psc[t] * b[SB_HI16(S.psi[t])] * U[SB_LO16(S.psi[t])];
     sphi = warp_sum(sphi); spsi = warp_sum(spsi);
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
-        double acc = S.pqc[2 * r] * b[S.pqi[r] & 255] * sphi + S.pqc[2 * r + 1] * b[(S.pqi[r] >> 8) & 255] * spsi;
+        double acc = S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
 #pragma unroll
-        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * b[(S.ei[e] >> 8) & 255] * U[S.ei[e] & 255]; }
+        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
         const int i = r * 32 + lane;
         if (i < SB_N) out[i] = acc;
     }
@@ -396,16 +424,16 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
 __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, const double* bd, const double* U, double* out, int lane) {
     double sphi = 0, spsi = 0, sphid = 0, spsid = 0;
 #pragma unroll
-    for (int t = 0; t < SB_TPH; t++) { double cu = S.phc[t] * U[S.phi[t] & 255]; sphi += cu * b[(S.phi[t] >> 8) & 255]; sphid += cu * bd[(S.phi[t] >> 8) & 255]; }
+    for (int t = 0; t < SB_TPH; t++) { double cu = S.phc[t] * U[SB_LO16(S.phi[t])]; sphi += cu * b[SB_HI16(S.phi[t])]; sphid += cu * bd[SB_HI16(S.phi[t])]; }
 #pragma unroll
-    for (int t = 0; t < SB_TPS; t++) { double cu = S.psc[t] * U[S.psi[t] & 255]; spsi += cu * b[(S.psi[t] >> 8) & 255]; spsid += cu * bd[(S.psi[t] >> 8) & 255]; }
+    for (int t = 0; t < SB_TPS; t++) { double cu = S.psc[t] * U[SB_LO16(S.psi[t])]; spsi += cu * b[SB_HI16(S.psi[t])]; spsid += cu * bd[SB_HI16(S.psi[t])]; }
     sphi = warp_sum(sphi); spsi = warp_sum(spsi); sphid = warp_sum(sphid); spsid = warp_sum(spsid);
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
-        const int pb = S.pqi[r] & 255, qb = (S.pqi[r] >> 8) & 255;
+        const int pb = SB_LO16(S.pqi[r]), qb = SB_HI16(S.pqi[r]);
         double acc = S.pqc[2 * r] * (bd[pb] * sphi + b[pb] * sphid) + S.pqc[2 * r + 1] * (bd[qb] * spsi + b[qb] * spsid);
 #pragma unroll
-        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * bd[(S.ei[e] >> 8) & 255] * U[S.ei[e] & 255]; }
+        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * bd[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
         const int i = r * 32 + lane;
         if (i < SB_N) out[i] = acc;
     }
@@ -429,8 +457,8 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         for (int w = 0; w < SB_WD; w++) {
             const int e = r * SB_WD + w;
             const unsigned ix = S.ei[e];
-            const double v = -S.ec[e] * b[(ix >> 8) & 255];
-            const int kind = (ix >> 16) & 15, tgt = ix >> 20;
+            const double v = -S.ec[e] * b[SB_E_B(ix)];
+            const int kind = SB_E_KIND(ix), tgt = SB_E_TGT(ix);
             if (kind == 0) dacc += v;
             else if (kind == 1) uacc += v;
             else if (S.ec[e] != 0.0) { if (kind == 2) mm[tgt] += v; else blk[tgt] += v; }
@@ -443,13 +471,13 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255;
+            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]);
             if (len > 0) {
                 double* dip = di + start; double* mmp = mm + start; const double* upp = up + start;
                 double dj = dip[0];
                 if (ph > 0) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
+                    for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.pk[q], c); if (ch != SB_NOKID) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
                 }
                 double dinv = 1.0 / dj;
                 dip[0] = dinv;
@@ -473,7 +501,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             const int v = sb_dense_start[bb] + i;
             double dj = di[v];
 #pragma unroll
-            for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
+            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
             di[v] = dj;
         }
         __syncwarp();
@@ -528,7 +556,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255;
+            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]);
             if (len > 0) {
                 const double* mmp = mm + start;
 #pragma unroll
@@ -538,7 +566,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
                     double acc = rp[0];
                     if (ph > 0) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) { const int ch = (S.pk[q] >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * rr[a][ch]; }
+                        for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.pk[q], c); if (ch != SB_NOKID) acc -= mm[ch] * rr[a][ch]; }
                     }
                     av[0] = acc;
 #pragma unroll
@@ -559,7 +587,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             for (int a = 0; a < NR; a++) {
                 double acc = rr[a][vstart + i];
 #pragma unroll
-                for (int c = 0; c < 4; c++) { const int ch = (S.dk >> (8 * c)) & 255; if (ch != 255) acc -= mm[ch] * rr[a][ch]; }
+                for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) acc -= mm[ch] * rr[a][ch]; }
                 rr[a][vstart + i] = acc;
             }
         }
@@ -579,14 +607,14 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
 #pragma unroll
         for (int rd = 0; rd < SB_PR; rd++) {
             const int q = ph * SB_PR + rd;
-            const int start = S.ph[q] & 255, len = (S.ph[q] >> 8) & 255, par = (S.ph[q] >> 16) & 255;
+            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]), par = SB_P_PAR(S.ph[q]);
             if (len > 0) {
                 const double *upp = up + start, *dip = di + start;
 #pragma unroll
                 for (int a = 0; a < NR; a++) {
                     double* rp = rr[a] + start;
                     double xs[SB_PL];
-                    double xv = (par == 255) ? 0.0 : rr[a][par];
+                    double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
 #pragma unroll
                     for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, rp[pos] * dip[pos]); xs[pos] = xv; }
 #pragma unroll
@@ -601,9 +629,9 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
 __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, const double* r, double& s1, double& s2, int lane) {
     double a = 0, c = 0;
 #pragma unroll
-    for (int t = 0; t < SB_TPH; t++) a += S.phc[t] * b[(S.phi[t] >> 8) & 255] * r[S.phi[t] & 255];
+    for (int t = 0; t < SB_TPH; t++) a += S.phc[t] * b[SB_HI16(S.phi[t])] * r[SB_LO16(S.phi[t])];
 #pragma unroll
-    for (int t = 0; t < SB_TPS; t++) c += S.psc[t] * b[(S.psi[t] >> 8) & 255] * r[S.psi[t] & 255];
+    for (int t = 0; t < SB_TPS; t++) c += S.psc[t] * b[SB_HI16(S.psi[t])] * r[SB_LO16(S.psi[t])];
     s1 = warp_sum(a); s2 = warp_sum(c);
 }
 
@@ -688,7 +716,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
 #pragma unroll
                 for (int r = 0; r < SB_R; r++) {
                     const int i = r * 32 + lane;
-                    if (i < SB_N) { Zp[i] = S.pqc[2 * r] * bs[S.pqi[r] & 255]; Zq[i] = S.pqc[2 * r + 1] * bs[(S.pqi[r] >> 8) & 255]; }
+                    if (i < SB_N) { Zp[i] = S.pqc[2 * r] * bs[SB_LO16(S.pqi[r])]; Zq[i] = S.pqc[2 * r + 1] * bs[SB_HI16(S.pqi[r])]; }
                 }
                 __syncwarp();
                 { double* const zz[2] = {Zp, Zq}; sb_bsolve<2>(S, zz, di, up, mm, blk, lane); }

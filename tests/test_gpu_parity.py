@@ -253,3 +253,33 @@ def test_parameter_sweep_matches_single_calls(sb):
     th2 = th[:1].copy(); th2[0, 1] *= 1.1
     P2 = sb.spectrum_matter_sweep(prob, names, th2, ks)
     assert P2[0, -1] > P[0, -1]
+
+
+def test_high_lmax(sb, oracle):
+    """runtests.jl:808-812 ("High lmax"): ΛCDM(lmax = 32) (N = 236 unknowns; 10-bit schedule indices) solves k = 1e-1 … 1e3 successfully
+    and matches the oracle's P(k)."""
+    M = sb.ΛCDM(lmax=32)
+    prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+    assert prob.N == 236
+    ks = np.array([1e-1, 1e0, 1e1, 1e2, 1e3])
+    sol = sb.solve(prob, ks)
+    assert sb.issuccess(sol)
+    P = sb.spectrum_matter(prob, ks, bgsol=sol.bg)
+    obg = oracle.Background.from_knots(oracle.planck18(lmax=32), sol.bg.t, sol.bg.y, sol.bg.dy, sol.bg.tau0, sol.bg.kappa0)
+    Po, _ = oracle.spectrum_matter(obg, ks)
+    assert np.abs(P / Po - 1).max() < 1e-4
+
+
+def test_stability_latin_hypercube(sb):
+    """runtests.jl:507-546 ("Stability"): ±50 % Latin hypercube around the fiducial, ks = [1, 10, 100, 1000]: 100 % success,
+    for ΛCDM and w0waCDM (40 samples each here; scripts/stability_check.py runs the reference's 100)."""
+    for M in (sb.ΛCDM(lmax=10), sb.w0waCDM(lmax=10)):
+        pars = sb.parameters_Planck18(M)
+        prob = sb.CosmologyProblem(M, pars)
+        names = ["h", "Omega_c", "Omega_b", "YHe", "Neff", "m_eV", "T0"]
+        fid = np.array([pars[k] for k in names])
+        n = 40
+        rng = np.random.default_rng(1)
+        u = (rng.permuted(np.tile(np.arange(n), (len(names), 1)), axis=1).T + rng.random((n, len(names)))) / n
+        P, info = sb.spectrum_matter_sweep(prob, names, fid * (0.5 + u), np.array([1.0, 10.0, 100.0, 1000.0]), return_info=True)
+        assert info == dict(background_failures=0, mode_failures=0) and np.isfinite(P).all() and (P > 0).all()
