@@ -299,7 +299,7 @@ struct SbSolveArgs {
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
 #define SB_SM_BLK (SB_SM_BD + SB_NB)
 #define SB_SM_KP (SB_SM_BLK + SB_BLKSTORE)
-#define SB_SM_DOUBLES (SB_SM_KP + 8)
+#define SB_SM_DOUBLES (SB_SM_KP + 8 + 24)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
@@ -402,8 +402,46 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
     return j;
 }
 
-// out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU
-__device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane) {
+// Batched look-up of the basis at the stage times of one Rosenbrock attempt: slots 1..5 = t + c_s·dt (and, if with0, slot 0 = t
+// together with ḃ(t)).  Lanes 0..5 locate their slot's table node in parallel and publish (node, w, hs, τ) through shared memory;
+// then all lanes sweep the (slot, basis) items, so that every L2 access of the attempt is in flight at once.
+__device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x4*/, int lane) {
+    int jend = jt;
+    if (lane < 6) {
+        const double tau = t + ((lane == 0) ? 0.0 : cc[lane]) * dt;
+        int j = jt;
+        while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
+        const double tj = __ldg(tb.t + j), hs = (__ldg(tb.t + j + 1) - tj) / tb.msub;
+        const double f = (tau - tj) / hs;
+        const int sidx = max(0, min((int)f, tb.msub - 1));
+        slotp[lane * 4 + 0] = __longlong_as_double((long long)j * tb.msub + sidx);
+        slotp[lane * 4 + 1] = f - sidx;
+        slotp[lane * 4 + 2] = hs;
+        slotp[lane * 4 + 3] = tau;
+        jend = j;
+    }
+    jend = __shfl_sync(SB_FULL, jend, 5);
+    __syncwarp();
+    const int s0 = with0 ? 0 : 1;
+    for (int q = s0 * SB_NB + lane; q < 6 * SB_NB; q += SB_WARP) {
+        const int s = q / SB_NB, m = q - s * SB_NB;
+        const long long node = __double_as_longlong(slotp[s * 4 + 0]);
+        const double w = slotp[s * 4 + 1], hs = slotp[s * 4 + 2], w1 = w - 1.0;
+        const unsigned pk = sb_basis_pack[m];
+        const int be = SB_LO16(pk);
+        const double* n0 = tb.tab + (size_t)node * 2 * SB_NBETA;
+        const double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n0 + 2 * SB_NBETA + be), d1 = __ldg(n0 + 3 * SB_NBETA + be);
+        const double kk = kp[SB_HI16(pk)];
+        bs[q] = kk * ((1 + 2 * w) * w1 * w1 * v0 + w * w1 * w1 * hs * d0 + w * w * (3 - 2 * w) * v1 + w * w * w1 * hs * d1);
+        if (s == 0) bdv[m] = kk * (6 * w * w1 * (v0 - v1) / hs + (3 * w - 1) * w1 * d0 + w * (3 * w - 2) * d1);
+    }
+    return jend;
+}
+
+// out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU.
+// FUSE: out = J(b)·U + radd[r] + hd·dT  (the stage right-hand side is assembled in the same pass: one store per row)
+template <bool FUSE>
+__device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane, const double* radd = nullptr, double hd = 0.0, const double* dT = nullptr) {
     double sphi = 0, spsi = 0;
 #pragma unroll
     for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[SB_HI16(S.phi[t])] * U[SB_LO16(S.phi[t])];
@@ -412,10 +450,11 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
     sphi = warp_sum(sphi); spsi = warp_sum(spsi);
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
+        const int i = r * 32 + lane;
         double acc = S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
 #pragma unroll
         for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
-        const int i = r * 32 + lane;
+        if (FUSE) { if (i < SB_N) acc += radd[r] + hd * dT[i]; }
         if (i < SB_N) out[i] = acc;
     }
     __syncwarp();
@@ -681,7 +720,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
             int jt = sb_interval(A.tb, t); // knot interval of the current time
             jt = sb_basis_at(S, A.tb, t, jt, kp, bs, bdv, lane);
             __syncwarp();
-            sb_eval_f(S, bs, u, f0, lane); nf++;
+            sb_eval_f<false>(S, bs, u, f0, lane); nf++;
             sb_eval_dT(S, bs, bdv, u, dT, lane);
             { // automatic initial step (Hairer), order 5
                 double d0 = 0, d1 = 0;
@@ -693,7 +732,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
                 sb_basis_at(S, A.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
                 __syncwarp();
-                sb_eval_f(S, bs + SB_NB, U, K, lane); nf++;
+                sb_eval_f<false>(S, bs + SB_NB, U, K, lane); nf++;
                 double d2 = 0;
                 for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; double r = (K[i] - f0[i]) / sk; d2 += r * r; }
                 d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
@@ -702,15 +741,16 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
                 __syncwarp();
             }
-            int jend = jt; // interval of t + dt after the step (becomes jt on accept)
+            int jend = jt;       // interval of t + dt after the step (becomes jt on accept)
+            bool moved = false;  // t advanced since f0, dT and the slot-0 basis were evaluated
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
-                // basis at the 5 later stage times
-#pragma unroll
-                for (int s = 1; s < 6; s++) { const int js = sb_basis_at(S, A.tb, t + cc[s] * dt, jt, kp, bs + s * SB_NB, nullptr, lane); if (s == 5) jend = js; }
+                // basis at the stage times of this attempt (one batched table look-up)
+                jend = sb_basis_batch(S, A.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
                 __syncwarp();
+                if (moved) { sb_eval_f<false>(S, bs, u, f0, lane); nf++; sb_eval_dT(S, bs, bdv, u, dT, lane); moved = false; }
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
                 sb_factor(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane);
 #pragma unroll
@@ -727,42 +767,43 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
                 const double idet = 1.0 / (m11 * m22 - m12 * m21);
                 const double idt = 1.0 / dt;
-                // 8 stages.  U_s = u + Σ_j a_sj k_j and R_s = Σ_j (C_sj/dt) k_j are accumulated together (each k_j is read once per
-                // stage; coefficients padded with zeros so that the 7-term loops are branch-free and the owned rows interleave)
+                // 8 stages.  Per stage: (A) lane-local: finish k_{s-1} with its pending Woodbury correction and accumulate U_s = u + Σ a_sj k_j,
+                // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve; (D) hub dot products
+                // (the rank-2 correction k_s += Z c is applied lazily in (A) of the next stage: no extra pass, no extra barrier).
+                double c1p = 0, c2p = 0;
                 for (int s = 0; s < 8; s++) {
                     double* ks = K + s * SB_N;
-                    double Racc[SB_R];
+                    const double hd_ = dt * cd[s];
                     if (s > 0) {
-                        double ca[7], cq[7];
+                        double ca[7], cq[7], Racc[SB_R];
 #pragma unroll
                         for (int j = 0; j < 7; j++) { ca[j] = cA[s][j]; cq[j] = cC[s][j] * idt; }
+                        double* kprev = ks - SB_N;
 #pragma unroll
                         for (int r = 0; r < SB_R; r++) {
                             const int i = min(r * 32 + lane, SB_N - 1);
+                            const double kp_ = kprev[i] + Zp[i] * c1p + Zq[i] * c2p;
                             double ua = u[i], ra = 0;
 #pragma unroll
-                            for (int j = 0; j < 7; j++) { const double kj = (j < s) ? K[j * SB_N + i] : 0.0; ua = fma(ca[j], kj, ua); ra = fma(cq[j], kj, ra); }
+                            for (int j = 0; j < 7; j++) { const double kj = (j < s - 1) ? K[j * SB_N + i] : ((j == s - 1) ? kp_ : 0.0); ua = fma(ca[j], kj, ua); ra = fma(cq[j], kj, ra); }
                             Racc[r] = ra;
-                            if (r * 32 + lane < SB_N) U[i] = ua;
+                            if (r * 32 + lane < SB_N) { U[i] = ua; kprev[i] = kp_; }
                         }
                         __syncwarp();
-                        sb_eval_f(S, bs + cslot[s] * SB_NB, U, ks, lane); nf++;
-                    }
-                    const double hd_ = dt * cd[s];
+                        sb_eval_f<true>(S, bs + cslot[s] * SB_NB, U, ks, lane, Racc, hd_, dT); nf++;
+                    } else {
 #pragma unroll
-                    for (int r = 0; r < SB_R; r++) {
-                        const int i = r * 32 + lane;
-                        if (i < SB_N) ks[i] = ((s > 0) ? ks[i] + Racc[r] : f0[i]) + hd_ * dT[i];
+                        for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) ks[i] = f0[i] + hd_ * dT[i]; }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); } nsolve++;
                     double s1, s2;
                     sb_hub_dots(S, bs, ks, s1, s2, lane);
-                    const double c1 = (m22 * s1 - m12 * s2) * idet, c2 = (-m21 * s1 + m11 * s2) * idet;
-#pragma unroll
-                    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) ks[i] += Zp[i] * c1 + Zq[i] * c2; }
-                    __syncwarp();
+                    c1p = (m22 * s1 - m12 * s2) * idet; c2p = (-m21 * s1 + m11 * s2) * idet;
                 }
+#pragma unroll
+                for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) K[7 * SB_N + i] += Zp[i] * c1p + Zq[i] * c2p; }
+                __syncwarp();
                 // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
                 double es = 0; bool bad = false;
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
@@ -797,10 +838,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
                 if (last) break;
                 dt = dtnew;
-                jt = sb_basis_at(S, A.tb, t, jend, kp, bs, bdv, lane);
-                __syncwarp();
-                sb_eval_f(S, bs, u, f0, lane); nf++;
-                sb_eval_dT(S, bs, bdv, u, dT, lane);
+                jt = jend;
+                moved = true;
             }
         }
         for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
