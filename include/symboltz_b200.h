@@ -62,11 +62,12 @@ int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, co
 
 /* CMB source functions at every saved (k, τ) (replaces getsym(prob.pt, Ss) in source_grid's output_func,
  * src/observables/fourier.jl:267-281, with ST and SE of src/models/cosmologies.jl:99-104).
- * dsrcbg: scratch of nt * sbm_srcbg_stride() doubles.  dS[nk][2][nt]; scale_k != 0 returns (k·ST, k²·SE) as fed to the
- * line-of-sight integrator (src/observables/angular.jl:293). */
+ * dsrcbg: scratch of nt * sbm_srcbg_stride() doubles.  dS[nk][nS][nt], nS = 2 (ST, SE) or 3 (+ the lensing source Sψ of
+ * src/models/cosmologies.jl:105, which needs taurec); scale_k != 0 returns (k·ST, k²·SE) as fed to the line-of-sight integrator
+ * (src/observables/angular.jl:293). */
 int sbm_srcbg_stride(void);
 int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, int nk,
-                const double* dks, const double* dusave, double* dS, int scale_k, void* stream);
+                const double* dks, const double* dusave, double* dS, int scale_k, int nS, double taurec, void* stream);
 int sbm_smem_bytes(void);
 
 /* Host-side diagnostics of the generated code (unit tests of the generator; not a solve path). */
@@ -86,11 +87,12 @@ int sbl_bessel_table(int nl, const int* dls, int nxp, double step, double* dy_, 
 
 /* Θ_l(k) for fine-k indices [k0, k0+nk) of dks[nk_total]: optional barycentric interpolation from nc coarse nodes
  * (dBw[nk_total][nc], NULL = sources already on the fine grid), trapezoid weights dwt[nt], χ = dchi[nt], Hermite j_l table,
- * Θ_T/k and Θ_E √((l+2)!/(l−2)!)/k² rescaling.  dSc[nc or nk_total][2][nt]; dTheta[2][nl][nk_total].
+ * Θ_T/k and Θ_E √((l+2)!/(l−2)!)/k² rescaling; with nS = 3 the third (lensing ψ) source uses the Limber approximation for
+ * l >= l_limber (src/observables/angular.jl:155-178).  dSc[nc or nk_total][nS][nt]; dTheta[nS][nl][nk_total].
  * (replaces source_kinterp, src/observables/fourier.jl:232-247; los_integrate, src/observables/angular.jl:109-152;
  * the rescaling of src/observables/angular.jl:301-306) */
-int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nt, const double* dchi, const double* dwt, int nl,
-            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, void* stream);
+int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nS, int nt, const double* dchi, const double* dwt, int nl,
+            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, int l_limber, void* stream);
 
 /* C_l^{AB} = Σ_{k in [k0,k1)} c_k Θ^A_l(k) Θ^B_l(k), c_k = w_k (2/π) k² P0(k) with w_k the natural-cubic-spline integration
  * weights through (0,0) + ks (host-computed).  dCl[nmodes][nl].

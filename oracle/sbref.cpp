@@ -794,8 +794,8 @@ static double delta_m(const Derived& D, const Spline& spl, double tau, double k,
 }
 
 // CMB sources at one (τ,k) from the state u, via order-3 jets along the flow (cosmologies.jl:99-104).
-// out = {ST, SE, ST_SW, ST_ISW, ST_Doppler, ST_polarization}
-static void cmb_sources(const Derived& D, const Spline& spl, double tau, double k, const double* u0, double* out) {
+// out = {ST, SE, ST_SW, ST_ISW, ST_Doppler, ST_polarization, Sψ};  Sψ = −(Ψ+Φ)(τ−τrec)/(τ0−τrec)/(τ0−τ) for τ ≥ τrec (cosmologies.jl:105)
+static void cmb_sources(const Derived& D, const Spline& spl, double taurec, double tau, double k, const double* u0, double* out) {
     const int n = D.N;
     Jet tj(tau); tj.c[1] = 1;
     // background jets by Picard iteration on the bg RHS, starting from the splined value
@@ -822,6 +822,7 @@ static void cmb_sources(const Derived& D, const Spline& spl, double tau, double 
     double chi = D.tau0 - tau;
     double SE = 3.0 / 16.0 * (v * ob.Pig).c[0] / ((k * chi) * (k * chi));
     out[0] = ST_SW + ST_ISW + ST_Dop + ST_pol; out[1] = SE; out[2] = ST_SW; out[3] = ST_ISW; out[4] = ST_Dop; out[5] = ST_pol;
+    out[6] = (tau >= taurec) ? -(Psi.c[0] + Phi.c[0]) * (tau - taurec) / (D.tau0 - taurec) / (D.tau0 - tau) : 0.0;
 }
 
 // ------------------------------------------------------------------ C interface (ctypes)
@@ -904,14 +905,14 @@ void sbo_delta_m(const SboParams* p, int nb, const double* t, const double* y, c
     for (int i = 0; i < nk; i++) out[i] = delta_m(D, spl, tau, ks[i], u + (size_t)i * D.N);
 }
 
-// CMB sources on a grid: u[nk][nt][N] → out[nk][nt][6]
-void sbo_sources(const SboParams* p, int nb, const double* t, const double* y, const double* dy, double tau0, double kappa0,
+// CMB sources on a grid: u[nk][nt][N] → out[nk][nt][7]
+void sbo_sources(const SboParams* p, int nb, const double* t, const double* y, const double* dy, double tau0, double kappa0, double taurec,
                  int nk, const double* ks, int nt, const double* taus, const double* u, double* out) {
     Derived D; derive(*p, D); D.tau0 = tau0; D.kappa0 = kappa0;
     Spline spl{nb, t, y, dy};
 #pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < nk; i++)
-        for (int j = 0; j < nt; j++) cmb_sources(D, spl, taus[j], ks[i], u + ((size_t)i * nt + j) * D.N, out + ((size_t)i * nt + j) * 6);
+        for (int j = 0; j < nt; j++) cmb_sources(D, spl, taurec, taus[j], ks[i], u + ((size_t)i * nt + j) * D.N, out + ((size_t)i * nt + j) * 7);
 }
 
 // Timing of the per-step building blocks of the CPU path (diagnostic for the reported CPU baseline): out[0..5] = µs per call of

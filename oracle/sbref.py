@@ -204,12 +204,12 @@ def spectrum_matter(bg, ks, kτini=1e-2, τinimax=1e-4, **kw):
 
 
 def sources(bg, ks, taus, usave):
-    """CMB sources from saved states: returns array [nk, nτ, 6] = (ST, SE, SW, ISW, Doppler, polarization)."""
+    """CMB sources from saved states: returns array [nk, nτ, 7] = (ST, SE, SW, ISW, Doppler, polarization, Sψ)."""
     ks = np.ascontiguousarray(ks, dtype=float)
     taus = np.ascontiguousarray(taus, dtype=float)
     usave = np.ascontiguousarray(usave)
-    out = np.zeros((len(ks), len(taus), 6))
-    lib().sbo_sources(C.byref(bg.p), *bg._spl(), C.c_double(bg.tau0), C.c_double(bg.kappa0), C.c_int(len(ks)), _p(ks), C.c_int(len(taus)), _p(taus), _p(usave), _p(out))
+    out = np.zeros((len(ks), len(taus), 7))
+    lib().sbo_sources(C.byref(bg.p), *bg._spl(), C.c_double(bg.tau0), C.c_double(bg.kappa0), C.c_double(bg.taurec), C.c_int(len(ks)), _p(ks), C.c_int(len(taus)), _p(taus), _p(usave), _p(out))
     return out
 
 
@@ -300,6 +300,68 @@ def los_integrate(Ss, ls, taus, ks, jl):
         J = jl(ils, (k * chis)[None, :])  # [nl, nτ]
         Is[ik] = J @ (ws * Ss[:, ik])
     return Is
+
+
+def los_limber(S, ls, taus, ks, l_limber):
+    """Limber branch of los_integrate for l ≥ l_limber: Θ_l(k) = √(π/(2l+1)) S(τ0 − (l+½)/k, k)/k with the reference's cubic Hermite
+    interpolation in χ (finite-difference slopes), src/observables/angular.jl:155-178.  S[nτ, nk] → [nk, nl] (zero for l < l_limber)."""
+    taus = np.asarray(taus)
+    chis = taus[-1] - taus
+    nt = len(taus)
+    out = np.zeros((len(ks), len(ls)))
+    for ik, k in enumerate(ks):
+        for il, l in enumerate(ls):
+            if l < l_limber:
+                continue
+            chi = (l + 0.5) / k
+            if chi > chis[0]:
+                continue
+            im = int(np.searchsorted(taus, taus[-1] - chi, side="left"))  # searchsortedfirst (0-based)
+            Sm = S[im, ik]
+            if im == 0:
+                continue  # the reference leaves tmp[il] untouched (zero) in this branch
+            ip = im - 1
+            chim, chip, Sp = chis[im], chis[ip], S[ip, ik]
+            dchi = chip - chim
+            dSm = (S[im + 1, ik] - Sp) / (chis[im + 1] - chip) if im <= nt - 2 else (Sp - Sm) / dchi
+            dSp = (Sm - S[im - 2, ik]) / (chim - chis[im - 2]) if ip >= 1 else (Sp - Sm) / dchi
+            t = (chi - chim) / dchi
+            t2, t3 = t * t, t * t * t
+            Sv = (2 * t3 - 3 * t2 + 1) * Sm + (t3 - 2 * t2 + t) * dchi * dSm + (-2 * t3 + 3 * t2) * Sp + (t3 - t2) * dchi * dSp
+            out[ik, il] = np.sqrt(np.pi / (2 * l + 1)) * Sv / k
+    return out
+
+
+def spectrum_cmb_lensing(modes, bg, jl, normalization="Cl", l_limber=10, order=130, kmin=1e-2, kmax=1e4, k0=2000.0, dkt0=np.pi, ntau=300, taucut=1e-2, nthreads=0, return_all=False):
+    """spectrum_cmb with lensing modes (ψ): tanh-stretched Chebyshev grid to k = 1e4, Sψ source, Limber for l ≥ l_limber
+    (src/observables/angular.jl:225-226, 267-269, 293-309).  modes: pairs of T, E, P (P = ψ)."""
+    ls = np.asarray(jl.l)
+    ks_fine = lingrid(kmin, kmax, step=dkt0 / bg.tau0)
+    ts = bg.t[bg.t >= taucut]
+    taus = ts[0] + (ts[-1] - ts[0]) * cosgrid(0.0, 1.0, length=ntau)
+    taus[-1] = ts[-1]
+    ys = chebpoints(order, np.tanh(kmin / k0), np.tanh(kmax / k0))
+    kc = k0 * np.arctanh(ys)
+    kc[-1], kc[0] = kmin, kmax
+    sol = solvept(bg, kc, ptivini=-np.inf, saveat=taus, nthreads=nthreads)
+    S = sources(bg, kc, taus, sol["usave"])
+    Sc = [(kc[:, None] * S[:, :, 0]).T, (kc[:, None] ** 2 * S[:, :, 1]).T, S[:, :, 6].T.copy()]
+    B = chebyshev_interp_matrix(ys, np.tanh(ks_fine / k0))
+    Sf = []
+    for a in Sc:
+        a[-1, :] = 0.0
+        Sf.append(a @ B.T)
+    ThT = los_integrate(Sf[0], ls, taus, ks_fine, jl) / ks_fine[:, None]
+    ThE = los_integrate(Sf[1], ls, taus, ks_fine, jl) * np.sqrt((ls + 2.0) * (ls + 1.0) * ls * (ls - 1.0))[None, :] / ks_fine[:, None] ** 2
+    ThP = los_integrate(Sf[2], ls, taus, ks_fine, jl)
+    lim = los_limber(Sf[2], ls, taus, ks_fine, l_limber)
+    ThP[:, ls >= l_limber] = lim[:, ls >= l_limber]
+    P0s = spectrum_primordial(ks_fine, bg)
+    Th = {"T": ThT, "E": ThE, "P": ThP}
+    out = np.stack([spectrum_cmb_from_theta(Th[m[0]], Th[m[1]], P0s, ls, ks_fine, normalization) for m in modes], axis=1)
+    if return_all:
+        return out, dict(ks_fine=ks_fine, kc=kc, taus=taus, Sf=Sf, Th=Th, sol=sol)
+    return out
 
 
 def natural_spline_integral(xs, ys):

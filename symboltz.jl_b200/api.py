@@ -397,12 +397,22 @@ def spectrum_matter(prob, ks, kτini=1e-2, τinimax=1e-4, bgsol=None, return_sol
 class ChebyshevInterpolator:
     """Chebyshev nodes (stored descending) + barycentric weights (src/observables/fourier.jl:419-459)."""
 
-    def __init__(self, xmin, xmax, order):
+    def __init__(self, xmin, xmax, order, f=None, finv=None):
+        """f / finv: monotone domain transform y = f(x) and its inverse (e.g. fk_tanh for the lensing grid, angular.jl:225-226)."""
         if not xmax > xmin:
             raise ValueError(f"Interval {(xmin, xmax)} is not sorted")
-        self.xs = chebpoints(order, xmin, xmax)
+        self.f = f if f is not None else (lambda x: x)
+        if f is None:
+            self.xs = chebpoints(order, xmin, xmax)
+            self.ys = self.xs
+        else:
+            if finv is None:
+                raise ValueError("a transform f needs its inverse finv")
+            self.ys = chebpoints(order, float(f(xmin)), float(f(xmax)))
+            self.xs = np.asarray(finv(self.ys), dtype=np.float64)
+            if not (np.isclose(self.xs[-1], xmin) and np.isclose(self.xs[0], xmax)):
+                raise ValueError("f(x) and f⁻¹(x) are not inverses")
         self.xs[-1], self.xs[0] = xmin, xmax
-        self.ys = self.xs
         n = order
         self.ws = np.array([1.0 if j % 2 == 0 else -1.0 for j in range(n + 1)])
         self.ws[0] /= 2
@@ -416,7 +426,7 @@ class ChebyshevInterpolator:
 
     def matrix(self, x_fine):
         """Barycentric interpolation matrix B[nfine, ncoarse] (formula of fourier.jl:524-535; exact hit returns the node value)."""
-        x_fine = np.asarray(x_fine, dtype=np.float64)
+        x_fine = np.asarray(self.f(np.asarray(x_fine, dtype=np.float64)), dtype=np.float64)
         D = x_fine[:, None] - self.ys[None, :]
         hit = D == 0
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -425,6 +435,14 @@ class ChebyshevInterpolator:
         rows = hit.any(axis=1)
         B[rows] = hit[rows].astype(np.float64)
         return B
+
+
+def fk_tanh(k, k0=2000.0):
+    return np.tanh(np.asarray(k) / k0)
+
+
+def fk_tanh_inv(y, k0=2000.0):
+    return k0 * np.arctanh(np.asarray(y))
 
 
 class SourceGrid:
@@ -438,8 +456,8 @@ class SourceGrid:
         return np.ascontiguousarray(self.dS.cpu().numpy().transpose(2, 0, 1))
 
 
-def source_grid(prob, taus, ks, bgsol, scale_k=True, **ptopts):
-    """Solve the modes `ks` saving at `taus` and evaluate the CMB sources (k·ST, k²·SE) there
+def source_grid(prob, taus, ks, bgsol, scale_k=True, lensing=False, **ptopts):
+    """Solve the modes `ks` saving at `taus` and evaluate the CMB sources (k·ST, k²·SE[, Sψ if lensing]) there
     (reference source_grid(prob, Ss, τs, ks, bgsol), src/observables/fourier.jl:267-281 with Ss of angular.jl:293)."""
     taus = np.ascontiguousarray(taus, dtype=np.float64)
     if taus.min() < bgsol.t[0] or taus.max() > bgsol.t[-1]:
@@ -448,12 +466,13 @@ def source_grid(prob, taus, ks, bgsol, scale_k=True, **ptopts):
     d = bgsol.device()
     dev = sol.d_uend.device
     nk, nt = len(sol.ks), len(taus)
-    dS = torch.empty((nk, 2, nt), dtype=torch.float64, device=dev)
+    nS = 3 if lensing else 2
+    dS = torch.empty((nk, nS, nt), dtype=torch.float64, device=dev)
     stride = prob.lib.sbm_srcbg_stride()
     scratch = torch.empty(nt * stride, dtype=torch.float64, device=dev)
     dtaus = torch.from_numpy(taus).to(dev)
     rc = prob.lib.sbm_sources(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(nt), _cptr(dtaus), _cptr(scratch), C.c_int(nk), _cptr(sol.d_ks),
-                              _cptr(sol.d_usave), _cptr(dS), C.c_int(1 if scale_k else 0), _stream())
+                              _cptr(sol.d_usave), _cptr(dS), C.c_int(1 if scale_k else 0), C.c_int(nS), C.c_double(bgsol.taurec), _stream())
     if rc != 0:
         raise RuntimeError(f"sbm_sources failed with code {rc}")
     return SourceGrid(dS, sol.ks, taus, sol)
@@ -527,11 +546,12 @@ def _trapz_weights(taus):
     return w
 
 
-def los_integrate(Sgrid, jl, ks_fine=None, kinterp=None, k_range=None, theta=None):
+def los_integrate(Sgrid, jl, ks_fine=None, kinterp=None, k_range=None, theta=None, l_limber=None):
     """Θ_l(k) = Σ_τ w_τ S(τ,k) j_l(k(τ0−τ)) with Θ_T/k and Θ_E √((l+2)!/(l−2)!)/k² rescaling
     (reference los_integrate + rescale, src/observables/angular.jl:109-152, 301-306).
-    Sgrid holds (k·ST, k²·SE).  With `kinterp`, Sgrid is on the coarse nodes and the interpolation to ks_fine is fused.
-    Returns device tensor Theta[2][nl][nk_fine]."""
+    Sgrid holds (k·ST, k²·SE[, Sψ]).  With `kinterp`, Sgrid is on the coarse nodes and the interpolation to ks_fine is fused.
+    For a third (lensing) source the Limber approximation is used for l ≥ l_limber (angular.jl:155-178, 307-309; default: never).
+    Returns device tensor Theta[nS][nl][nk_fine]."""
     _require_cuda()
     taus = Sgrid.taus
     ks_fine = Sgrid.ks if ks_fine is None else np.ascontiguousarray(ks_fine, dtype=np.float64)
@@ -551,11 +571,12 @@ def los_integrate(Sgrid, jl, ks_fine=None, kinterp=None, k_range=None, theta=Non
         nc = len(kinterp.xs)
     else:
         Bw, nc = None, nk
+    nS = Sgrid.dS.shape[1]
     if theta is None:
-        theta = torch.zeros((2, nl, nk), dtype=torch.float64, device=dev)
+        theta = torch.zeros((nS, nl, nk), dtype=torch.float64, device=dev)
     k_lo, k_hi = (0, nk) if k_range is None else k_range
-    rc = los_lib().sbl_los(C.c_int(k_hi - k_lo), C.c_int(k_lo), C.c_int(nk), _cptr(dks), C.c_int(nc), _cptr(Bw), _cptr(Sgrid.dS), C.c_int(nt), _cptr(chi), _cptr(wt), C.c_int(nl), _cptr(jl.d_l),
-                           _cptr(jl.y), _cptr(jl.dy), C.c_double(jl.invdx), C.c_double(jl.dx), C.c_int(jl.nx), _cptr(theta), _stream())
+    rc = los_lib().sbl_los(C.c_int(k_hi - k_lo), C.c_int(k_lo), C.c_int(nk), _cptr(dks), C.c_int(nc), _cptr(Bw), _cptr(Sgrid.dS), C.c_int(nS), C.c_int(nt), _cptr(chi), _cptr(wt), C.c_int(nl), _cptr(jl.d_l),
+                           _cptr(jl.y), _cptr(jl.dy), C.c_double(jl.invdx), C.c_double(jl.dx), C.c_int(jl.nx), _cptr(theta), C.c_int(2**31 - 1 if l_limber is None else int(l_limber)), _stream())
     if rc != 0:
         raise RuntimeError(f"sbl_los failed with code {rc}")
     return theta
@@ -594,7 +615,7 @@ def natural_spline_weights(x):
     return w
 
 
-_MODE_IDX = {"T": 0, "E": 1}
+_MODE_IDX = {"T": 0, "E": 1, "ψ": 2, "P": 2}  # P: ASCII alias of ψ (lensing potential)
 
 
 def spectrum_cmb_from_theta(theta, modes, P0s, ls, ks, normalization="Cl", k_mask=None):
@@ -655,10 +676,11 @@ def spline_ls(spectra_coarse, ls_coarse, ls_fine):
     return out
 
 
-def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, direct=False, dkt0=math.pi, ntau=300, taucut=1e-2,
+def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, direct=False, dkt0=math.pi, ntau=300, taucut=1e-2, l_limber=10,
                  bgsol=None, ptopts=None, group=None, return_all=False):
-    """Angular spectra C_l^{AB}, AB ∈ {TT, EE, TE, ET} at jl.l (optionally splined to `ls`)
-    (reference spectrum_cmb(modes, prob, jl[, ls]), src/observables/angular.jl:260-359).
+    """Angular spectra C_l^{AB}, A, B ∈ {T, E, ψ} at jl.l (optionally splined to `ls`)
+    (reference spectrum_cmb(modes, prob, jl[, ls]), src/observables/angular.jl:260-359).  With a lensing mode (ψ, alias P) the default
+    k-grid is the tanh-stretched order-130 Chebyshev grid to k = 1e4 and the ψ line-of-sight integral uses Limber for l ≥ l_limber.
     direct=True solves every fine k instead of interpolating from the Chebyshev nodes.
     With torch.distributed initialised (group or default) the modes are sharded over ranks and the partial C_l are all-reduced."""
     modes = [modes] if isinstance(modes, str) else list(modes)
@@ -668,22 +690,24 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
     import torch.distributed as dist
     world, rank = (dist.get_world_size(group), dist.get_rank(group)) if (dist.is_available() and dist.is_initialized()) else (1, 0)
     bg = bgsol if bgsol is not None else solvebg(prob)
-    if kinterp is None:
-        kinterp = ChebyshevInterpolator(1e-2, 2e3, 60)
+    lensing = any(c in ("ψ", "P") for m in modes for c in m)
+    if kinterp is None:  # angular.jl:267-273
+        kinterp = ChebyshevInterpolator(1e-2, 1e4, 130, f=fk_tanh, finv=fk_tanh_inv) if lensing else ChebyshevInterpolator(1e-2, 2e3, 60)
     ks_fine, taus = cmb_grids(bg, kinterp.minimum(), kinterp.maximum(), dkt0, ntau, taucut)
     ptopts = dict(ptopts or {})
     nkf = len(ks_fine)
     ks_solve = ks_fine if direct else kinterp.xs
     # shard the ODE solves over ranks, strided in k so that cost (∝ k) balances; no exchange during the solve
     mine = np.arange(rank, len(ks_solve), world)
-    S = source_grid(prob, taus, ks_solve[mine], bg, **ptopts)
+    S = source_grid(prob, taus, ks_solve[mine], bg, lensing=lensing, **ptopts)
     if world > 1:
-        full = torch.zeros((len(ks_solve), 2, len(taus)), dtype=torch.float64, device=S.dS.device)
+        full = torch.zeros((len(ks_solve), S.dS.shape[1], len(taus)), dtype=torch.float64, device=S.dS.device)
+        S.dS[:, :, -1] = 0  # χ = 0 row (Inf/NaN in SE, Sψ) is dropped by the LOS kernel anyway; keep the reduction finite
         full[torch.from_numpy(mine).to(S.dS.device)] = S.dS
         dist.all_reduce(full, group=group)  # gather of the sources: supports are disjoint, so a sum is an all-gather
         S = SourceGrid(full, ks_solve, taus, S.sol)
     lo, hi = (nkf * rank) // world, (nkf * (rank + 1)) // world  # contiguous fine-k slice for LOS + partial C_l
-    theta = los_integrate(S, jl, ks_fine=ks_fine, kinterp=None if direct else kinterp, k_range=(lo, hi))
+    theta = los_integrate(S, jl, ks_fine=ks_fine, kinterp=None if direct else kinterp, k_range=(lo, hi), l_limber=l_limber if lensing else None)
     mask = np.zeros(nkf)
     mask[lo:hi] = 1.0
     P0s = spectrum_primordial(ks_fine, prob)
@@ -799,14 +823,14 @@ class CMBPlan:
     def sources(self):
         P, t, y, dy = self._views()
         rc = self.prob.lib.sbm_sources(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.nt), _cptr(self.d_taus), _cptr(self.d_srcbg), C.c_int(self.nk), _cptr(self.d_ks),
-                                       _cptr(self.d_usave), _cptr(self.d_S), C.c_int(1), _stream())
+                                       _cptr(self.d_usave), _cptr(self.d_S), C.c_int(1), C.c_int(2), C.c_double(0.0), _stream())
         if rc != 0:
             raise RuntimeError(f"sbm_sources failed with code {rc}")
 
     def los_cl(self):
         jl, L = self.jl, los_lib()
-        rc = L.sbl_los(C.c_int(self.nkf), C.c_int(0), C.c_int(self.nkf), _cptr(self.d_ksf), C.c_int(self.nk), _cptr(self.d_Bw), _cptr(self.d_S), C.c_int(self.nt), _cptr(self.d_chi), _cptr(self.d_wt),
-                       C.c_int(self.nl), _cptr(jl.d_l), _cptr(jl.y), _cptr(jl.dy), C.c_double(jl.invdx), C.c_double(jl.dx), C.c_int(jl.nx), _cptr(self.d_theta), _stream())
+        rc = L.sbl_los(C.c_int(self.nkf), C.c_int(0), C.c_int(self.nkf), _cptr(self.d_ksf), C.c_int(self.nk), _cptr(self.d_Bw), _cptr(self.d_S), C.c_int(2), C.c_int(self.nt), _cptr(self.d_chi), _cptr(self.d_wt),
+                       C.c_int(self.nl), _cptr(jl.d_l), _cptr(jl.y), _cptr(jl.dy), C.c_double(jl.invdx), C.c_double(jl.dx), C.c_int(jl.nx), _cptr(self.d_theta), C.c_int(2**31 - 1), _stream())
         if rc != 0:
             raise RuntimeError(f"sbl_los failed with code {rc}")
         rc = L.sbl_cl(C.c_int(self.nl), C.c_int(self.nkf), C.c_int(0), C.c_int(self.nkf), _cptr(self.d_ck), _cptr(self.d_theta), C.c_int(len(self.modes)), _cptr(self.d_mA), _cptr(self.d_mB), _cptr(self.d_Cl), _stream())

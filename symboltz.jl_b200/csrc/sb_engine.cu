@@ -873,9 +873,9 @@ __global__ void sb_srcbg_kernel(const double* __restrict__ P, SbSpline spl, int 
 
 // CMB source functions ST, SE (reference src/models/cosmologies.jl:99-104) at every saved (k, τ): one thread per point.
 // Derivatives of unknowns are expanded through the ODE itself (u̇ = J u, ü = J̇ u + J u̇), as MTK does symbolically.
-// out layout: S[ik][iS][it], iS = 0: ST, 1: SE
+// out layout: S[ik][iS][it], iS = 0: ST, 1: SE, (nS == 3) 2: Sψ = −(Ψ+Φ)(τ−τrec)/(τ0−τrec)/(τ0−τ) for τ ≥ τrec (lensing source, cosmologies.jl:105)
 __global__ void sb_source_kernel(int nt, const double* __restrict__ taus, const double* __restrict__ srcbg, int nk, const double* __restrict__ ks,
-                                 const double* __restrict__ usave, double* __restrict__ S, int scale_k) {
+                                 const double* __restrict__ usave, double* __restrict__ S, int scale_k, int nS, double taurec) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nk * nt) return;
     int ik = idx / nt, it = idx % nt;
@@ -911,8 +911,12 @@ __global__ void sb_source_kernel(int nt, const double* __restrict__ taus, const 
     double ST = v * (u[SB_I_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
     double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
     if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
-    S[((size_t)ik * 2 + 0) * nt + it] = ST;
-    S[((size_t)ik * 2 + 1) * nt + it] = SE;
+    S[((size_t)ik * nS + 0) * nt + it] = ST;
+    S[((size_t)ik * nS + 1) * nt + it] = SE;
+    if (nS > 2) {
+        const double tau = taus[it];
+        S[((size_t)ik * nS + 2) * nt + it] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
+    }
 }
 
 // ================================================================================================ C ABI (device pointers)
@@ -969,15 +973,15 @@ int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, co
     return 0;
 }
 
-// sources: dsrcbg is scratch of nt·sbm_srcbg_stride() doubles; dS: [nk][2][nt]
+// sources: dsrcbg is scratch of nt·sbm_srcbg_stride() doubles; dS: [nk][nS][nt], nS = 2 (ST, SE) or 3 (+ lensing Sψ, needs taurec)
 int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, int nk, const double* dks,
-                const double* dusave, double* dS, int scale_k, void* stream) {
+                const double* dusave, double* dS, int scale_k, int nS, double taurec, void* stream) {
     if (nk <= 0 || nt <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     sb_srcbg_kernel<<<(nt + 63) / 64, 64, 0, st>>>(dP, SbSpline{nb, dt, dy, ddy}, nt, dtaus, dsrcbg);
     SB_CUDA_CHECK(cudaGetLastError());
     int n = nk * nt;
-    sb_source_kernel<<<(n + 127) / 128, 128, 0, st>>>(nt, dtaus, dsrcbg, nk, dks, dusave, dS, scale_k);
+    sb_source_kernel<<<(n + 127) / 128, 128, 0, st>>>(nt, dtaus, dsrcbg, nk, dks, dusave, dS, scale_k, nS, taurec);
     SB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -76,34 +76,35 @@ __global__ void sbl_bessel_kernel(int nl, const int* __restrict__ ls, int nxp, d
 
 // One CTA per fine k: optional barycentric k-interpolation of the coarse sources (in shared memory), trapezoid-weighted
 // line-of-sight sum against the Hermite-interpolated j_l table, Θ rescaling.  Threads: x → l, y → τ slice.
-// Sc layout [nc][2][nt] (coarse k, source, time);  Bw [nk][nc] barycentric weights (NULL: direct, nc == nk);
-// jy/jdy [nx][nl];  Theta out [2][nl][nk].
-__global__ void sbl_los_kernel(int nk, int k0, const double* __restrict__ ks, int nc, const double* __restrict__ Bw, const double* __restrict__ Sc, int nt,
+// nS sources (2: T, E; 3: + lensing ψ).  Sc layout [nc][nS][nt];  Bw [nk][nc] barycentric weights (NULL: direct, nc == nk);
+// jy/jdy [nx][nl];  Theta out [nS][nl][nk].  For the ψ source and l >= l_limber the Limber approximation
+// Θ_l = √(π/(2l+1)) S(τ0 − (l+½)/k)/k replaces the integral (reference src/observables/angular.jl:155-178).
+#define SBL_MAXS 3
+__global__ void sbl_los_kernel(int nk, int k0, const double* __restrict__ ks, int nc, const double* __restrict__ Bw, const double* __restrict__ Sc, int nS, int nt,
                                const double* __restrict__ chi, const double* __restrict__ wt, int nl, const int* __restrict__ ls, const double* __restrict__ jy,
-                               const double* __restrict__ jdy, double invdx, double dxc, int nxp, double* __restrict__ Theta, int nk_total) {
+                               const double* __restrict__ jdy, double invdx, double dxc, int nxp, double* __restrict__ Theta, int nk_total, int l_limber) {
     extern __shared__ double sh[];
-    double* SwT = sh;            // [nt] weighted temperature source
-    double* SwE = sh + nt;       // [nt]
-    double* red = sh + 2 * nt;   // [TS][LT][2] reduction scratch
-    const int ik = blockIdx.x;   // local index in [0, nk)
+    double* Sw = sh;                         // [nS][nt] trapezoid-weighted sources
+    double* Sraw = sh + nS * nt;             // [nt] unweighted ψ source (Limber), only if nS == 3
+    double* red = sh + (nS + (nS > 2 ? 1 : 0)) * nt; // [TS][LT][nS] reduction scratch
+    const int ik = blockIdx.x;
     const int LT = blockDim.x, TS = blockDim.y;
     const int tid = threadIdx.y * LT + threadIdx.x, nthr = LT * TS;
     const double k = ks[k0 + ik];
-    for (int o = tid; o < 2 * nt; o += nthr) {
+    for (int o = tid; o < nS * nt; o += nthr) {
         int s = o / nt, it = o % nt;
         double v;
         if (Bw) {
             const double* bw = Bw + (size_t)(k0 + ik) * nc;
             v = 0;
-            for (int j = 0; j < nc; j++) v += bw[j] * Sc[((size_t)j * 2 + s) * nt + it];
-        } else v = Sc[((size_t)(k0 + ik) * 2 + s) * nt + it];
-        v *= wt[it];
-        if (it == nt - 1) v = 0.0; // reference zeroes the last row (χ = 0), angular.jl:296
-        sh[o] = v;
+            for (int j = 0; j < nc; j++) { const double sc = (it == nt - 1) ? 0.0 : Sc[((size_t)j * nS + s) * nt + it]; v += bw[j] * sc; } // last row (χ = 0) zeroed, angular.jl:296
+        } else v = (it == nt - 1) ? 0.0 : Sc[((size_t)(k0 + ik) * nS + s) * nt + it];
+        if (s == 2) Sraw[it] = v;
+        sh[o] = v * wt[it];
     }
     __syncthreads();
     const int il = threadIdx.x;
-    double aT = 0, aE = 0;
+    double acc[SBL_MAXS] = {0, 0, 0};
     if (il < nl) {
         for (int it = threadIdx.y; it < nt; it += TS) {
             double w = k * chi[it] * invdx;
@@ -114,18 +115,39 @@ __global__ void sbl_los_kernel(int nk, int k0, const double* __restrict__ ks, in
             const size_t o0 = (size_t)i * nl + il, o1 = o0 + nl;
             const double ym = __ldg(jy + o0), yp = __ldg(jy + o1), dm = __ldg(jdy + o0), dp = __ldg(jdy + o1);
             const double j = (1 + 2 * w) * wm1 * wm1 * ym + w * w * (3 - 2 * w) * yp + w * wm1 * (wm1 * dm + w * dp) * dxc; // angular.jl:38-48
-            aT += SwT[it] * j;
-            aE += SwE[it] * j;
+#pragma unroll
+            for (int s = 0; s < SBL_MAXS; s++) if (s < nS) acc[s] += Sw[s * nt + it] * j;
         }
     }
-    red[(threadIdx.y * LT + threadIdx.x) * 2] = aT;
-    red[(threadIdx.y * LT + threadIdx.x) * 2 + 1] = aE;
+    for (int s = 0; s < nS; s++) red[(threadIdx.y * LT + threadIdx.x) * nS + s] = acc[s];
     __syncthreads();
     if (threadIdx.y == 0 && il < nl) {
-        for (int s = 1; s < TS; s++) { aT += red[(s * LT + il) * 2]; aE += red[(s * LT + il) * 2 + 1]; }
+        for (int t = 1; t < TS; t++) for (int s = 0; s < nS; s++) acc[s] += red[(t * LT + il) * nS + s];
         const double l = (double)ls[il];
-        Theta[((size_t)0 * nl + il) * nk_total + k0 + ik] = aT / k;                                                   // angular.jl:302
-        Theta[((size_t)1 * nl + il) * nk_total + k0 + ik] = aE * sqrt((l + 2) * (l + 1) * l * (l - 1)) / (k * k);     // angular.jl:305
+        Theta[((size_t)0 * nl + il) * nk_total + k0 + ik] = acc[0] / k;                                                   // angular.jl:302
+        Theta[((size_t)1 * nl + il) * nk_total + k0 + ik] = acc[1] * sqrt((l + 2) * (l + 1) * l * (l - 1)) / (k * k);     // angular.jl:305
+        if (nS > 2) {
+            double th = acc[2];
+            if (ls[il] >= l_limber) { // Limber: cubic Hermite in χ with finite-difference slopes, as the reference
+                th = 0.0;
+                const double chiL = (l + 0.5) / k;
+                if (chiL <= chi[0]) {
+                    int lo = 0, hi = nt - 1; // first index with χ_i <= χL (χ descending) == searchsortedfirst(τs, τ0 − χL)
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (chi[mid] <= chiL) hi = mid; else lo = mid + 1; }
+                    const int im = lo;
+                    if (im > 0) {
+                        const int ip = im - 1;
+                        const double Sm = Sraw[im], Sp = Sraw[ip], chim = chi[im], chip = chi[ip], dchi = chip - chim;
+                        const double dSm = (im <= nt - 2) ? (Sraw[im + 1] - Sp) / (chi[im + 1] - chip) : (Sp - Sm) / dchi;
+                        const double dSp = (ip >= 1) ? (Sm - Sraw[im - 2]) / (chim - chi[im - 2]) : (Sp - Sm) / dchi;
+                        const double t = (chiL - chim) / dchi, t2 = t * t, t3 = t2 * t;
+                        const double Sv = (2 * t3 - 3 * t2 + 1) * Sm + (t3 - 2 * t2 + t) * dchi * dSm + (-2 * t3 + 3 * t2) * Sp + (t3 - t2) * dchi * dSp;
+                        th = sqrt(3.14159265358979323846 / (2 * l + 1)) * Sv / k;
+                    }
+                }
+            }
+            Theta[((size_t)2 * nl + il) * nk_total + k0 + ik] = th;
+        }
     }
 }
 
@@ -165,15 +187,16 @@ int sbl_bessel_table(int nl, const int* dls, int nxp, double step, double* dy_, 
 }
 
 // Line-of-sight integration for fine-k indices [k0, k0+nk) of a grid with nk_total points (multi-GPU: each rank its slice).
-int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nt, const double* dchi, const double* dwt, int nl,
-            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, void* stream) {
+int sbl_los(int nk, int k0, int nk_total, const double* dks, int nc, const double* dBw, const double* dSc, int nS, int nt, const double* dchi, const double* dwt, int nl,
+            const int* dls, const double* djy, const double* djdy, double invdx, double dx, int nxp, double* dTheta, int l_limber, void* stream) {
     if (nk <= 0) return 0;
+    if (nS < 2 || nS > SBL_MAXS) return -3;
     int LT = ((nl + 31) / 32) * 32;
     if (LT > 1024) return -2;
     int TS = 512 / LT; if (TS > 8) TS = 8; if (TS < 1) TS = 1;
-    size_t smem = (size_t)(2 * nt + 2 * LT * TS) * sizeof(double);
+    size_t smem = (size_t)((nS + (nS > 2 ? 1 : 0)) * nt + nS * LT * TS) * sizeof(double);
     if (smem > 48 * 1024) SBL_CUDA_CHECK(cudaFuncSetAttribute(sbl_los_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sbl_los_kernel<<<nk, dim3(LT, TS), smem, (cudaStream_t)stream>>>(nk, k0, dks, nc, dBw, dSc, nt, dchi, dwt, nl, dls, djy, djdy, invdx, dx, nxp, dTheta, nk_total);
+    sbl_los_kernel<<<nk, dim3(LT, TS), smem, (cudaStream_t)stream>>>(nk, k0, dks, nc, dBw, dSc, nS, nt, dchi, dwt, nl, dls, djy, djdy, invdx, dx, nxp, dTheta, nk_total, l_limber);
     SBL_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

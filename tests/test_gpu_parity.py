@@ -283,3 +283,22 @@ def test_stability_latin_hypercube(sb):
         u = (rng.permuted(np.tile(np.arange(n), (len(names), 1)), axis=1).T + rng.random((n, len(names)))) / n
         P, info = sb.spectrum_matter_sweep(prob, names, fid * (0.5 + u), np.array([1.0, 10.0, 100.0, 1000.0]), return_info=True)
         assert info == dict(background_failures=0, mode_failures=0) and np.isfinite(P).all() and (P > 0).all()
+
+
+def test_lensing_spectrum_vs_class_and_oracle(sb, oracle, prob5, bg5, obg_same):
+    """§8f rank 2: lensing potential spectrum (Sψ source, tanh-stretched order-130 Chebyshev grid to k = 1e4, Limber for l ≥ 10).
+    Reference criterion runtests.jl:886: D_l^{φφ} vs CLASS at rtol 2e-3 (2-norm); vs the oracle pipeline element-wise 3e-4."""
+    d = np.loadtxt(os.path.join(GOLDEN, "class_Cl.dat"))
+    lc, PP = d[:, 0], d[:, 3]
+    ls = np.unique(np.round(np.exp(np.linspace(np.log(2), np.log(2500), 48))).astype(int))
+    jl = sb.SphericalBesselCache(ls, xcut=1e4 * bg5.tau0 * 1.001)
+    Dl, ex = sb.spectrum_cmb(["ψψ", "TT", "ψT"], prob5, jl, normalization="Dl", bgsol=bg5, return_all=True)
+    assert ex["S"].sol.success and len(ex["S"].ks) == 131 and ex["theta"].shape[0] == 3
+    Dl_all = sb.spline_ls(Dl[:, :1], ls, lc)
+    assert np.linalg.norm(Dl_all[:, 0] - PP) <= 2e-3 * np.linalg.norm(PP)
+    obg = oracle.Background.from_knots(oracle.planck18(lmax=5), bg5.t, bg5.y, bg5.dy, bg5.tau0, bg5.kappa0, taurec=bg5.taurec)
+    ojl = oracle.SphericalBesselCache(ls, xcut=1e4 * bg5.tau0 * 1.001)
+    oDl = oracle.spectrum_cmb_lensing(["PP", "TT", "PT"], obg, ojl, normalization="Dl")
+    assert np.abs(Dl[:, 0] / oDl[:, 0] - 1).max() < 3e-4
+    assert np.abs(Dl[:, 1] / oDl[:, 1] - 1).max() < 3e-4
+    assert np.abs(Dl[:, 2] - oDl[:, 2]).max() <= 3e-4 * np.abs(oDl[:, 2]).max()

@@ -120,3 +120,14 @@ def test_cmb_spectra_vs_class(oracle, obg5):
     Dl_all = oracle.spline_ls(Dl, ls, lc)
     assert np.linalg.norm(Dl_all[:, 0] - TT) <= 2e-3 * np.linalg.norm(TT)
     assert np.linalg.norm(Dl_all[:, 1] - EE) <= 2e-3 * np.linalg.norm(EE)
+
+
+def test_lensing_spectrum_vs_class(oracle, obg5):
+    """runtests.jl:886: D_l^{φφ} vs CLASS, rtol = 2e-3 (2-norm); lensing path = Sψ source, tanh-stretched Chebyshev grid to k = 1e4, Limber for l ≥ 10."""
+    d = np.loadtxt(os.path.join(GOLDEN, "class_Cl.dat"))
+    lc, PP = d[:, 0], d[:, 3]
+    ls = np.unique(np.round(np.exp(np.linspace(np.log(2), np.log(2500), 32))).astype(int))
+    jl = oracle.SphericalBesselCache(ls, xcut=1e4 * obg5.tau0 * 1.001)
+    Dl = oracle.spectrum_cmb_lensing(["PP"], obg5, jl, normalization="Dl")
+    Dl_all = oracle.spline_ls(Dl, ls, lc)
+    assert np.linalg.norm(Dl_all[:, 0] - PP) <= 2e-3 * np.linalg.norm(PP)
