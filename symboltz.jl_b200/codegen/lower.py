@@ -376,13 +376,17 @@ def generate(m: Model):
 
     # ---------------- per-lane schedules for the integrator (warp = 32 lanes), layout [item][lane] (one coalesced line per item).
     # Path decomposition of the elimination forest: a path is a maximal chain v0 -> v1 -> ... in which every vertex after the
-    # first has exactly one child (the previous one).  One lane owns one path per phase and runs the elimination / substitution
-    # recurrences along it in registers; phase(path) = 0 for paths starting at a leaf, else 1 + max phase of the paths feeding
-    # its first vertex.  Dense 2-core members are not on paths (block step).  The integrator works in a RELABELLED state order
-    # in which every path is a contiguous index range (phase by phase, dense members last), so that the recurrences address
-    # shared memory as base + compile-time offset; sb_nat / sb_newidx convert at the kernel boundary (ICs, saved states).
-    dense_blocks = [b for b in L.blocks if len(b) > 1]
-    in_dense = {v for b in dense_blocks for v in b}
+    # first has exactly one child (the previous one).  One lane owns one path and runs the elimination / substitution
+    # recurrences along it in registers.  Paths starting at a leaf form phase 0.  What sits above them is the "top":
+    #   * top blocks: the dense 2-core blocks, grown by every higher-phase path coupled to them (e.g. F1 joins {F2,G0,G1,G2}):
+    #     inverted explicitly (pivoted Gauss-Jordan), applied as a mat-vec, lane = 8*block + row;
+    #   * root paths: the remaining higher-phase paths; they must be roots of the forest fed by phase-0 paths only, so
+    #     that their forward and backward substitutions complete in the same step as the block mat-vec.
+    # A solve is then three warp-synchronous steps: phase-0 forward | top | phase-0 backward.
+    # The integrator works in a RELABELLED state order in which every path is a contiguous index range (phase-0 paths, root
+    # paths, top blocks), so that the recurrences address shared memory as base + compile-time offset; sb_nat / sb_newidx
+    # convert at the kernel boundary (ICs, saved states).
+    in_dense = {v for b in L.blocks if len(b) > 1 for v in b}
     path_of, paths, pphase = {}, [], []
     for v in sorted(range(N), key=lambda i: L.level[i]):
         if v in in_dense:
@@ -396,19 +400,70 @@ def generate(m: Model):
             paths.append([v])
             pphase.append(0 if not ch else 1 + max(pphase[path_of[c]] for c in ch))
         path_of[v] = pid
-    NPH = max(pphase) + 1
-    PL = max(len(p) for p in paths)
-    PR = max((sum(1 for q in pphase if q == ph) + 31) // 32 for ph in range(NPH))
+    nbr = [set() for _ in range(N)]
+    for i in range(N):
+        for (j, _, _) in L.rows[i]:
+            if i != j:
+                nbr[i].add(j)
+                nbr[j].add(i)
+    top_sets = [set(b) for b in L.blocks if len(b) > 1]
+    absorbed, grew = set(), True
+    while grew:
+        grew = False
+        for pid, p in enumerate(paths):
+            if pphase[pid] == 0 or pid in absorbed:
+                continue
+            hit = [t for t in top_sets if any(w in t for v in p for w in nbr[v])]
+            if hit:
+                assert len(hit) == 1, "a path bridging two dense blocks is not supported"
+                hit[0].update(p)
+                absorbed.add(pid)
+                grew = True
+    top_blocks = [sorted(t) for t in top_sets]
+    tblk_of = {v: (bi, pos) for bi, b in enumerate(top_blocks) for pos, v in enumerate(b)}
+    toff = [0]
+    for b in top_blocks:
+        toff.append(toff[-1] + len(b) ** 2)
+    TOPSTORE, TOPMAX = toff[-1], max([len(b) for b in top_blocks] + [1])
+    paths0 = [p for pid, p in enumerate(paths) if pphase[pid] == 0]
+    rpaths = [p for pid, p in enumerate(paths) if pphase[pid] > 0 and pid not in absorbed]
+    for pid, p in enumerate(paths):
+        if pphase[pid] > 0 and pid not in absorbed:
+            assert pphase[pid] == 1 and L.parent[p[-1]] < 0, "higher-phase paths must be forest roots fed by leaf paths"
+    for v in tblk_of:
+        assert all(c not in tblk_of and pphase[path_of[c]] == 0 for c in L.children[v] if c not in tblk_of)
+    assert len(top_blocks) <= 3 and all(len(b) <= 8 for b in top_blocks)
+    PL = max(len(p) for p in paths0)
+    PR = (len(paths0) + 31) // 32
+    TL = max([len(p) for p in rpaths] + [1])
+    TR = max(1, (len(rpaths) + 31) // 32)
     nat = []  # new index -> natural index
-    for ph in range(NPH):
-        for pid, q in enumerate(pphase):
-            if q == ph:
-                nat += paths[pid]
-    for b in dense_blocks:
+    for p in paths0 + rpaths:
+        nat += p
+    for b in top_blocks:
         nat += b
     assert sorted(nat) == list(range(N)) and N <= 1022
+    # roles of the J_local entries in this schedule: 0 diag, 1 "up" (row child, col parent), 2 "lo" (row parent, col child),
+    # 3 top-block entry (target = offset into the block store)
+    sroles = []
+    for i in range(N):
+        rr = []
+        for (j, _, _) in L.rows[i]:
+            if i == j:
+                rr.append((0, 0))
+            elif i in tblk_of and j in tblk_of:
+                assert tblk_of[i][0] == tblk_of[j][0]
+                bb, nbk = tblk_of[i][0], len(top_blocks[tblk_of[i][0]])
+                rr.append((3, toff[bb] + tblk_of[i][1] * nbk + tblk_of[j][1]))
+            elif L.parent[i] == j:
+                rr.append((1, i))
+            elif L.parent[j] == i:
+                rr.append((2, j))
+            else:
+                raise AssertionError(f"entry ({i},{j}) neither tree edge nor top-block entry")
+        sroles.append(rr)
     # index width of the packed schedules: 8 bits when everything fits (cheaper byte extraction on the device), else 10
-    BITS = 8 if (N <= 254 and NB <= 255 and sum(len(b) ** 2 for b in L.blocks) <= 255) else 10
+    BITS = 8 if (N <= 254 and NB <= 255 and TOPSTORE <= 255) else 10
     HB = 8 if BITS == 8 else 16          # width of the two-field words
     KSH = 2 * BITS                       # role kind position in the ELL index word
     TSH = 20 if BITS == 8 else 22        # role target position
@@ -417,19 +472,14 @@ def generate(m: Model):
         inv[old_i] = new_i
     R = (N + 31) // 32
     WD = max(len(r) for r in L.rows)
-    assert NB <= 1023 and sum(len(b) ** 2 for b in L.blocks) <= 1023
+    assert NB <= 1023 and TOPSTORE <= 1023
     ell_coef = [0.0] * (R * WD * 32)
     ell_idx = [0] * (R * WD * 32)
     for i in range(N):
         ni = inv[i]
         lane, r = ni % 32, ni // 32
-        for w, ((j, c, b), (rk, ri)) in enumerate(zip(L.rows[i], L.roles[i])):
-            tgt = 0
-            if rk == 2:
-                tgt = inv[ri]
-            elif rk == 3:
-                bb, pos = L.blk_of[i]
-                tgt = boff[bb] + pos * len(L.blocks[bb]) + ri
+        for w, ((j, c, b), (rk, ri)) in enumerate(zip(L.rows[i], sroles[i])):
+            tgt = inv[ri] if rk == 2 else (ri if rk == 3 else 0)
             ell_coef[(r * WD + w) * 32 + lane] = c
             ell_idx[(r * WD + w) * 32 + lane] = inv[j] | (b << BITS) | (rk << KSH) | (tgt << TSH)
     pq_coef = [0.0] * (R * 2 * 32)
@@ -453,41 +503,39 @@ def generate(m: Model):
         return cf, ix
     phc, phi_ = _terms(L.hub["phi"], TPH)
     psc, psi_ = _terms(L.hub["psi"], TPS)
-    # path descriptors [phase][round][lane]: head = start | len<<8 | parent_of_last<<16 (255: root); kids = children of the first vertex
-    p_head = [0] * (NPH * PR * 32)
+    # path descriptors [round][lane]: head = start | len<<8 | parent_of_last<<16 (255: root); kids = children of the first vertex.
+    # Root paths start on the first lane after the top-block lanes so that the two kinds of top work do not share lanes.
     NONE = (1 << BITS) - 1
     NOKIDS = NONE | (NONE << BITS) | (NONE << (2 * BITS))
     NOPAR = 255 if BITS == 8 else 4095
     LSH, PSH = (8, 16) if BITS == 8 else (12, 20)
-    p_kids = [NOKIDS] * (NPH * PR * 32)
-    for ph in range(NPH):
-        mine = [i for i, q in enumerate(pphase) if q == ph]
-        for q, pid in enumerate(mine):
-            rd, lane = q // 32, q % 32
-            p = paths[pid]
+
+    def _kids(v):
+        kids = [inv[c] for c in L.children[v] if c not in tblk_of]
+        assert len(kids) <= 3
+        kids += [NONE] * (3 - len(kids))
+        return kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
+
+    def _paths(plist, rounds, lane0):
+        head, kid = [0] * (rounds * 32), [NOKIDS] * (rounds * 32)
+        for q, p in enumerate(plist):
+            rd, lane = q // 32, (q + lane0) % 32
             start = inv[p[0]]
             assert [inv[v] for v in p] == list(range(start, start + len(p)))
             par = L.parent[p[-1]]
             par = NOPAR if par < 0 else inv[par]
-            p_head[(ph * PR + rd) * 32 + lane] = start | (len(p) << LSH) | (par << PSH)
-            kids = [inv[c] for c in L.children[p[0]]]
-            assert len(kids) <= 3
-            kids += [NONE] * (3 - len(kids))
-            p_kids[(ph * PR + rd) * 32 + lane] = kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
-    d_kids = [NOKIDS] * 32
-    for bi, b in enumerate(dense_blocks):
+            head[rd * 32 + lane] = start | (len(p) << LSH) | (par << PSH)
+            kid[rd * 32 + lane] = _kids(p[0])
+        return head, kid
+    p_head, p_kids = _paths(paths0, PR, 0)
+    r_head, r_kids = _paths(rpaths, TR, 8 * len(top_blocks))
+    t_kids = [NOKIDS] * 32
+    for bi, b in enumerate(top_blocks):
         for pos, v in enumerate(b):
-            kids = [inv[c] for c in L.children[v]]
-            assert len(kids) <= 3
-            kids += [NONE] * (3 - len(kids))
-            d_kids[bi * 8 + pos] = kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
-    assert len(dense_blocks) <= 4 and all(len(b) <= 8 for b in dense_blocks)
-    dbn = [len(b) for b in dense_blocks]
-    dboff = [boff[L.blocks.index(b)] for b in dense_blocks]
-    dbstart = [inv[b[0]] for b in dense_blocks]
-    for b in dense_blocks:
+            t_kids[bi * 8 + pos] = _kids(v)
         assert [inv[v] for v in b] == list(range(inv[b[0]], inv[b[0]] + len(b)))
-    for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NDENSE", len(dense_blocks)), ("SB_NPH", NPH), ("SB_PL", PL), ("SB_PR", PR)]:
+    for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NTOP", len(top_blocks)), ("SB_TOPMAX", TOPMAX),
+                      ("SB_TOPSTORE", max(1, TOPSTORE)), ("SB_PL", PL), ("SB_PR", PR), ("SB_TL", TL), ("SB_TR", TR)]:
         W(f"#define {name} {val}")
     W(_arr("short", "sb_nat", nat))
     W(_arr("short", "sb_newidx", inv))
@@ -501,10 +549,12 @@ def generate(m: Model):
     W(_arr("unsigned int", "sb_psi_idx", psi_, "{}u"))
     W(_arr("unsigned int", "sb_path_head", p_head, "{}u"))
     W(_arr("unsigned int", "sb_path_kids", p_kids, "{}u"))
-    W(_arr("unsigned int", "sb_dense_kids", d_kids, "{}u"))
-    W(_arr("int", "sb_dense_n", dbn))
-    W(_arr("int", "sb_dense_off", dboff))
-    W(_arr("int", "sb_dense_start", dbstart))
+    W(_arr("unsigned int", "sb_root_head", r_head, "{}u"))
+    W(_arr("unsigned int", "sb_root_kids", r_kids, "{}u"))
+    W(_arr("unsigned int", "sb_top_kids", t_kids, "{}u"))
+    W(_arr("int", "sb_top_n", [len(b) for b in top_blocks]))
+    W(_arr("int", "sb_top_off", toff[:-1]))
+    W(_arr("int", "sb_top_start", [inv[b[0]] for b in top_blocks]))
     W(_arr("unsigned int", "sb_basis_pack", [(b[0] | ((b[1] + 3) << HB)) for b in L.basis], "{}u"))
 
     flops = {}

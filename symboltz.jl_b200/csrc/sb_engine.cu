@@ -298,7 +298,7 @@ struct SbSolveArgs {
 #define SB_SM_BS (SB_SM_ZQ + SB_N)
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
 #define SB_SM_BLK (SB_SM_BD + SB_NB)
-#define SB_SM_KP (SB_SM_BLK + SB_BLKSTORE)
+#define SB_SM_KP (SB_SM_BLK + SB_TOPSTORE)
 #define SB_SM_DOUBLES (SB_SM_KP + 8 + 24)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
@@ -348,8 +348,9 @@ struct SbLane {
     unsigned pqi[SB_R];
     double phc[SB_TPH], psc[SB_TPS]; // hub functionals φ, ψ: one term per lane and slot
     unsigned phi[SB_TPH], psi[SB_TPS];
-    unsigned ph[SB_NPH * SB_PR], pk[SB_NPH * SB_PR]; // owned elimination paths (contiguous index ranges): start|len<<8|parent<<16, first-vertex children
-    unsigned dk;               // dense-block member owned by this lane (lane = block*8+row): its forest children
+    unsigned ph[SB_PR], pk[SB_PR]; // owned phase-0 elimination paths (contiguous index ranges): start|len<<8|parent<<16, first-vertex children
+    unsigned rh[SB_TR], rk[SB_TR]; // owned root paths (the part of the top that is not in a block)
+    unsigned dk;               // top-block member owned by this lane (lane = block*8+row): its forest children
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
     __device__ __forceinline__ void load(int lane) {
 #pragma unroll
@@ -361,8 +362,10 @@ struct SbLane {
 #pragma unroll
         for (int t = 0; t < SB_TPS; t++) { psc[t] = sb_psi_coef[t * 32 + lane]; psi[t] = sb_psi_idx[t * 32 + lane]; }
 #pragma unroll
-        for (int q = 0; q < SB_NPH * SB_PR; q++) { ph[q] = sb_path_head[q * 32 + lane]; pk[q] = sb_path_kids[q * 32 + lane]; }
-        dk = sb_dense_kids[lane];
+        for (int q = 0; q < SB_PR; q++) { ph[q] = sb_path_head[q * 32 + lane]; pk[q] = sb_path_kids[q * 32 + lane]; }
+#pragma unroll
+        for (int q = 0; q < SB_TR; q++) { rh[q] = sb_root_head[q * 32 + lane]; rk[q] = sb_root_kids[q * 32 + lane]; }
+        dk = sb_top_kids[lane];
 #pragma unroll
         for (int r = 0; r < SB_NBR; r++) { int m = r * 32 + lane; bp[r] = (m < SB_NB) ? sb_basis_pack[m] : 0u; }
     }
@@ -480,13 +483,13 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
 }
 
 
-// Factor B = x·I − J_local(b) along the generated elimination paths (zero fill, no pivoting: the chains have sign-skew
-// off-diagonals and non-negative damping, so pivots only grow) + explicit pivoted inverse of the dense 2-core blocks.
-// Leaves 1/pivot in di (raw diagonal for dense members), multipliers in mm, entries towards the parent in up, block inverses in blk.
+// Factor B = x·I − J_local(b): phase-0 elimination paths (zero fill, no pivoting: the chains have sign-skew off-diagonals
+// and non-negative damping, so pivots only grow), then the top = root paths + explicit pivoted inverse of the top blocks.
+// Leaves 1/pivot in di, multipliers in mm, (entry towards the parent)/pivot in up, block inverses in blk.
 __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane) {
 #pragma unroll
     for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) mm[i] = 0; }
-    for (int i = lane; i < SB_BLKSTORE; i += SB_WARP) blk[i] = 0;
+    for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0;
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
@@ -505,164 +508,187 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
     __syncwarp();
+    // phase 0: every vertex but the last of a path is finished here (multiplier and parent coupling scaled by 1/pivot); the
+    // last one keeps its raw multiplier for the owner of its parent, which forms the Schur term mm_raw * (up/pivot)
 #pragma unroll
-    for (int ph = 0; ph < SB_NPH; ph++) {
+    for (int rd = 0; rd < SB_PR; rd++) {
+        const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
+        if (len > 0) {
+            double* dip = di + start; double* mmp = mm + start; double* upp = up + start;
+            double dinv = 1.0 / dip[0];
+            dip[0] = dinv;
 #pragma unroll
-        for (int rd = 0; rd < SB_PR; rd++) {
-            const int q = ph * SB_PR + rd;
-            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]);
-            if (len > 0) {
-                double* dip = di + start; double* mmp = mm + start; const double* upp = up + start;
-                double dj = dip[0];
-                if (ph > 0) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.pk[q], c); if (ch != SB_NOKID) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
-                }
-                double dinv = 1.0 / dj;
-                dip[0] = dinv;
-#pragma unroll
-                for (int pos = 1; pos < SB_PL; pos++) {
-                    if (pos < len) {
-                        const double m = mmp[pos - 1] * dinv;
-                        mmp[pos - 1] = m;
-                        dj = dip[pos] - m * upp[pos - 1];
-                        dinv = 1.0 / dj;
-                        dip[pos] = dinv;
-                    }
+            for (int pos = 1; pos < SB_PL; pos++) {
+                if (pos < len) {
+                    const double mr = mmp[pos - 1], u = upp[pos - 1] * dinv;
+                    mmp[pos - 1] = mr * dinv;
+                    upp[pos - 1] = u;
+                    dinv = 1.0 / fma(-mr, u, dip[pos]);
+                    dip[pos] = dinv;
                 }
             }
+            upp[len - 1] *= dinv;
         }
-        __syncwarp();
     }
-    if (SB_NDENSE > 0) {
+    __syncwarp();
+    // top: root paths (fed by phase-0 paths only) ...
+#pragma unroll
+    for (int rd = 0; rd < SB_TR; rd++) {
+        const int start = SB_P_START(S.rh[rd]), len = SB_P_LEN(S.rh[rd]);
+        if (len > 0) {
+            double* dip = di + start; double* mmp = mm + start; double* upp = up + start;
+            double dj = dip[0];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.rk[rd], c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
+            double dinv = 1.0 / dj;
+            dip[0] = dinv;
+#pragma unroll
+            for (int pos = 1; pos < SB_TL; pos++) {
+                if (pos < len) {
+                    const double mr = mmp[pos - 1], u = upp[pos - 1] * dinv;
+                    mmp[pos - 1] = mr * dinv;
+                    upp[pos - 1] = u;
+                    dinv = 1.0 / fma(-mr, u, dip[pos]);
+                    dip[pos] = dinv;
+                }
+            }
+            upp[len - 1] = 0;
+        }
+    }
+    // ... and top blocks: gather the children's Schur terms into the diagonal, then Gauss-Jordan with partial pivoting, one
+    // matrix row [A | I] per lane (lane = block*8 + row), rows exchanged by warp shuffles within the 8-lane group ->
+    // explicit inverse (block solves become mat-vecs)
+    if (SB_NTOP > 0) {
         const int bb = lane >> 3, i = lane & 7;
-        if (bb < SB_NDENSE && i < sb_dense_n[bb]) { // gather the children's Schur contributions into the block diagonal
-            const int v = sb_dense_start[bb] + i;
-            double dj = di[v];
+        int nb = 0, off = 0, vstart = 0;
+        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; vstart = sb_top_start[bb]; }
+        double dj = 1.0;
+        if (i < nb) {
+            dj = di[vstart + i];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double m = mm[ch] * di[ch]; mm[ch] = m; dj -= m * up[ch]; } }
-            di[v] = dj;
+            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
         }
-        __syncwarp();
-        // Gauss-Jordan with partial pivoting, one matrix row [A | I] per lane (lane = block*8 + row), rows exchanged by
-        // warp shuffles within the 8-lane group -> explicit inverse (block solves become mat-vecs)
-        {
-            int nb = 0, off = 0, vstart = 0;
-            if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; vstart = sb_dense_start[bb]; }
-            double Ar[SB_MAXBLOCK], Ir[SB_MAXBLOCK];
+        double Ar[SB_TOPMAX], Ir[SB_TOPMAX];
 #pragma unroll
-            for (int j = 0; j < SB_MAXBLOCK; j++) {
-                Ar[j] = (i < nb && j < nb) ? ((i == j) ? di[vstart + i] : blk[off + i * nb + j]) : ((i == j) ? 1.0 : 0.0);
-                Ir[j] = (i == j) ? 1.0 : 0.0;
-            }
-            int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
-            const int base = lane & ~7;
+        for (int j = 0; j < SB_TOPMAX; j++) {
+            Ar[j] = (i == j) ? dj : ((i < nb && j < nb) ? blk[off + i * nb + j] : 0.0);
+            Ir[j] = (i == j) ? 1.0 : 0.0;
+        }
+        int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
+        const int base = lane & ~7;
 #pragma unroll
-            for (int kx = 0; kx < SB_MAXBLOCK; kx++) {
-                // pivot search among rows not used yet
-                double best = (myrow < 0 && i < SB_MAXBLOCK) ? fabs(Ar[kx]) : -1.0; int who = i;
+        for (int kx = 0; kx < SB_TOPMAX; kx++) {
+            // pivot search among rows not used yet
+            double best = (myrow < 0 && i < SB_TOPMAX) ? fabs(Ar[kx]) : -1.0; int who = i;
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
-                if (i == who) myrow = kx;
-                const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
-                const double inv = 1.0 / piv;
-                const double l = (i == who) ? 0.0 : Ar[kx];
+            for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
+            if (i == who) myrow = kx;
+            const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
+            const double inv = 1.0 / piv;
+            const double l = (i == who) ? 0.0 : Ar[kx];
 #pragma unroll
-                for (int j = 0; j < SB_MAXBLOCK; j++) {
-                    const double pa = __shfl_sync(SB_FULL, Ar[j], base + who) * inv, pi_ = __shfl_sync(SB_FULL, Ir[j], base + who) * inv;
-                    if (i == who) { Ar[j] = pa; Ir[j] = pi_; } else { Ar[j] -= l * pa; Ir[j] -= l * pi_; }
-                }
-            }
-            if (bb < SB_NDENSE && myrow >= 0 && myrow < nb) {
-#pragma unroll
-                for (int j = 0; j < SB_MAXBLOCK; j++) if (j < nb) blk[off + myrow * nb + j] = Ir[j];
+            for (int j = 0; j < SB_TOPMAX; j++) {
+                const double pa = __shfl_sync(SB_FULL, Ar[j], base + who) * inv, pi_ = __shfl_sync(SB_FULL, Ir[j], base + who) * inv;
+                if (i == who) { Ar[j] = pa; Ir[j] = pi_; } else { Ar[j] -= l * pa; Ir[j] -= l * pi_; }
             }
         }
-        __syncwarp();
+        if (bb < SB_NTOP && myrow >= 0 && myrow < nb) {
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) if (j < nb) blk[off + myrow * nb + j] = Ir[j];
+        }
     }
-    // all Schur updates are done: scale the parent couplings by the inverse pivots (backward substitution = 1 fma per vertex)
-#pragma unroll
-    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) up[i] *= di[i]; }
     __syncwarp();
 }
 
-// r <- B^{-1} r for NR right-hand sides at once (independent recurrences interleave: the solve is latency-bound):
-// forward along the owned paths (registers), dense blocks (mat-vec with the explicit inverse), backward along the paths.
+// r <- B^{-1} r for NR right-hand sides at once (independent recurrences interleave: the solve is latency-bound), in three
+// warp-synchronous steps: forward along the phase-0 paths (registers) | top: root paths forward + backward, top blocks =
+// gather the children's terms, exchange by shuffles, mat-vec with the explicit inverse | backward along the phase-0 paths.
 template <int NR>
 __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[NR], const double* di, const double* up, const double* mm, const double* blk, int lane) {
 #pragma unroll
-    for (int ph = 0; ph < SB_NPH; ph++) {
-#pragma unroll
-        for (int rd = 0; rd < SB_PR; rd++) {
-            const int q = ph * SB_PR + rd;
-            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]);
-            if (len > 0) {
-                const double* mmp = mm + start;
-#pragma unroll
-                for (int a = 0; a < NR; a++) {
-                    double* rp = rr[a] + start;
-                    double av[SB_PL];
-                    double acc = rp[0];
-                    if (ph > 0) {
-#pragma unroll
-                        for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.pk[q], c); if (ch != SB_NOKID) acc -= mm[ch] * rr[a][ch]; }
-                    }
-                    av[0] = acc;
-#pragma unroll
-                    for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; }
-#pragma unroll
-                    for (int pos = 0; pos < SB_PL; pos++) if (pos < len && (pos > 0 || ph > 0)) rp[pos] = av[pos];
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (SB_NDENSE > 0) { // dense blocks: lane = block*8 + row
-        const int bb = lane >> 3, i = lane & 7;
-        int nb = 0, off = 0, vstart = 0;
-        if (bb < SB_NDENSE) { nb = sb_dense_n[bb]; off = sb_dense_off[bb]; vstart = sb_dense_start[bb]; }
-        if (i < nb) {
+    for (int rd = 0; rd < SB_PR; rd++) {
+        const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
+        if (len > 0) {
+            const double* mmp = mm + start;
 #pragma unroll
             for (int a = 0; a < NR; a++) {
-                double acc = rr[a][vstart + i];
+                double* rp = rr[a] + start;
+                double av[SB_PL];
+                double acc = rp[0];
 #pragma unroll
-                for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) acc -= mm[ch] * rr[a][ch]; }
-                rr[a][vstart + i] = acc;
+                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; }
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
             }
         }
-        __syncwarp();
-        double xi[NR];
-#pragma unroll
-        for (int a = 0; a < NR; a++) { xi[a] = 0; if (i < nb) for (int j = 0; j < nb; j++) xi[a] = fma(blk[off + i * nb + j], rr[a][vstart + j], xi[a]); }
-        __syncwarp();
-        if (i < nb) {
-#pragma unroll
-            for (int a = 0; a < NR; a++) rr[a][vstart + i] = xi[a];
-        }
-        __syncwarp();
     }
+    __syncwarp();
 #pragma unroll
-    for (int ph = SB_NPH - 1; ph >= 0; ph--) {
+    for (int rd = 0; rd < SB_TR; rd++) {
+        const int start = SB_P_START(S.rh[rd]), len = SB_P_LEN(S.rh[rd]);
+        if (len > 0) {
+            const double *mmp = mm + start, *upp = up + start, *dip = di + start;
 #pragma unroll
-        for (int rd = 0; rd < SB_PR; rd++) {
-            const int q = ph * SB_PR + rd;
-            const int start = SB_P_START(S.ph[q]), len = SB_P_LEN(S.ph[q]), par = SB_P_PAR(S.ph[q]);
-            if (len > 0) {
-                const double *upp = up + start, *dip = di + start;
+            for (int a = 0; a < NR; a++) {
+                double* rp = rr[a] + start;
+                double av[SB_TL];
+                double acc = rp[0];
 #pragma unroll
-                for (int a = 0; a < NR; a++) {
-                    double* rp = rr[a] + start;
-                    double xs[SB_PL];
-                    double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
+                for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.rk[rd], c); if (ch != SB_NOKID) acc = fma(-mm[ch], rr[a][ch], acc); }
+                av[0] = acc;
 #pragma unroll
-                    for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, rp[pos] * dip[pos]); xs[pos] = xv; }
+                for (int pos = 1; pos < SB_TL; pos++) if (pos < len) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; }
+                double xv = 0.0;
 #pragma unroll
-                    for (int pos = 0; pos < SB_PL; pos++) if (pos < len) rp[pos] = xs[pos];
-                }
+                for (int pos = SB_TL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, av[pos] * dip[pos]); av[pos] = xv; }
+#pragma unroll
+                for (int pos = 0; pos < SB_TL; pos++) if (pos < len) rp[pos] = av[pos];
             }
         }
-        __syncwarp();
     }
+    if (SB_NTOP > 0) { // top blocks: lane = block*8 + row
+        const int bb = lane >> 3, i = lane & 7, base = lane & ~7;
+        int nb = 0, off = 0, vstart = 0;
+        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; vstart = sb_top_start[bb]; }
+        double g[NR], brow[SB_TOPMAX];
+#pragma unroll
+        for (int j = 0; j < SB_TOPMAX; j++) brow[j] = (i < nb && j < nb) ? blk[off + i * nb + j] : 0.0;
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            g[a] = 0;
+            if (i < nb) {
+                g[a] = rr[a][vstart + i];
+#pragma unroll
+                for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) g[a] = fma(-mm[ch], rr[a][ch], g[a]); }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            double xi = 0;
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) xi = fma(brow[j], __shfl_sync(SB_FULL, g[a], base + j), xi);
+            if (i < nb) rr[a][vstart + i] = xi;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int rd = 0; rd < SB_PR; rd++) {
+        const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]), par = SB_P_PAR(S.ph[rd]);
+        if (len > 0) {
+            const double *upp = up + start, *dip = di + start;
+#pragma unroll
+            for (int a = 0; a < NR; a++) {
+                double* rp = rr[a] + start;
+                double xs[SB_PL];
+                double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
+#pragma unroll
+                for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, rp[pos] * dip[pos]); xs[pos] = xv; }
+#pragma unroll
+                for (int pos = 0; pos < SB_PL; pos++) if (pos < len) rp[pos] = xs[pos];
+            }
+        }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, const double* r, double& s1, double& s2, int lane) {
