@@ -437,11 +437,14 @@ def generate(m: Model):
     PR = (len(paths0) + 31) // 32
     TL = max([len(p) for p in rpaths] + [1])
     TR = max(1, (len(rpaths) + 31) // 32)
-    nat = []  # new index -> natural index
-    for p in paths0 + rpaths:
-        nat += p
+    # new index -> natural index: top blocks first, then the paths by decreasing length of their longest J_local row, so that
+    # the long rows share a round of the row-parallel sweeps (row i belongs to lane i % 32, round i / 32) and the ELL
+    # storage of each round is only as wide as its longest row
+    nat = []
     for b in top_blocks:
         nat += b
+    for p in sorted(paths0 + rpaths, key=lambda p: -max(len(L.rows[v]) for v in p)):
+        nat += p
     assert sorted(nat) == list(range(N)) and N <= 1022
     # roles of the J_local entries in this schedule: 0 diag, 1 "up" (row child, col parent), 2 "lo" (row parent, col child),
     # 3 top-block entry (target = offset into the block store)
@@ -471,17 +474,19 @@ def generate(m: Model):
     for new_i, old_i in enumerate(nat):
         inv[old_i] = new_i
     R = (N + 31) // 32
-    WD = max(len(r) for r in L.rows)
+    wdr = [max([len(L.rows[nat[ni]]) for ni in range(r * 32, min(N, r * 32 + 32))] + [1]) for r in range(R)]  # ELL width per round
+    eoff = [sum(wdr[:r]) for r in range(R)]
+    ELLN = sum(wdr)
     assert NB <= 1023 and TOPSTORE <= 1023
-    ell_coef = [0.0] * (R * WD * 32)
-    ell_idx = [0] * (R * WD * 32)
+    ell_coef = [0.0] * (ELLN * 32)
+    ell_idx = [0] * (ELLN * 32)
     for i in range(N):
         ni = inv[i]
         lane, r = ni % 32, ni // 32
         for w, ((j, c, b), (rk, ri)) in enumerate(zip(L.rows[i], sroles[i])):
             tgt = inv[ri] if rk == 2 else (ri if rk == 3 else 0)
-            ell_coef[(r * WD + w) * 32 + lane] = c
-            ell_idx[(r * WD + w) * 32 + lane] = inv[j] | (b << BITS) | (rk << KSH) | (tgt << TSH)
+            ell_coef[(eoff[r] + w) * 32 + lane] = c
+            ell_idx[(eoff[r] + w) * 32 + lane] = inv[j] | (b << BITS) | (rk << KSH) | (tgt << TSH)
     pq_coef = [0.0] * (R * 2 * 32)
     pq_idx = [0] * (R * 32)
     for (i, c, b) in L.hub["p"]:
@@ -534,9 +539,12 @@ def generate(m: Model):
         for pos, v in enumerate(b):
             t_kids[bi * 8 + pos] = _kids(v)
         assert [inv[v] for v in b] == list(range(inv[b[0]], inv[b[0]] + len(b)))
-    for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_WD", WD), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NTOP", len(top_blocks)), ("SB_TOPMAX", TOPMAX),
+    for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_ELLN", ELLN), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NTOP", len(top_blocks)), ("SB_TOPMAX", TOPMAX),
                       ("SB_TOPSTORE", max(1, TOPSTORE)), ("SB_PL", PL), ("SB_PR", PR), ("SB_TL", TL), ("SB_TR", TR)]:
         W(f"#define {name} {val}")
+    _sel = lambda vals: " : ".join(f"(r) == {r} ? {v}" for r, v in enumerate(vals[:-1])) + (" : " if len(vals) > 1 else "") + str(vals[-1])
+    W(f"#define SB_WDR(r) ({_sel(wdr)})   // ELL width of round r")
+    W(f"#define SB_EOFF(r) ({_sel(eoff)})  // first ELL slot of round r")
     W(_arr("short", "sb_nat", nat))
     W(_arr("short", "sb_newidx", inv))
     W(_arr("double", "sb_ell_coef", ell_coef, "{!r}"))

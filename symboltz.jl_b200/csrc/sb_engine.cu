@@ -299,9 +299,12 @@ struct SbSolveArgs {
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
 #define SB_SM_BLK (SB_SM_BD + SB_NB)
 #define SB_SM_KP (SB_SM_BLK + SB_TOPSTORE)
-#define SB_SM_DOUBLES (SB_SM_KP + 8 + 24)
+#define SB_SM_DOUBLES (SB_SM_KP + 8 + 48)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
+#ifndef SB_MINBLOCKS
+#define SB_MINBLOCKS 8
+#endif
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
 // packed schedule fields (generator: lower.py).  SB_IDXBITS = 8 when N <= 254 and NB <= 255 (byte extraction), else 10 (N <= 1022).
@@ -342,8 +345,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Per-lane schedules produced by the code generator, kept in registers for the lifetime of the kernel
 // (every loop over them is fully unrolled so that the arrays never become addressable local memory).
 struct SbLane {
-    double ec[SB_R * SB_WD];   // J_local ELL coefficients of the rows owned by this lane
-    unsigned ei[SB_R * SB_WD]; // col | basis<<8 | role<<16 | target<<20
+    double ec[SB_ELLN];         // J_local ELL coefficients of the rows owned by this lane
+    unsigned ei[SB_ELLN]; // col | basis<<8 | role<<16 | target<<20
     double pqc[SB_R * 2];      // hub vectors p, q at the owned rows
     unsigned pqi[SB_R];
     double phc[SB_TPH], psc[SB_TPS]; // hub functionals φ, ψ: one term per lane and slot
@@ -354,7 +357,7 @@ struct SbLane {
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
     __device__ __forceinline__ void load(int lane) {
 #pragma unroll
-        for (int e = 0; e < SB_R * SB_WD; e++) { ec[e] = sb_ell_coef[e * 32 + lane]; ei[e] = sb_ell_idx[e * 32 + lane]; }
+        for (int e = 0; e < SB_ELLN; e++) { ec[e] = sb_ell_coef[e * 32 + lane]; ei[e] = sb_ell_idx[e * 32 + lane]; }
 #pragma unroll
         for (int r = 0; r < SB_R; r++) { pqc[2 * r] = sb_pq_coef[(2 * r) * 32 + lane]; pqc[2 * r + 1] = sb_pq_coef[(2 * r + 1) * 32 + lane]; pqi[r] = sb_pq_idx[r * 32 + lane]; }
 #pragma unroll
@@ -408,7 +411,7 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 // Batched look-up of the basis at the stage times of one Rosenbrock attempt: slots 1..5 = t + c_s·dt (and, if with0, slot 0 = t
 // together with ḃ(t)).  Lanes 0..5 locate their slot's table node in parallel and publish (node, w, hs, τ) through shared memory;
 // then all lanes sweep the (slot, basis) items, so that every L2 access of the attempt is in flight at once.
-__device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x4*/, int lane) {
+__device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x8*/, int lane) {
     int jend = jt;
     if (lane < 6) {
         const double tau = t + ((lane == 0) ? 0.0 : cc[lane]) * dt;
@@ -417,10 +420,11 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
         const double tj = __ldg(tb.t + j), hs = (__ldg(tb.t + j + 1) - tj) / tb.msub;
         const double f = (tau - tj) / hs;
         const int sidx = max(0, min((int)f, tb.msub - 1));
-        slotp[lane * 4 + 0] = __longlong_as_double((long long)j * tb.msub + sidx);
-        slotp[lane * 4 + 1] = f - sidx;
-        slotp[lane * 4 + 2] = hs;
-        slotp[lane * 4 + 3] = tau;
+        const double w = f - sidx, w1 = w - 1.0;
+        double* sp = slotp + lane * 8; // table node and the cubic-Hermite weights of (v0, d0, v1, d1); slot 0 also the derivative weights
+        sp[0] = __longlong_as_double((long long)j * tb.msub + sidx);
+        sp[1] = (1 + 2 * w) * w1 * w1; sp[2] = w * w1 * w1 * hs; sp[3] = w * w * (3 - 2 * w); sp[4] = w * w * w1 * hs;
+        sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
         jend = j;
     }
     jend = __shfl_sync(SB_FULL, jend, 5);
@@ -428,15 +432,15 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
     const int s0 = with0 ? 0 : 1;
     for (int q = s0 * SB_NB + lane; q < 6 * SB_NB; q += SB_WARP) {
         const int s = q / SB_NB, m = q - s * SB_NB;
-        const long long node = __double_as_longlong(slotp[s * 4 + 0]);
-        const double w = slotp[s * 4 + 1], hs = slotp[s * 4 + 2], w1 = w - 1.0;
+        const double* sp = slotp + s * 8;
+        const long long node = __double_as_longlong(sp[0]);
         const unsigned pk = sb_basis_pack[m];
         const int be = SB_LO16(pk);
         const double* n0 = tb.tab + (size_t)node * 2 * SB_NBETA;
         const double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n0 + 2 * SB_NBETA + be), d1 = __ldg(n0 + 3 * SB_NBETA + be);
         const double kk = kp[SB_HI16(pk)];
-        bs[q] = kk * ((1 + 2 * w) * w1 * w1 * v0 + w * w1 * w1 * hs * d0 + w * w * (3 - 2 * w) * v1 + w * w * w1 * hs * d1);
-        if (s == 0) bdv[m] = kk * (6 * w * w1 * (v0 - v1) / hs + (3 * w - 1) * w1 * d0 + w * (3 * w - 2) * d1);
+        bs[q] = kk * (sp[1] * v0 + sp[2] * d0 + sp[3] * v1 + sp[4] * d1);
+        if (s == 0) bdv[m] = kk * (sp[5] * (v0 - v1) + sp[6] * d0 + sp[7] * d1);
     }
     return jend;
 }
@@ -456,7 +460,7 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
         const int i = r * 32 + lane;
         double acc = S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
 #pragma unroll
-        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
+        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; acc += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
         if (FUSE) { if (i < SB_N) acc += radd[r] + hd * dT[i]; }
         if (i < SB_N) out[i] = acc;
     }
@@ -475,7 +479,7 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
         const int pb = SB_LO16(S.pqi[r]), qb = SB_HI16(S.pqi[r]);
         double acc = S.pqc[2 * r] * (bd[pb] * sphi + b[pb] * sphid) + S.pqc[2 * r + 1] * (bd[qb] * spsi + b[qb] * spsid);
 #pragma unroll
-        for (int w = 0; w < SB_WD; w++) { const int e = r * SB_WD + w; acc += S.ec[e] * bd[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
+        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; acc += S.ec[e] * bd[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
         const int i = r * 32 + lane;
         if (i < SB_N) out[i] = acc;
     }
@@ -496,8 +500,8 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         const int i = r * 32 + lane;
         double dacc = x, uacc = 0;
 #pragma unroll
-        for (int w = 0; w < SB_WD; w++) {
-            const int e = r * SB_WD + w;
+        for (int w = 0; w < SB_WDR(r); w++) {
+            const int e = SB_EOFF(r) + w;
             const unsigned ix = S.ei[e];
             const double v = -S.ec[e] * b[SB_E_B(ix)];
             const int kind = SB_E_KIND(ix), tgt = SB_E_TGT(ix);
@@ -702,7 +706,12 @@ __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, co
 
 // Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
 // queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
-__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel(SbSolveArgs A) {
+#ifdef SB_NOLB
+__global__ void sb_integrate_kernel
+#else
+__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_integrate_kernel
+#endif
+    (SbSolveArgs A) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31;
     double* sm = sm_all + (threadIdx.x >> 5) * SB_SM_DOUBLES;
@@ -801,20 +810,45 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA) sb_integrate_kernel
                     double* ks = K + s * SB_N;
                     const double hd_ = dt * cd[s];
                     if (s > 0) {
-                        double ca[7], cq[7], Racc[SB_R];
-#pragma unroll
-                        for (int j = 0; j < 7; j++) { ca[j] = cA[s][j]; cq[j] = cC[s][j] * idt; }
+                        // U_s = u + Σ_{j<s} a_sj k_j (stages 7, 8: U_s = U_{s-1} + k_{s-1}, the tableau rows repeat) and R_s = Σ_{j<s} (C_sj/dt) k_j;
+                        // the switch enters the unrolled sum at the oldest-but-(s-2) stage so that absent terms cost nothing
+                        double Racc[SB_R], ua[SB_R];
+                        int ii[SB_R];
+                        const bool inc = s >= 6;
                         double* kprev = ks - SB_N;
+                        {
+                            const double al = cA[s][s - 1], cl = cC[s][s - 1] * idt;
 #pragma unroll
-                        for (int r = 0; r < SB_R; r++) {
-                            const int i = min(r * 32 + lane, SB_N - 1);
-                            const double kp_ = kprev[i] + Zp[i] * c1p + Zq[i] * c2p;
-                            double ua = u[i], ra = 0;
-#pragma unroll
-                            for (int j = 0; j < 7; j++) { const double kj = (j < s - 1) ? K[j * SB_N + i] : ((j == s - 1) ? kp_ : 0.0); ua = fma(ca[j], kj, ua); ra = fma(cq[j], kj, ra); }
-                            Racc[r] = ra;
-                            if (r * 32 + lane < SB_N) { U[i] = ua; kprev[i] = kp_; }
+                            for (int r = 0; r < SB_R; r++) {
+                                const int i = min(r * 32 + lane, SB_N - 1);
+                                ii[r] = i;
+                                const double kp_ = kprev[i] + Zp[i] * c1p + Zq[i] * c2p;
+                                ua[r] = fma(al, kp_, inc ? U[i] : u[i]);
+                                Racc[r] = cl * kp_;
+                                if (r * 32 + lane < SB_N) kprev[i] = kp_;
+                            }
                         }
+#define SB_STAGE_TERM(j, WITHU)                                                                                   \
+    {                                                                                                             \
+        const double a_ = cA[s][j], c_ = cC[s][j] * idt;                                                          \
+        _Pragma("unroll") for (int r = 0; r < SB_R; r++) {                                                        \
+            const double kj = K[(j) * SB_N + ii[r]];                                                              \
+            if (WITHU && !inc) ua[r] = fma(a_, kj, ua[r]);                                                        \
+            Racc[r] = fma(c_, kj, Racc[r]);                                                                       \
+        }                                                                                                         \
+    }
+                        switch (s - 1) {
+                            case 6: SB_STAGE_TERM(5, false) [[fallthrough]];
+                            case 5: SB_STAGE_TERM(4, false) [[fallthrough]];
+                            case 4: SB_STAGE_TERM(3, true) [[fallthrough]];
+                            case 3: SB_STAGE_TERM(2, true) [[fallthrough]];
+                            case 2: SB_STAGE_TERM(1, true) [[fallthrough]];
+                            case 1: SB_STAGE_TERM(0, true) [[fallthrough]];
+                            default: break;
+                        }
+#undef SB_STAGE_TERM
+#pragma unroll
+                        for (int r = 0; r < SB_R; r++) if (r * 32 + lane < SB_N) U[ii[r]] = ua[r];
                         __syncwarp();
                         sb_eval_f<true>(S, bs + cslot[s] * SB_NB, U, ks, lane, Racc, hd_, dT); nf++;
                     } else {
