@@ -435,15 +435,19 @@ def generate(m: Model):
     assert len(top_blocks) <= 3 and all(len(b) <= 8 for b in top_blocks)
     PL = max(len(p) for p in paths0)
     PR = (len(paths0) + 31) // 32
+    # single-vertex root paths share the top-block lanes' gather code (lanes after the block lanes) as long as they fit in the warp
+    singles = [p[0] for p in rpaths if len(p) == 1][:max(0, 32 - 8 * len(top_blocks))]
+    allpaths = paths0 + rpaths
+    rpaths = [p for p in rpaths if not (len(p) == 1 and p[0] in singles)]
     TL = max([len(p) for p in rpaths] + [1])
-    TR = max(1, (len(rpaths) + 31) // 32)
+    TR = (len(rpaths) + 31) // 32
     # new index -> natural index: top blocks first, then the paths by decreasing length of their longest J_local row, so that
     # the long rows share a round of the row-parallel sweeps (row i belongs to lane i % 32, round i / 32) and the ELL
     # storage of each round is only as wide as its longest row
     nat = []
     for b in top_blocks:
         nat += b
-    for p in sorted(paths0 + rpaths, key=lambda p: -max(len(L.rows[v]) for v in p)):
+    for p in sorted(allpaths, key=lambda p: -max(len(L.rows[v]) for v in p)):
         nat += p
     assert sorted(nat) == list(range(N)) and N <= 1022
     # roles of the J_local entries in this schedule: 0 diag, 1 "up" (row child, col parent), 2 "lo" (row parent, col child),
@@ -457,7 +461,7 @@ def generate(m: Model):
             elif i in tblk_of and j in tblk_of:
                 assert tblk_of[i][0] == tblk_of[j][0]
                 bb, nbk = tblk_of[i][0], len(top_blocks[tblk_of[i][0]])
-                rr.append((3, toff[bb] + tblk_of[i][1] * nbk + tblk_of[j][1]))
+                rr.append((3, N + toff[bb] + tblk_of[i][1] * nbk + tblk_of[j][1]))  # the block store follows mm[N] in shared memory
             elif L.parent[i] == j:
                 rr.append((1, i))
             elif L.parent[j] == i:
@@ -477,7 +481,7 @@ def generate(m: Model):
     wdr = [max([len(L.rows[nat[ni]]) for ni in range(r * 32, min(N, r * 32 + 32))] + [1]) for r in range(R)]  # ELL width per round
     eoff = [sum(wdr[:r]) for r in range(R)]
     ELLN = sum(wdr)
-    assert NB <= 1023 and TOPSTORE <= 1023
+    assert NB <= 1023 and N + TOPSTORE <= (4095 if BITS == 8 else 1023)
     ell_coef = [0.0] * (ELLN * 32)
     ell_idx = [0] * (ELLN * 32)
     for i in range(N):
@@ -533,14 +537,19 @@ def generate(m: Model):
             kid[rd * 32 + lane] = _kids(p[0])
         return head, kid
     p_head, p_kids = _paths(paths0, PR, 0)
-    r_head, r_kids = _paths(rpaths, TR, 8 * len(top_blocks))
-    t_kids = [NOKIDS] * 32
+    r_head, r_kids = _paths(rpaths, max(1, TR), 8 * len(top_blocks) + len(singles))
+    t_kids, t_vert = [NOKIDS] * 32, [NONE] * 32
+    for q, v in enumerate(singles):
+        t_kids[8 * len(top_blocks) + q] = _kids(v)
+        t_vert[8 * len(top_blocks) + q] = inv[v]
     for bi, b in enumerate(top_blocks):
         for pos, v in enumerate(b):
             t_kids[bi * 8 + pos] = _kids(v)
+            t_vert[bi * 8 + pos] = inv[v]
         assert [inv[v] for v in b] == list(range(inv[b[0]], inv[b[0]] + len(b)))
     for name, val in [("SB_IDXBITS", BITS), ("SB_R", R), ("SB_ELLN", ELLN), ("SB_TPH", TPH), ("SB_TPS", TPS), ("SB_NTOP", len(top_blocks)), ("SB_TOPMAX", TOPMAX),
-                      ("SB_TOPSTORE", max(1, TOPSTORE)), ("SB_PL", PL), ("SB_PR", PR), ("SB_TL", TL), ("SB_TR", TR)]:
+                      ("SB_TOPSTORE", max(1, TOPSTORE)), ("SB_PL", PL), ("SB_PR", PR), ("SB_TL", TL), ("SB_TR", TR), ("SB_NSINGLE", len(singles)),
+                      ("SB_UNIQUE_TARGETS", int(all(len({(rk, ri) for (rk, ri) in sroles[i] if rk >= 2}) == sum(1 for (rk, ri) in sroles[i] if rk >= 2) for i in range(N))))]:
         W(f"#define {name} {val}")
     _sel = lambda vals: " : ".join(f"(r) == {r} ? {v}" for r, v in enumerate(vals[:-1])) + (" : " if len(vals) > 1 else "") + str(vals[-1])
     W(f"#define SB_WDR(r) ({_sel(wdr)})   // ELL width of round r")
@@ -560,6 +569,7 @@ def generate(m: Model):
     W(_arr("unsigned int", "sb_root_head", r_head, "{}u"))
     W(_arr("unsigned int", "sb_root_kids", r_kids, "{}u"))
     W(_arr("unsigned int", "sb_top_kids", t_kids, "{}u"))
+    W(_arr("unsigned int", "sb_top_vert", t_vert, "{}u"))
     W(_arr("int", "sb_top_n", [len(b) for b in top_blocks]))
     W(_arr("int", "sb_top_off", toff[:-1]))
     W(_arr("int", "sb_top_start", [inv[b[0]] for b in top_blocks]))

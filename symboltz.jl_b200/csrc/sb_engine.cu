@@ -293,12 +293,12 @@ struct SbSolveArgs {
 #define SB_SM_DI (SB_SM_F0 + SB_N)
 #define SB_SM_UP (SB_SM_DI + SB_N)
 #define SB_SM_MM (SB_SM_UP + SB_N)
-#define SB_SM_ZP (SB_SM_MM + SB_N)
+#define SB_SM_BLK (SB_SM_MM + SB_N) // must follow mm: the factorisation scatters into mm and blk through one index
+#define SB_SM_ZP (SB_SM_BLK + SB_TOPSTORE)
 #define SB_SM_ZQ (SB_SM_ZP + SB_N)
 #define SB_SM_BS (SB_SM_ZQ + SB_N)
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
-#define SB_SM_BLK (SB_SM_BD + SB_NB)
-#define SB_SM_KP (SB_SM_BLK + SB_TOPSTORE)
+#define SB_SM_KP (SB_SM_BD + SB_NB)
 #define SB_SM_DOUBLES (SB_SM_KP + 8 + 48)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
@@ -352,8 +352,8 @@ struct SbLane {
     double phc[SB_TPH], psc[SB_TPS]; // hub functionals φ, ψ: one term per lane and slot
     unsigned phi[SB_TPH], psi[SB_TPS];
     unsigned ph[SB_PR], pk[SB_PR]; // owned phase-0 elimination paths (contiguous index ranges): start|len<<8|parent<<16, first-vertex children
-    unsigned rh[SB_TR], rk[SB_TR]; // owned root paths (the part of the top that is not in a block)
-    unsigned dk;               // top-block member owned by this lane (lane = block*8+row): its forest children
+    unsigned rh[SB_TR + 1], rk[SB_TR + 1]; // owned multi-vertex root paths (the part of the top that is neither in a block nor a single vertex)
+    unsigned tv, dk;           // top vertex owned by this lane (block member: lane = block*8+row, or single root) and its forest children
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
     __device__ __forceinline__ void load(int lane) {
 #pragma unroll
@@ -368,7 +368,7 @@ struct SbLane {
         for (int q = 0; q < SB_PR; q++) { ph[q] = sb_path_head[q * 32 + lane]; pk[q] = sb_path_kids[q * 32 + lane]; }
 #pragma unroll
         for (int q = 0; q < SB_TR; q++) { rh[q] = sb_root_head[q * 32 + lane]; rk[q] = sb_root_kids[q * 32 + lane]; }
-        dk = sb_top_kids[lane];
+        dk = sb_top_kids[lane]; tv = sb_top_vert[lane];
 #pragma unroll
         for (int r = 0; r < SB_NBR; r++) { int m = r * 32 + lane; bp[r] = (m < SB_NB) ? sb_basis_pack[m] : 0u; }
     }
@@ -430,6 +430,16 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
     jend = __shfl_sync(SB_FULL, jend, 5);
     __syncwarp();
     const int s0 = with0 ? 0 : 1;
+    // pull the 2 x 2 table rows of every slot into L1 first (one round trip to L2 for the whole attempt instead of one per sweep iteration)
+    {
+        constexpr int LINES = (4 * SB_NBETA * 8 + 127) / 128 + 1;
+        for (int q = s0 * LINES + lane; q < 6 * LINES; q += SB_WARP) {
+            const int s = q / LINES, l = q - s * LINES;
+            const long long node = __double_as_longlong(slotp[s * 8]);
+            const char* pa = (const char*)(tb.tab + (size_t)node * 2 * SB_NBETA) + l * 128;
+            if (l * 128 < 4 * SB_NBETA * 8 + 120) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+        }
+    }
     for (int q = s0 * SB_NB + lane; q < 6 * SB_NB; q += SB_WARP) {
         const int s = q / SB_NB, m = q - s * SB_NB;
         const double* sp = slotp + s * 8;
@@ -507,7 +517,13 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             const int kind = SB_E_KIND(ix), tgt = SB_E_TGT(ix);
             if (kind == 0) dacc += v;
             else if (kind == 1) uacc += v;
-            else if (S.ec[e] != 0.0) { if (kind == 2) mm[tgt] += v; else blk[tgt] += v; }
+            else if (S.ec[e] != 0.0) { // multiplier (target < N) or top-block entry (target >= N: blk follows mm)
+#if SB_UNIQUE_TARGETS
+                mm[tgt] = v;
+#else
+                mm[tgt] += v;
+#endif
+            }
         }
         if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
@@ -537,7 +553,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
     __syncwarp();
     // top: root paths (fed by phase-0 paths only) ...
 #pragma unroll
-    for (int rd = 0; rd < SB_TR; rd++) {
+    for (int rd = 0; rd < SB_TR; rd++) { // (no such paths in the ΛCDM / w0waCDM models: SB_TR = 0)
         const int start = SB_P_START(S.rh[rd]), len = SB_P_LEN(S.rh[rd]);
         if (len > 0) {
             double* dip = di + start; double* mmp = mm + start; double* upp = up + start;
@@ -559,23 +575,24 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             upp[len - 1] = 0;
         }
     }
-    // ... and top blocks: gather the children's Schur terms into the diagonal, then Gauss-Jordan with partial pivoting, one
-    // matrix row [A | I] per lane (lane = block*8 + row), rows exchanged by warp shuffles within the 8-lane group ->
-    // explicit inverse (block solves become mat-vecs)
-    if (SB_NTOP > 0) {
+    // ... and top vertices (block members and single roots): gather the children's Schur terms into the diagonal; singles
+    // are done with that; blocks: Gauss-Jordan with partial pivoting, one matrix row [A | I] per lane (lane = block*8 + row),
+    // rows exchanged by warp shuffles within the 8-lane group -> explicit inverse (block solves become mat-vecs)
+    {
         const int bb = lane >> 3, i = lane & 7;
-        int nb = 0, off = 0, vstart = 0;
-        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; vstart = sb_top_start[bb]; }
+        int nb = 0, off = 0;
+        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; }
         double dj = 1.0;
-        if (i < nb) {
-            dj = di[vstart + i];
+        if (S.tv != SB_NOKID) {
+            dj = di[S.tv];
 #pragma unroll
             for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
+            if (i >= nb) { di[S.tv] = 1.0 / dj; up[S.tv] = 0; }
         }
         double Ar[SB_TOPMAX], Ir[SB_TOPMAX];
 #pragma unroll
         for (int j = 0; j < SB_TOPMAX; j++) {
-            Ar[j] = (i == j) ? dj : ((i < nb && j < nb) ? blk[off + i * nb + j] : 0.0);
+            Ar[j] = (i == j) ? ((i < nb) ? dj : 1.0) : ((i < nb && j < nb) ? blk[off + i * nb + j] : 0.0);
             Ir[j] = (i == j) ? 1.0 : 0.0;
         }
         int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
@@ -628,7 +645,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
     }
     __syncwarp();
 #pragma unroll
-    for (int rd = 0; rd < SB_TR; rd++) {
+    for (int rd = 0; rd < SB_TR; rd++) { // (no such paths in the ΛCDM / w0waCDM models: SB_TR = 0)
         const int start = SB_P_START(S.rh[rd]), len = SB_P_LEN(S.rh[rd]);
         if (len > 0) {
             const double *mmp = mm + start, *upp = up + start, *dip = di + start;
@@ -650,28 +667,32 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             }
         }
     }
-    if (SB_NTOP > 0) { // top blocks: lane = block*8 + row
+    { // top vertices: block members (lane = block*8 + row) and single roots gather their children's terms in one pass
         const int bb = lane >> 3, i = lane & 7, base = lane & ~7;
-        int nb = 0, off = 0, vstart = 0;
-        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; vstart = sb_top_start[bb]; }
+        int nb = 0, off = 0;
+        if (bb < SB_NTOP) { nb = sb_top_n[bb]; off = sb_top_off[bb]; }
+        const bool mine = S.tv != SB_NOKID, inblk = i < nb;
         double g[NR], brow[SB_TOPMAX];
+        const double dtv = (mine && !inblk) ? di[S.tv] : 0.0;
 #pragma unroll
-        for (int j = 0; j < SB_TOPMAX; j++) brow[j] = (i < nb && j < nb) ? blk[off + i * nb + j] : 0.0;
+        for (int j = 0; j < SB_TOPMAX; j++) brow[j] = (inblk && j < nb) ? blk[off + i * nb + j] : 0.0;
 #pragma unroll
         for (int a = 0; a < NR; a++) {
             g[a] = 0;
-            if (i < nb) {
-                g[a] = rr[a][vstart + i];
+            if (mine) {
+                g[a] = rr[a][S.tv];
 #pragma unroll
                 for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) g[a] = fma(-mm[ch], rr[a][ch], g[a]); }
             }
         }
 #pragma unroll
         for (int a = 0; a < NR; a++) {
-            double xi = 0;
+            double xi = g[a] * dtv; // single root: forward and backward substitution are one division by the pivot
+            if (SB_NTOP > 0) {
 #pragma unroll
-            for (int j = 0; j < SB_TOPMAX; j++) xi = fma(brow[j], __shfl_sync(SB_FULL, g[a], base + j), xi);
-            if (i < nb) rr[a][vstart + i] = xi;
+                for (int j = 0; j < SB_TOPMAX; j++) xi = fma(brow[j], __shfl_sync(SB_FULL, g[a], base + j), xi);
+            }
+            if (mine) rr[a][S.tv] = xi;
         }
     }
     __syncwarp();
