@@ -7,7 +7,7 @@
  *
  * Conventions: plain pointers and sizes only; doubles are IEEE binary64; τ in 1/H0, k in H0/c (reference
  * docs/src/conventions.md:14-18).  Pointers named d* are DEVICE pointers (cudaMalloc / torch / CUDA.jl memory), all others
- * are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points are
+ * are host pointers (the *_host entry points take host pointers only).  `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points are
  * asynchronous on that stream.  Return value: 0 (or a non-negative count where stated) on success, negative on error
  * (-1000 - cudaError for CUDA failures).  There is no CPU fallback: without a GPU every device entry point fails.
  *
@@ -70,6 +70,17 @@ int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, co
                 const double* dks, const double* dusave, double* dS, int scale_k, int nS, double taurec, void* stream);
 int sbm_smem_bytes(void);
 
+/* One-call HOST-buffer variant of the perturbation solve (for hosts without a device allocator: Julia without CUDA.jl, C):
+ * every pointer is a host pointer; the library allocates device memory, uploads the nb background knots, builds the β-table
+ * and interval look-up (msub = 16, 4096 entries), orders the work queue by descending k, runs sbm_solvept and -- when the
+ * outputs are non-NULL -- sbm_delta_m at tend (delta_m[nk]) and sbm_sources on the saved states (S[nk][nS][nsave], needs
+ * nsave > 0), and downloads.  usave[nk][nsave][N], uend[nk][N], retcode[nk], stats[nk][4], delta_m, S may each be NULL.
+ * Blocking.  (replaces solvept(ptprob, bgsol, ks, ptivini; saveat, output_func), src/solve.jl:543-569, as called from
+ * solve(prob, ks), src/solve.jl:398, spectrum_matter, src/observables/fourier.jl:90-97, and source_grid, fourier.jl:279) */
+int sbm_solvept_host(const double* P, int nb, const double* t, const double* y, const double* dy, int nk, const double* ks, const double* tini, double tend, int nsave,
+                     const double* saveat, double reltol, double abstol, int maxiters, double* usave, double* uend, int* retcode, long long* stats, double* delta_m, int nS,
+                     double taurec, int scale_k, double* S);
+
 /* Host-side diagnostics of the generated code (unit tests of the generator; not a solve path). */
 int sbm_debug_fjt(const double* P, const double* y, const double* yp, double tau, double k, const double* u, double* f, double* J, double* dT);
 int sbm_debug_split(const double* P, const double* y, const double* yp, double tau, double k, double* Jloc, double* hubs);
@@ -102,6 +113,14 @@ int sbl_cl(int nl, int nk, int k0, int k1, const double* dck, const double* dThe
 /* Standalone barycentric k-interpolation dSf[nk][n2t] = Σ_j dBw[k][j] dSc[j][n2t] (replaces source_kinterp,
  * src/observables/fourier.jl:232-247) */
 int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, double* dSf, void* stream);
+
+/* One-call HOST-buffer variant of k-interpolation + line of sight + C_l: builds the j_l table on the reference's grid
+ * (range(0, xmax, length = trunc(xmax/dx)), tabulated up to xcut), uploads ks[nk], Bw[nk][nc] (NULL: Sc is already on the fine
+ * grid), Sc[nc or nk][nS][nt], chi[nt], wt[nt], ls[nl], ck[nk], the mode pairs, runs sbl_los + sbl_cl and downloads
+ * Cl[nmodes][nl] and, if Theta != NULL, Theta[nS][nl][nk].  Blocking.
+ * (replaces the body of spectrum_cmb(modes, prob, jl, ls), src/observables/angular.jl:293-340, after source_grid) */
+int sbl_cmb_host(int nk, const double* ks, int nc, const double* Bw, const double* Sc, int nS, int nt, const double* chi, const double* wt, int nl, const int* ls, double dx,
+                 double xmax, double xcut, const double* ck, int nmodes, const int* modeA, const int* modeB, int l_limber, double* Cl, double* Theta);
 
 #ifdef __cplusplus
 }

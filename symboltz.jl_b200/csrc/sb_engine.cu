@@ -464,15 +464,28 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
     for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[SB_HI16(S.phi[t])] * U[SB_LO16(S.phi[t])];
 #pragma unroll
     for (int t = 0; t < SB_TPS; t++) spsi += S.psc[t] * b[SB_HI16(S.psi[t])] * U[SB_LO16(S.psi[t])];
-    sphi = warp_sum(sphi); spsi = warp_sum(spsi);
+    // the butterfly reduction of the two hub sums is interleaved, level by level, with the (independent) ELL row sums so that
+    // the shuffle latencies are covered by useful work; same operand order as warp_sum
+    double acc[SB_R];
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) {
+        const int o = 16 >> r;
+        double t1 = 0, t2 = 0;
+        if (o > 0) { t1 = __shfl_xor_sync(SB_FULL, sphi, o); t2 = __shfl_xor_sync(SB_FULL, spsi, o); }
+        double a_ = 0;
+#pragma unroll
+        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; a_ += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
+        acc[r] = a_;
+        if (o > 0) { sphi += t1; spsi += t2; }
+    }
+#pragma unroll
+    for (int o = (SB_R < 5 ? 16 >> SB_R : 0); o > 0; o >>= 1) { sphi += __shfl_xor_sync(SB_FULL, sphi, o); spsi += __shfl_xor_sync(SB_FULL, spsi, o); }
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
         const int i = r * 32 + lane;
-        double acc = S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
-#pragma unroll
-        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; acc += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
-        if (FUSE) { if (i < SB_N) acc += radd[r] + hd * dT[i]; }
-        if (i < SB_N) out[i] = acc;
+        double a_ = acc[r] + S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
+        if (FUSE) { if (i < SB_N) a_ += radd[r] + hd * dT[i]; }
+        if (i < SB_N) out[i] = a_;
     }
     __syncwarp();
 }
@@ -824,33 +837,29 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 const double idet = 1.0 / (m11 * m22 - m12 * m21);
                 const double idt = 1.0 / dt;
                 // 8 stages.  Per stage: (A) lane-local: finish k_{s-1} with its pending Woodbury correction and accumulate U_s = u + Σ a_sj k_j,
-                // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve; (D) hub dot products
-                // (the rank-2 correction k_s += Z c is applied lazily in (A) of the next stage: no extra pass, no extra barrier).
+                // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve.  The hub dot products of the
+                // rank-2 correction k_s += Z c and the correction itself are applied lazily in (A) of the next stage: no extra pass, no extra barrier.
                 double c1p = 0, c2p = 0;
                 for (int s = 0; s < 8; s++) {
                     double* ks = K + s * SB_N;
                     const double hd_ = dt * cd[s];
                     if (s > 0) {
                         // U_s = u + Σ_{j<s} a_sj k_j (stages 7, 8: U_s = U_{s-1} + k_{s-1}, the tableau rows repeat) and R_s = Σ_{j<s} (C_sj/dt) k_j;
-                        // the switch enters the unrolled sum at the oldest-but-(s-2) stage so that absent terms cost nothing
+                        // absent terms are skipped by warp-uniform branches.
+                        // The Woodbury coefficients of k_{s-1} need two warp reductions (hub dot products of the solve result); their
+                        // butterfly levels are interleaved with the accumulation of the older stages, which does not depend on them.
                         double Racc[SB_R], ua[SB_R];
                         int ii[SB_R];
                         const bool inc = s >= 6;
+                        const int nold = s - 1;
                         double* kprev = ks - SB_N;
-                        {
-                            const double al = cA[s][s - 1], cl = cC[s][s - 1] * idt;
+                        double h1 = 0, h2 = 0, t1, t2;
 #pragma unroll
-                            for (int r = 0; r < SB_R; r++) {
-                                const int i = min(r * 32 + lane, SB_N - 1);
-                                ii[r] = i;
-                                const double kp_ = kprev[i] + Zp[i] * c1p + Zq[i] * c2p;
-                                ua[r] = fma(al, kp_, inc ? U[i] : u[i]);
-                                Racc[r] = cl * kp_;
-                                if (r * 32 + lane < SB_N) kprev[i] = kp_;
-                            }
-                        }
+                        for (int t = 0; t < SB_TPH; t++) h1 += S.phc[t] * bs[SB_HI16(S.phi[t])] * kprev[SB_LO16(S.phi[t])];
+#pragma unroll
+                        for (int t = 0; t < SB_TPS; t++) h2 += S.psc[t] * bs[SB_HI16(S.psi[t])] * kprev[SB_LO16(S.psi[t])];
 #define SB_STAGE_TERM(j, WITHU)                                                                                   \
-    {                                                                                                             \
+    if (nold > (j)) {                                                                                             \
         const double a_ = cA[s][j], c_ = cC[s][j] * idt;                                                          \
         _Pragma("unroll") for (int r = 0; r < SB_R; r++) {                                                        \
             const double kj = K[(j) * SB_N + ii[r]];                                                              \
@@ -858,15 +867,36 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
             Racc[r] = fma(c_, kj, Racc[r]);                                                                       \
         }                                                                                                         \
     }
-                        switch (s - 1) {
-                            case 6: SB_STAGE_TERM(5, false) [[fallthrough]];
-                            case 5: SB_STAGE_TERM(4, false) [[fallthrough]];
-                            case 4: SB_STAGE_TERM(3, true) [[fallthrough]];
-                            case 3: SB_STAGE_TERM(2, true) [[fallthrough]];
-                            case 2: SB_STAGE_TERM(1, true) [[fallthrough]];
-                            case 1: SB_STAGE_TERM(0, true) [[fallthrough]];
-                            default: break;
+#define SB_LEVEL_ISSUE(o) t1 = __shfl_xor_sync(SB_FULL, h1, o); t2 = __shfl_xor_sync(SB_FULL, h2, o);
+#define SB_LEVEL_ADD h1 += t1; h2 += t2;
+                        SB_LEVEL_ISSUE(16)
+#pragma unroll
+                        for (int r = 0; r < SB_R; r++) { const int i = min(r * 32 + lane, SB_N - 1); ii[r] = i; ua[r] = inc ? U[i] : u[i]; Racc[r] = 0; }
+                        SB_LEVEL_ADD SB_LEVEL_ISSUE(8)
+                        SB_STAGE_TERM(0, true)
+                        SB_LEVEL_ADD SB_LEVEL_ISSUE(4)
+                        SB_STAGE_TERM(1, true)
+                        SB_LEVEL_ADD SB_LEVEL_ISSUE(2)
+                        SB_STAGE_TERM(2, true)
+                        SB_LEVEL_ADD SB_LEVEL_ISSUE(1)
+                        SB_STAGE_TERM(3, true)
+                        SB_STAGE_TERM(4, false)
+                        SB_STAGE_TERM(5, false)
+                        SB_LEVEL_ADD
+                        c1p = (m22 * h1 - m12 * h2) * idet; c2p = (-m21 * h1 + m11 * h2) * idet;
+                        {
+                            const double al = cA[s][s - 1], cl = cC[s][s - 1] * idt;
+#pragma unroll
+                            for (int r = 0; r < SB_R; r++) {
+                                const int i = ii[r];
+                                const double kp_ = kprev[i] + Zp[i] * c1p + Zq[i] * c2p;
+                                ua[r] = fma(al, kp_, ua[r]);
+                                Racc[r] = fma(cl, kp_, Racc[r]);
+                                if (r * 32 + lane < SB_N) kprev[i] = kp_;
+                            }
                         }
+#undef SB_LEVEL_ISSUE
+#undef SB_LEVEL_ADD
 #undef SB_STAGE_TERM
 #pragma unroll
                         for (int r = 0; r < SB_R; r++) if (r * 32 + lane < SB_N) U[ii[r]] = ua[r];
@@ -878,8 +908,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                         __syncwarp();
                     }
                     { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); } nsolve++;
+                }
+                {
                     double s1, s2;
-                    sb_hub_dots(S, bs, ks, s1, s2, lane);
+                    sb_hub_dots(S, bs, K + 7 * SB_N, s1, s2, lane);
                     c1p = (m22 * s1 - m12 * s2) * idet; c2p = (-m21 * s1 + m11 * s2) * idet;
                 }
 #pragma unroll
@@ -1064,6 +1096,78 @@ int sbm_sources(const double* dP, int nb, const double* dt, const double* dy, co
     int n = nk * nt;
     sb_source_kernel<<<(n + 127) / 128, 128, 0, st>>>(nt, dtaus, dsrcbg, nk, dks, dusave, dS, scale_k, nS, taurec);
     SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------- host-buffer entry point
+// Everything above takes device pointers (the host layer owns the device memory).  This one-call variant takes HOST pointers
+// only, so that a host language without a CUDA allocator (Julia without CUDA.jl, plain C) can bind the path with a single
+// ccall: it uploads the background knots, builds the β-table and the interval look-up, orders the work queue by descending
+// k, launches the solve (+ Δm and the CMB sources when asked for), and downloads the results.  Same kernels, same defaults
+// (msub = 16, 4096-entry look-up) as the Python host layer, hence identical results.
+struct SbDevBuf { // frees on scope exit
+    std::vector<void*> ptrs;
+    ~SbDevBuf() { for (void* q : ptrs) cudaFree(q); }
+    template <class T> cudaError_t get(T** out, size_t n, const T* host = nullptr) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(q);
+        *out = (T*)q;
+        if (host && n) e = cudaMemcpy(q, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+
+extern "C" {
+int sbm_solvept_host(const double* P, int nb, const double* t, const double* y, const double* dy, int nk, const double* ks, const double* tini, double tend, int nsave,
+                     const double* saveat, double reltol, double abstol, int maxiters, double* usave, double* uend, int* retcode, long long* stats, double* delta_m, int nS,
+                     double taurec, int scale_k, double* S) {
+    if (nb < 2 || nk < 0 || nsave < 0 || (S && (nS < 2 || nS > 3 || nsave == 0))) return -1;
+    if (nk == 0) return 0;
+    const int msub = 16, nlut = 4096;
+    const double s0 = log(t[0]), dsl = (log(t[nb - 1]) - s0) / nlut;
+    std::vector<int> lut(nlut), order(nk);
+    for (int q = 0, j = 0; q < nlut; q++) { // knot interval containing exp(s0 + q·dsl)
+        const double tq = exp(s0 + dsl * q);
+        while (j < nb - 2 && t[j + 1] <= tq) j++;
+        lut[q] = j;
+    }
+    for (int i = 0; i < nk; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ks[a] > ks[b]; });
+    SbDevBuf B;
+    double *dP, *dt, *dy_, *ddy, *dtab, *dks, *dtini, *dsave, *dus = nullptr, *due, *ddm = nullptr, *dsb = nullptr, *dS = nullptr;
+    int *dlut, *dorder, *dret, *dq;
+    long long* dst;
+    const bool keep = (usave || S) && nsave > 0;
+    SB_CUDA_CHECK(B.get(&dP, SB_NPAR, P)); SB_CUDA_CHECK(B.get(&dt, nb, t)); SB_CUDA_CHECK(B.get(&dy_, (size_t)nb * 5, y)); SB_CUDA_CHECK(B.get(&ddy, (size_t)nb * 5, dy));
+    SB_CUDA_CHECK(B.get(&dtab, ((size_t)(nb - 1) * msub + 1) * 2 * SB_NBETA)); SB_CUDA_CHECK(B.get(&dks, nk, ks)); SB_CUDA_CHECK(B.get(&dtini, nk, tini));
+    SB_CUDA_CHECK(B.get(&dsave, nsave, saveat)); SB_CUDA_CHECK(B.get(&dlut, nlut, lut.data())); SB_CUDA_CHECK(B.get(&dorder, nk, order.data()));
+    SB_CUDA_CHECK(B.get(&due, (size_t)nk * SB_N)); SB_CUDA_CHECK(B.get(&dret, nk)); SB_CUDA_CHECK(B.get(&dst, (size_t)nk * 4)); SB_CUDA_CHECK(B.get(&dq, 1));
+    if (keep) SB_CUDA_CHECK(B.get(&dus, (size_t)nk * nsave * SB_N));
+    int rc = sbm_build_table(dP, nb, dt, dy_, ddy, msub, dtab, nullptr);
+    if (rc < 0) return rc;
+    rc = sbm_solvept(dP, nb, dt, dy_, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, keep ? nsave : 0, dsave, reltol, abstol, maxiters, dus, due, dret, dst, dq, 0,
+                     nullptr, nullptr, 0);
+    if (rc < 0) return rc;
+    if (delta_m) {
+        SB_CUDA_CHECK(B.get(&ddm, nk));
+        rc = sbm_delta_m(dP, nb, dt, dy_, ddy, tend, nk, dks, due, ddm, nullptr);
+        if (rc < 0) return rc;
+    }
+    if (S) {
+        SB_CUDA_CHECK(B.get(&dsb, (size_t)nsave * SB_SRCBG_STRIDE)); SB_CUDA_CHECK(B.get(&dS, (size_t)nk * nS * nsave));
+        rc = sbm_sources(dP, nb, dt, dy_, ddy, nsave, dsave, dsb, nk, dks, dus, dS, scale_k, nS, taurec, nullptr);
+        if (rc < 0) return rc;
+    }
+    SB_CUDA_CHECK(cudaDeviceSynchronize());
+    if (uend) SB_CUDA_CHECK(cudaMemcpy(uend, due, (size_t)nk * SB_N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (usave && nsave) SB_CUDA_CHECK(cudaMemcpy(usave, dus, (size_t)nk * nsave * SB_N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (retcode) SB_CUDA_CHECK(cudaMemcpy(retcode, dret, (size_t)nk * sizeof(int), cudaMemcpyDeviceToHost));
+    if (stats) SB_CUDA_CHECK(cudaMemcpy(stats, dst, (size_t)nk * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (delta_m) SB_CUDA_CHECK(cudaMemcpy(delta_m, ddm, (size_t)nk * sizeof(double), cudaMemcpyDeviceToHost));
+    if (S) SB_CUDA_CHECK(cudaMemcpy(S, dS, (size_t)nk * nS * nsave * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 } // extern "C"

@@ -214,3 +214,51 @@ int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, d
     return 0;
 }
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------- host-buffer entry point
+// One-call variant for hosts without a CUDA allocator: HOST pointers only.  Builds the j_l table, uploads the sources and weights, runs k-interpolation + line of sight + C_l, downloads C_l (and Θ_l(k) if asked).
+#include <algorithm>
+#include <vector>
+struct SblDevBuf {
+    std::vector<void*> ptrs;
+    ~SblDevBuf() { for (void* q : ptrs) cudaFree(q); }
+    template <class T> cudaError_t get(T** out, size_t n, const T* host = nullptr) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(q);
+        *out = (T*)q;
+        if (host && n) e = cudaMemcpy(q, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+
+extern "C" int sbl_cmb_host(int nk, const double* ks, int nc, const double* Bw, const double* Sc, int nS, int nt, const double* chi, const double* wt, int nl, const int* ls, double dx,
+                            double xmax, double xcut, const double* ck, int nmodes, const int* modeA, const int* modeB, int l_limber, double* Cl, double* Theta) {
+    if (nk <= 0 || nl <= 0 || nt <= 0 || nmodes <= 0 || !(dx > 0)) return -1;
+    // the reference's grid range(0, xmax, length = trunc(xmax/dx)) + one padded point (src/observables/angular.jl:18-25), cut at xcut
+    const int n = (int)(xmax / dx);
+    if (n < 2) return -1;
+    const double step = xmax / (n - 1);
+    int nxp = n + 1;
+    if (xcut < xmax) nxp = std::min(nxp, (int)ceil(xcut / step) + 2);
+    SblDevBuf B;
+    double *dks, *dBw = nullptr, *dSc, *dchi, *dwt, *djy, *djdy, *dck, *dTh, *dCl;
+    int *dls, *dmA, *dmB;
+    SBL_CUDA_CHECK(B.get(&dks, nk, ks));
+    if (Bw) SBL_CUDA_CHECK(B.get(&dBw, (size_t)nk * nc, Bw));
+    SBL_CUDA_CHECK(B.get(&dSc, (size_t)(Bw ? nc : nk) * nS * nt, Sc)); SBL_CUDA_CHECK(B.get(&dchi, nt, chi)); SBL_CUDA_CHECK(B.get(&dwt, nt, wt));
+    SBL_CUDA_CHECK(B.get(&dls, nl, ls)); SBL_CUDA_CHECK(B.get(&djy, (size_t)nxp * nl)); SBL_CUDA_CHECK(B.get(&djdy, (size_t)nxp * nl));
+    SBL_CUDA_CHECK(B.get(&dck, nk, ck)); SBL_CUDA_CHECK(B.get(&dTh, (size_t)nS * nl * nk)); SBL_CUDA_CHECK(B.get(&dCl, (size_t)nmodes * nl));
+    SBL_CUDA_CHECK(B.get(&dmA, nmodes, modeA)); SBL_CUDA_CHECK(B.get(&dmB, nmodes, modeB));
+    int rc = sbl_bessel_table(nl, dls, nxp, step, djy, djdy, nullptr);
+    if (rc < 0) return rc;
+    rc = sbl_los(nk, 0, nk, dks, Bw ? nc : 0, dBw, dSc, nS, nt, dchi, dwt, nl, dls, djy, djdy, 1.0 / step, dx, nxp, dTh, l_limber, nullptr);
+    if (rc < 0) return rc;
+    rc = sbl_cl(nl, nk, 0, nk, dck, dTh, nmodes, dmA, dmB, dCl, nullptr);
+    if (rc < 0) return rc;
+    SBL_CUDA_CHECK(cudaDeviceSynchronize());
+    SBL_CUDA_CHECK(cudaMemcpy(Cl, dCl, (size_t)nmodes * nl * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Theta) SBL_CUDA_CHECK(cudaMemcpy(Theta, dTh, (size_t)nS * nl * nk * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -302,3 +302,48 @@ def test_lensing_spectrum_vs_class_and_oracle(sb, oracle, prob5, bg5, obg_same):
     assert np.abs(Dl[:, 0] / oDl[:, 0] - 1).max() < 3e-4
     assert np.abs(Dl[:, 1] / oDl[:, 1] - 1).max() < 3e-4
     assert np.abs(Dl[:, 2] - oDl[:, 2]).max() <= 3e-4 * np.abs(oDl[:, 2]).max()
+
+
+def test_host_buffer_abi_matches_device_pointer_path(sb, prob5, bg5, jl129):
+    """The one-call host-pointer entry points (what a Julia `ccall` without CUDA.jl binds) run the same kernels
+    with the same defaults as the device-pointer path used by the Python host layer: bit-identical outputs."""
+    import ctypes as C
+    import math
+    import torch
+    cp = lambda a: a.ctypes.data_as(C.c_void_p)
+    ks = np.ascontiguousarray(np.geomspace(0.5, 800.0, 37))
+    taus = np.ascontiguousarray(np.linspace(0.02, bg5.tau0, 25))
+    tini = np.full(len(ks), bg5.t[0])
+    N, nk, nt = prob5.N, len(ks), len(taus)
+    usave, uend = np.empty((nk, nt, N)), np.empty((nk, N))
+    ret, stats, dm, S = np.empty(nk, dtype=np.int32), np.empty((nk, 4), dtype=np.int64), np.empty(nk), np.empty((nk, 2, nt))
+    rc = prob5.lib.sbm_solvept_host(cp(bg5.P), C.c_int(len(bg5.t)), cp(bg5.t), cp(bg5.y), cp(bg5.dy), C.c_int(nk), cp(ks), cp(tini), C.c_double(bg5.t[-1]), C.c_int(nt), cp(taus),
+                                    C.c_double(1e-5), C.c_double(1e-5), C.c_int(100000), cp(usave), cp(uend), cp(ret), cp(stats), cp(dm), C.c_int(2), C.c_double(bg5.taurec), C.c_int(1), cp(S))
+    assert rc == 0 and (ret == 0).all()
+    grid = sb.source_grid(prob5, taus, ks, bg5)
+    sol = grid.sol
+    assert np.array_equal(uend, sol.uend) and np.array_equal(usave, sol.d_usave.cpu().numpy().reshape(nk, nt, N))
+    assert np.array_equal(stats, sol.stats) and np.array_equal(S, grid.dS.cpu().numpy())
+    assert np.allclose(sb.spectrum_primordial(ks, prob5) * dm**2, sb.spectrum_matter(prob5, ks, bgsol=bg5, kτini=0.0), rtol=1e-12)  # kτini = 0: start at the first background time, like tini above
+    # k-interpolation + line of sight + C_l in one host call vs the staged device path
+    kint = sb.ChebyshevInterpolator(1e-2, 2e3, 60)
+    ks_fine, taus2 = sb.cmb_grids(bg5)
+    rng = np.random.default_rng(11)
+    Sc = rng.standard_normal((len(kint.xs), 2, len(taus2)))
+    g2 = sb.SourceGrid(torch.from_numpy(Sc).cuda(), kint.xs, taus2, None)
+    theta = sb.los_integrate(g2, jl129, ks_fine=ks_fine, kinterp=kint)
+    P0 = sb.spectrum_primordial(ks_fine, prob5)
+    Cl = sb.spectrum_cmb_from_theta(theta, ["TT", "EE", "TE"], P0, jl129.l, ks_fine).cpu().numpy()
+    Bw = np.ascontiguousarray(kint.matrix(ks_fine))
+    Sz = Sc  # (the kernel zeroes the last-τ row itself, src/observables/angular.jl:296)
+    chi = np.ascontiguousarray(bg5.tau0 - taus2)
+    wt = np.ascontiguousarray(sb.api._trapz_weights(taus2))
+    ck = np.ascontiguousarray(sb.natural_spline_weights(np.concatenate([[0.0], ks_fine]))[1:] * (2 / math.pi) * ks_fine**2 * P0)
+    ls = np.ascontiguousarray(jl129.l.astype(np.int32))
+    mA, mB = np.array([0, 1, 0], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32)
+    Cl2, Th2 = np.empty((3, len(ls))), np.empty((2, len(ls), len(ks_fine)))
+    rc = sb.api.los_lib().sbl_cmb_host(C.c_int(len(ks_fine)), cp(ks_fine), C.c_int(len(kint.xs)), cp(Bw), cp(np.ascontiguousarray(Sz)), C.c_int(2), C.c_int(len(taus2)), cp(chi), cp(wt),
+                                   C.c_int(len(ls)), cp(ls), C.c_double(2 * math.pi / 15), C.c_double(20.0 * ls[-1]), C.c_double(2e3 * bg5.tau0 * 1.001), cp(ck), C.c_int(3), cp(mA), cp(mB),
+                                   C.c_int(2**31 - 1), cp(Cl2), cp(Th2))
+    assert rc == 0
+    assert np.array_equal(Th2, theta.cpu().numpy()) and np.array_equal(Cl2, Cl)
