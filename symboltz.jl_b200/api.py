@@ -379,8 +379,17 @@ def spectrum_primordial(k, prob_or_sol):
     return 2 * math.pi**2 * prob.derived["As"] / k**3 * (k / prob.derived["kpivot"]) ** (prob.pars["ns"] - 1)
 
 
-def spectrum_matter(prob, ks, kτini=1e-2, τinimax=1e-4, bgsol=None, return_solution=False, **kw):
-    """Total matter P(k, τ0) in (c/H0)³ for ks in H0/c (reference spectrum_matter(prob, k), src/observables/fourier.jl:79-101)."""
+def spectrum_matter(prob, ks, kτini=1e-2, τinimax=1e-4, bgsol=None, return_solution=False, sourceopts=None, coarse_length=9, **kw):
+    """Total matter P(k, τ0) in (c/H0)³ for ks in H0/c (reference spectrum_matter(prob, k), src/observables/fourier.jl:79-101).
+    A 2-tuple `ks = (kmin, kmax)` selects the adaptive method (src/observables/fourier.jl:112-128): log-spaced coarse grid of
+    `coarse_length` points refined with `sourceopts` (default atol = 4.0, rtol = 4e-3 on Δm); returns (ks, P)."""
+    if isinstance(ks, tuple) and len(ks) == 2:
+        kmin, kmax = float(ks[0]), float(ks[1])
+        k0s = np.exp(np.linspace(math.log(kmin), math.log(kmax), coarse_length))
+        k0s[0], k0s[-1] = kmin, kmax  # exp(log(k)) ≠ k with floats (fourier.jl:116-117)
+        opts = dict(atol=4.0, rtol=4e-3) if sourceopts is None else dict(sourceopts)
+        kk, D = source_grid_adaptive(prob, None, k0s, bgsol=bgsol, sources="matter", ktransform=(math.log, math.exp), **opts, **kw)
+        return kk, spectrum_primordial(kk, prob) * D[:, 0, 0] ** 2
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
     bg = bgsol if bgsol is not None else solvebg(prob)
     sol = solvept(prob, bg, ks, ptivini=lambda k: min(kτini / k, τinimax) if k > 0 else τinimax, **kw)
@@ -391,6 +400,77 @@ def spectrum_matter(prob, ks, kτini=1e-2, τinimax=1e-4, bgsol=None, return_sol
         raise RuntimeError(f"sbm_delta_m failed with code {rc}")
     P = spectrum_primordial(ks, prob) * dm.cpu().numpy() ** 2
     return (P, sol) if return_solution else P
+
+
+def refine_grid(evaluate, ks, atol=0.0, rtol=None, ktransform=None, nmaxks=1024, sort=True, skip_last_tau=True):
+    """Adaptive bisection of a k-grid (the refinement rule of source_grid_adaptive, src/observables/fourier.jl:312-407):
+    every interval (k1, k3) gets its midpoint k2 = f⁻¹((f(k1)+f(k3))/2) evaluated; if at any τ (the last one excluded when there
+    are several: χ = 0) `isapprox(S(k2), (S(k1)+S(k3))/2; atol, rtol)` fails (2-norm over the source vector), both halves are
+    refined in turn.  The reference spawns one task per midpoint; here each *level* of the bisection tree is one batched call
+    `evaluate(ks_new) -> [nk][nτ][nS]` (one GPU launch over all midpoints of the level).  The decision for an interval depends
+    only on its three points, so the final grid is the same tree.  Raises if more than `nmaxks` points are needed."""
+    f, finv = ktransform if ktransform is not None else ((lambda x: x), (lambda x: x))
+    ks = [float(k) for k in ks]
+    if len(ks) < 2:
+        raise ValueError("Initial k-grid must have at least 2 values")
+    for kk in (min(ks), max(ks)):
+        if not math.isclose(kk, finv(f(kk)), rel_tol=1e-8):
+            raise ValueError("ktransform is not a tuple of inverse functions")
+    if rtol is None:
+        rtol = math.sqrt(np.finfo(np.float64).eps) if atol <= 0 else 0.0  # Base.isapprox default
+    S = [v for v in np.asarray(evaluate(np.array(ks)), dtype=np.float64)]
+    nt = S[0].shape[0]
+    its = slice(0, max(nt - 1, 1)) if skip_last_tau else slice(0, nt)
+    queue = [(i - 1, i) for i in range(1, len(ks))]
+    while queue:
+        mids = [finv((f(ks[i1]) + f(ks[i3])) / 2) for (i1, i3) in queue]
+        if len(ks) + len(mids) > nmaxks:
+            raise RuntimeError(f"Source function refinement needs more than {nmaxks} k-refinements. Reduce refinement criteria.")
+        vals = np.asarray(evaluate(np.array(mids)), dtype=np.float64)
+        nxt = []
+        for (i1, i3), k2, v in zip(queue, mids, vals):
+            i2 = len(ks)
+            ks.append(k2)
+            S.append(v)
+            lin = (S[i1][its] + S[i3][its]) / 2
+            err = np.linalg.norm(v[its] - lin, axis=-1)
+            tol = np.maximum(atol, rtol * np.maximum(np.linalg.norm(v[its], axis=-1), np.linalg.norm(lin, axis=-1)))
+            if (~(err <= tol)).any():
+                nxt += [(i2, i3), (i1, i2)]
+        queue = nxt
+    ks, S = np.array(ks), np.stack(S)
+    if sort:
+        o = np.argsort(ks, kind="stable")
+        ks, S = ks[o], S[o]
+    return ks, S
+
+
+def source_grid_adaptive(prob, taus, ks, bgsol=None, sources="cmb", atol=0.0, rtol=None, ktransform=None, sort=True, nmaxks=1024, **ptopts):
+    """Adaptively refined source grid (reference source_grid_adaptive, src/observables/fourier.jl:312-416).  `sources`: "cmb" =
+    (ST, SE) at the times `taus`, or "matter" = Δm at τ0 (`taus` must be None: final time only).  All modes start at the first
+    background time (ptivini = −∞, src/solve.jl:533).  Returns (ks, S[nk][nτ][nS])."""
+    bg = bgsol if bgsol is not None else solvebg(prob)
+    if sources == "matter":
+        if taus is not None:
+            raise ValueError("matter sources are evaluated at the final time only")
+
+        def evaluate(kk):
+            sol = solvept(prob, bg, kk, **ptopts)
+            d = bg.device()
+            dm = torch.empty(len(kk), dtype=torch.float64, device=sol.d_uend.device)
+            rc = prob.lib.sbm_delta_m(_cptr(d["P"]), C.c_int(len(bg.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_double(bg.tau0), C.c_int(len(kk)), _cptr(sol.d_ks), _cptr(sol.d_uend), _cptr(dm), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_delta_m failed with code {rc}")
+            return dm.cpu().numpy()[:, None, None]
+    elif sources == "cmb":
+        if taus is None:
+            raise ValueError("CMB sources need the times `taus`")
+
+        def evaluate(kk):
+            return source_grid(prob, taus, kk, bg, scale_k=False, **ptopts).dS.cpu().numpy().transpose(0, 2, 1)
+    else:
+        raise ValueError(f"unknown sources {sources!r}")
+    return refine_grid(evaluate, ks, atol=atol, rtol=rtol, ktransform=ktransform, nmaxks=nmaxks, sort=sort)
 
 
 # ---------------------------------------------------------------------------------------------- sources and k-interpolation

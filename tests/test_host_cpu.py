@@ -200,3 +200,32 @@ def test_parameter_updater(sb, prob5):
     assert p2.pars["Omega_c"] == 0.3 and p2.pars["ns"] == 0.97 and p2.pars["h"] == prob5.pars["h"]
     assert p2.lib is prob5.lib  # the compiled engine is reused
     assert abs(p2.derived["Omega_L"] - (prob5.derived["Omega_L"] - (0.3 - prob5.pars["Omega_c"]))) < 1e-12
+
+
+def test_adaptive_refinement_rule(sb):
+    """refine_grid = the bisection rule of source_grid_adaptive (src/observables/fourier.jl:312-407) with the reference's
+    known-answer sources S = (τ + k, τ·k) (runtests.jl:193-214): linear in k, so every initial interval is bisected exactly
+    once; a curved source refines until linear interpolation meets isapprox; the 1024-point cap raises."""
+    taus = np.array([1.0, 2.0])
+    calls = []
+
+    def lin(ks):
+        calls.append(len(ks))
+        return np.stack([taus[None, :] + ks[:, None], taus[None, :] * ks[:, None]], axis=-1)
+    ks, S = sb.refine_grid(lin, np.linspace(1.0, 100.0, 3))
+    assert np.array_equal(ks, [1.0, 25.75, 50.5, 75.25, 100.0]) and S.shape == (5, 2, 2) and calls == [3, 2]
+    assert np.array_equal(S[:, :, 0], taus[None, :] + ks[:, None])
+    # curved source, log transform (what spectrum_matter(prob, (kmin, kmax)) uses): leaf intervals satisfy the criterion, and
+    # the grid is exactly the dyadic tree in ln k
+    fn = lambda ks: (np.sin(3 * np.log(ks)) * ks**0.5)[:, None, None]
+    ks, S = sb.refine_grid(fn, np.array([1.0, 10.0, 100.0]), atol=1e-3, rtol=1e-3, ktransform=(np.log, np.exp))
+    assert (np.diff(ks) > 0).all() and ks[0] == 1.0 and ks[-1] == 100.0 and 17 < len(ks) < 1024
+    y = np.log(ks) / np.log(100.0)
+    assert np.allclose(y * 2**12, np.round(y * 2**12), atol=1e-6)  # dyadic in ln k
+    mid = fn(np.exp((np.log(ks[:-1]) + np.log(ks[1:])) / 2))[:, 0, 0]
+    lin2 = (S[:-1, 0, 0] + S[1:, 0, 0]) / 2
+    assert (np.abs(mid - lin2) <= 4 * np.maximum(1e-3, 1e-3 * np.abs(mid))).all()  # children of accepted intervals are 4x closer (2nd order)
+    with pytest.raises(RuntimeError, match="more than 1024"):
+        sb.refine_grid(lambda ks: np.sin(1e4 * ks)[:, None, None], np.array([1.0, 10.0]), atol=1e-6)
+    with pytest.raises(ValueError):
+        sb.refine_grid(lin, np.array([1.0]))
