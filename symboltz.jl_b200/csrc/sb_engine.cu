@@ -641,19 +641,20 @@ template <int NR>
 __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[NR], const double* di, const double* up, const double* mm, const double* blk, int lane) {
 #pragma unroll
     for (int rd = 0; rd < SB_PR; rd++) {
+        // The recurrence runs unpredicated over the longest path length: past the end of a shorter path (or on a lane without a
+        // path) it reads neighbouring shared-memory values and computes garbage that is never stored.  This keeps the dependent
+        // DFMA chain free of predicated register moves and lets all loads issue from one base register.
         const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
-        if (len > 0) {
-            const double* mmp = mm + start;
+        const double* mmp = mm + start;
 #pragma unroll
-            for (int a = 0; a < NR; a++) {
-                double* rp = rr[a] + start;
-                double av[SB_PL];
-                double acc = rp[0];
+        for (int a = 0; a < NR; a++) {
+            double* rp = rr[a] + start;
+            double av[SB_PL];
+            double acc = rp[0];
 #pragma unroll
-                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; }
+            for (int pos = 1; pos < SB_PL; pos++) { const bool in = pos < len; const double m_ = in ? mmp[pos - 1] : 0.0, r_ = in ? rp[pos] : 0.0; acc = fma(-m_, acc, r_); av[pos] = acc; }
 #pragma unroll
-                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
-            }
+            for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
         }
     }
     __syncwarp();
@@ -711,19 +712,19 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
     __syncwarp();
 #pragma unroll
     for (int rd = 0; rd < SB_PR; rd++) {
+        // backward along the path from its last vertex (q = 0) to its first, again unpredicated: offsets count down from the end
         const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]), par = SB_P_PAR(S.ph[rd]);
-        if (len > 0) {
-            const double *upp = up + start, *dip = di + start;
+        const int end = start + len - 1;
+        const double *upe = up + end, *die = di + end;
 #pragma unroll
-            for (int a = 0; a < NR; a++) {
-                double* rp = rr[a] + start;
-                double xs[SB_PL];
-                double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
+        for (int a = 0; a < NR; a++) {
+            double* re = rr[a] + end;
+            double xs[SB_PL];
+            double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
 #pragma unroll
-                for (int pos = SB_PL - 1; pos >= 0; pos--) if (pos < len) { xv = fma(-upp[pos], xv, rp[pos] * dip[pos]); xs[pos] = xv; }
+            for (int q = 0; q < SB_PL; q++) { const bool in = q < len; const double u_ = in ? upe[-q] : 0.0, r_ = in ? re[-q] : 0.0, d_ = in ? die[-q] : 0.0; xv = fma(-u_, xv, r_ * d_); xs[q] = xv; }
 #pragma unroll
-                for (int pos = 0; pos < SB_PL; pos++) if (pos < len) rp[pos] = xs[pos];
-            }
+            for (int q = 0; q < SB_PL; q++) if (q < len) re[-q] = xs[q];
         }
     }
     __syncwarp();
@@ -748,7 +749,11 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
     (SbSolveArgs A) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31;
+#if SB_WARPS_PER_CTA == 1
+    double* const sm = sm_all; // constant base: shared-memory accesses become [index.X8 + immediate], no address arithmetic
+#else
     double* sm = sm_all + (threadIdx.x >> 5) * SB_SM_DOUBLES;
+#endif
     double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
            *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
     const double reltol = A.reltol, abstol = A.abstol;
