@@ -56,6 +56,22 @@ int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, co
                 double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas,
                 void* stream, double* dtrace, int ntrace);
 
+/* The same solve under a STATIC, preemptive schedule built by the caller from a per-mode cost estimate (no reference
+ * counterpart: the reference spawns one dynamic task per mode, src/solve.jl:566; this replaces the atomic queue when the batch
+ * has fewer than ~2 modes per resident warp and the queue's non-preemptive makespan is far from sum/warps).
+ * ditems[nitems][3] = (mode, quota, cont): quota > 0 parks the mode after that many attempted steps (at the next accepted
+ * step) and publishes a continuation record; cont = 1 waits for the record (bounded: 5 s, then retcode 4) and integrates to
+ * the end.  dibeg[nlists + 1]: item range of each warp; nlists must be a multiple of the warps per CTA and at most
+ * sbm_resident_warps() (every list has to be resident from the start).  dcont: nk * sbm_cont_stride() doubles, dflags: nk ints.
+ * Results are bit-identical to sbm_solvept for every schedule. */
+int sbm_solvept_sched(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                      const double* dtab, int nk, const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol,
+                      double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems,
+                      const int* dibeg, int nlists, double* dcont, int* dflags, void* stream);
+int sbm_cont_stride(void);
+int sbm_resident_warps(void);
+int sbm_warps_per_cta(void);
+
 /* Total-matter gauge-invariant overdensity Δm(τ, k_i) from states du[nk][N] (replaces the observed-function evaluation
  * inside spectrum_matter(sol, k), src/observables/fourier.jl:39-52, 90-97). */
 int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, double tau, int nk, const double* dks, const double* du, double* dout, void* stream);

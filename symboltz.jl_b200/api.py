@@ -223,7 +223,7 @@ def parameter_updater(prob, idxs):
     return updater
 
 
-RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
+RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable", 4: "ScheduleTimeout"}
 
 
 class BackgroundSolution:
@@ -311,9 +311,79 @@ class PerturbationSolution:
         return bool((self.retcode == 0).all())
 
 
-def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0):
+def build_schedule(cost, nlists, min_piece=24):
+    """Static preemptive schedule of independent modes over `nlists` resident warps (McNaughton's wrap-around rule).
+
+    The reference spawns one dynamic task per mode (src/solve.jl:566); the kernel's default is the same thing, an atomic queue
+    in descending-k order.  With fewer than ~2 modes per resident warp that is far from balanced (two of the `nlists + 1`
+    largest modes must share a warp), so here the modes are laid end to end in units of estimated attempted steps
+    (`cost[i]`, any positive estimate) and cut into `nlists` equal chunks of length T = max(Σcost / nlists, max cost).
+    A mode that straddles a cut runs its FIRST attempts (the part after the cut) as the first item of the next list, parks,
+    and is finished as the LAST item of the previous list, so the two pieces never overlap in time when the estimate is exact.
+    Pieces shorter than `min_piece` attempts are not split off.  Returns (items[nitems, 3] int32 = (mode, quota, cont),
+    ibeg[nlists + 1] int32, T)."""
+    cost = np.maximum(np.asarray(cost, dtype=np.float64), 1.0)
+    nk = len(cost)
+    order = np.argsort(-cost, kind="stable")
+    T = max(cost.sum() / nlists, cost.max()) * (1 + 1e-12)
+    lists = [[] for _ in range(nlists)]
+    tails = [None] * nlists  # continuation that ends list w
+    pos = 0.0
+    for m in order:
+        c = cost[m]
+        w = min(int(pos / T), nlists - 1)
+        cut = (w + 1) * T
+        end = pos + c
+        if end <= cut or w == nlists - 1:
+            lists[w].append((m, 0, 0))
+        else:
+            p1, p2 = cut - pos, end - cut  # before / after the cut
+            if p2 < min_piece:
+                lists[w].append((m, 0, 0))
+            elif p1 < min_piece:
+                lists[w + 1].insert(0, (m, 0, 0))
+            else:
+                lists[w + 1].insert(0, (m, int(round(p2)), 0))
+                tails[w] = (m, 0, 1)
+        pos = end
+    items, ibeg = [], [0]
+    for w in range(nlists):
+        items.extend(lists[w])
+        if tails[w] is not None:
+            items.append(tails[w])
+        ibeg.append(len(items))
+    items = np.asarray(items, dtype=np.int32).reshape(-1, 3)
+    assert sorted(items[items[:, 2] == 0, 0].tolist()) == list(range(nk))
+    return items, np.asarray(ibeg, dtype=np.int32), T
+
+
+class ModeCostModel:
+    """Attempted Rosenbrock steps per mode as a smooth function of k, learnt from the statistics of a finished solve
+    (piecewise linear in k through `nknots` quantile knots; the curve barely depends on the cosmology, scripts/cost_model.py)."""
+
+    def __init__(self, ks, attempts, nknots=48):
+        ks, attempts = np.asarray(ks, dtype=np.float64), np.asarray(attempts, dtype=np.float64)
+        o = np.argsort(ks)
+        ks, attempts = ks[o], attempts[o]
+        edges = np.unique(np.linspace(0, len(ks), min(nknots, len(ks)) + 1).astype(int))
+        self.kn = np.array([ks[0]] + [ks[a:b].mean() for a, b in zip(edges[:-1], edges[1:])] + [ks[-1]])
+        self.cn = np.array([attempts[0]] + [attempts[a:b].mean() for a, b in zip(edges[:-1], edges[1:])] + [attempts[-1]])
+        self.kn, i = np.unique(self.kn, return_index=True)
+        self.cn = self.cn[i]
+
+    def __call__(self, ks):
+        return np.interp(np.asarray(ks, dtype=np.float64), self.kn, self.cn)
+
+
+def resident_warps(prob):
+    return int(prob.lib.sbm_resident_warps())
+
+
+def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None):
     """Perturbation solve over independent k-modes on the GPU (reference solvept, src/solve.jl:543-569).
-    ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527)."""
+    ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527).
+    cost: optional per-mode estimate of attempted steps (array or vectorised callable ks -> cost, e.g. a ModeCostModel): run under the static preemptive
+    schedule of `build_schedule` instead of the atomic queue (same results, better balance for few modes per warp)."""
     _require_cuda()
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
     nk = len(ks)
@@ -340,9 +410,21 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     else:
         dsave, usave, ns = None, None, 0
     dtrace = torch.zeros((trace, 3), dtype=torch.float64, device=dev) if trace else None  # debug: (t, dt, EEst) of mode 0
-    rc = prob.lib.sbm_solvept(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
-                              C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
-                              _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), C.c_int(nctas), _stream(), _cptr(dtrace), C.c_int(trace))
+    if cost is not None and nk > 0:
+        cvec = np.asarray(cost(ks) if callable(cost) else cost, dtype=np.float64) * np.ones(nk)
+        wpc = int(prob.lib.sbm_warps_per_cta())
+        nlists = max(wpc, min(resident_warps(prob), nk) // wpc * wpc)
+        items, ibeg, _ = build_schedule(np.nan_to_num(cvec, nan=1.0), nlists)
+        ditems, dibeg = torch.from_numpy(items).to(dev), torch.from_numpy(ibeg).to(dev)
+        dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
+        dflags = torch.zeros(nk, dtype=torch.int32, device=dev)
+        rc = prob.lib.sbm_solvept_sched(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+                                        C.c_int(nk), _cptr(dks), _cptr(dtini), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                        _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream())
+    else:
+        rc = prob.lib.sbm_solvept(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+                                  C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                  _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), C.c_int(nctas), _stream(), _cptr(dtrace), C.c_int(trace))
     if rc < 0:
         raise RuntimeError(f"sbm_solvept failed with code {rc}")
     sol = PerturbationSolution(prob, bgsol, ks, tini, saveat, uend, usave, retcode, stats, dks)
@@ -859,6 +941,24 @@ class CMBPlan:
         self.h2d_bytes = self.h_in.numel() * 8 + self.h_lut.numel() * 4
         self.d2h_bytes = self.h_Cl.numel() * 8
         self.launches_resident, self.launches_e2e = 5, 6
+        self.cost_model, self.d_items = None, None
+
+    def learn_schedule(self, model=None):
+        """Switch the perturbation launch from the atomic queue to the static preemptive schedule (`build_schedule`), with the
+        per-mode cost taken from `model` (a ModeCostModel) or learnt from the step counters of this plan's last solve
+        (blocking read of 64 KB).  Returns the model so that other plans / later cosmologies can reuse it."""
+        lib = self.prob.lib
+        if model is None:
+            st = self.d_stats.cpu().numpy()
+            model = ModeCostModel(self.ks_solve, st[:, 0] + st[:, 1])
+        self.cost_model = model
+        wpc = int(lib.sbm_warps_per_cta())
+        self.nlists = max(wpc, min(int(lib.sbm_resident_warps()), self.nk) // wpc * wpc)
+        items, ibeg, self.sched_T = build_schedule(model(self.ks_solve), self.nlists)
+        self.d_items, self.d_ibeg = torch.from_numpy(items).to(self.dev), torch.from_numpy(ibeg).to(self.dev)
+        self.d_cont = torch.empty(self.nk * int(lib.sbm_cont_stride()), dtype=torch.float64, device=self.dev)
+        self.d_flags = torch.zeros(self.nk, dtype=torch.int32, device=self.dev)
+        return model
 
     def stage(self, bg):
         """Copy a background solution (same number of knots) into the pinned staging buffer."""
@@ -894,6 +994,14 @@ class CMBPlan:
     def solve(self):
         P, t, y, dy = self._views()
         lib = self.prob.lib
+        if self.d_items is not None:
+            rc = lib.sbm_solvept_sched(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
+                                       C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
+                                       C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), _cptr(self.d_items), _cptr(self.d_ibeg),
+                                       C.c_int(self.nlists), _cptr(self.d_cont), _cptr(self.d_flags), _stream())
+            if rc < 0:
+                raise RuntimeError(f"sbm_solvept_sched failed with code {rc}")
+            return
         rc = lib.sbm_solvept(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
                              C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), _cptr(self.d_order), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
                              C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), C.c_int(0), _stream(), None, C.c_int(0))

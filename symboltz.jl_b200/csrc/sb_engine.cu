@@ -41,7 +41,7 @@ static const double hc[8] = SB_R5_c_INIT;
 static const double hd[8] = SB_R5_d_INIT;
 static const double hH[3][8] = SB_R5_H_INIT;
 
-enum { SB_RC_SUCCESS = 0, SB_RC_MAXITERS = 1, SB_RC_DTMIN = 2, SB_RC_UNSTABLE = 3 };
+enum { SB_RC_SUCCESS = 0, SB_RC_MAXITERS = 1, SB_RC_DTMIN = 2, SB_RC_UNSTABLE = 3, SB_RC_SCHEDULE = 4 };
 
 // ------------------------------------------------------------------------------------------------ spline (host+device)
 // Cubic Hermite spline of the background unknowns (reference: DataInterpolations.CubicHermiteSpline, utils.jl:126)
@@ -282,7 +282,13 @@ struct SbSolveArgs {
     int* queue;
     double* trace;    // optional debug trace of mode 0: (t, dt, EEst) per attempted step
     int ntrace;
+    // optional static schedule (sbm_solvept_sched): warp w runs items [ibeg[w], ibeg[w+1]); item = (mode, quota, cont)
+    const int* items;
+    const int* ibeg;
+    double* cont;     // [nk][SB_CONT] continuation records
+    int* flags;       // [nk]: 0 not yet parked, 1 parked (record valid), 2 finished inside the first piece
 };
+#define SB_CONT (SB_N + 12)
 
 // shared-memory layout per warp (doubles)
 #define SB_SM_U 0
@@ -760,12 +766,26 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
     SbLane S;
     S.load(lane);
 
+    int item = 0, item_end = 0;
+    if (A.items) { item = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5)]; item_end = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5) + 1]; }
     while (true) {
-        int qi = 0;
-        if (lane == 0) qi = atomicAdd(A.queue, 1);
-        qi = __shfl_sync(SB_FULL, qi, 0);
-        if (qi >= A.nk) break;
-        const int mode = A.order ? A.order[qi] : qi;
+        // work: either the atomic queue over whole modes, or this warp's static item list.  An item is a mode with an attempt
+        // quota (> 0: park the mode after that many attempts and publish a continuation record) or a continuation (cont = 1:
+        // wait for the record and integrate to the end).  Parking happens right after an accepted step, where the only live
+        // state is (u, t, dt, controller, save index, table interval, counters): the resumed mode repeats exactly the
+        // arithmetic an uninterrupted one would do, so results do not depend on the schedule.
+        int mode, quota = 0, resume = 0;
+        if (A.items) {
+            if (item >= item_end) break;
+            mode = A.items[3 * item]; quota = A.items[3 * item + 1]; resume = A.items[3 * item + 2];
+            item++;
+        } else {
+            int qi = 0;
+            if (lane == 0) qi = atomicAdd(A.queue, 1);
+            qi = __shfl_sync(SB_FULL, qi, 0);
+            if (qi >= A.nk) break;
+            mode = A.order ? A.order[qi] : qi;
+        }
         const double k = A.ks[mode];
         double t = A.tini[mode];
         const double tend = A.tend;
@@ -780,6 +800,36 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
             continue;
         }
         if (lane < 7) kp[lane] = pow(k, (double)(lane - 3));
+        SbController ctl; ctl.init();
+        double dt = 0;
+        int jt = 0, it0 = 0;
+        bool parked = false;
+        if (resume) {
+            int f = 0;
+            if (lane == 0) { // bounded wait (5 s): a schedule whose lists are not all resident must fail, not hang
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while ((f = *(volatile int*)(A.flags + mode)) == 0) {
+                    __nanosleep(200);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 5000000000ull) { f = 3; break; }
+                }
+            }
+            f = __shfl_sync(SB_FULL, f, 0);
+            __threadfence();
+            if (f == 2) continue; // the mode finished within its first piece
+            if (f == 3) {
+                for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = NAN;
+                if (lane == 0) { A.retcode[mode] = SB_RC_SCHEDULE; for (int j = 0; j < 4; j++) A.stats[4 * mode + j] = 0; }
+                continue;
+            }
+            const double* c = A.cont + (size_t)mode * SB_CONT;
+            for (int i = lane; i < SB_N; i += SB_WARP) u[i] = __ldcg(c + i);
+            t = __ldcg(c + SB_N); dt = __ldcg(c + SB_N + 1); ctl.qold = __ldcg(c + SB_N + 2); ctl.q11 = __ldcg(c + SB_N + 3);
+            isave = (int)__ldcg(c + SB_N + 4); jt = (int)__ldcg(c + SB_N + 5); it0 = (int)__ldcg(c + SB_N + 6);
+            naccept = (long long)__ldcg(c + SB_N + 7); nreject = (long long)__ldcg(c + SB_N + 8); nf = (long long)__ldcg(c + SB_N + 9); nsolve = (long long)__ldcg(c + SB_N + 10);
+            __syncwarp();
+        } else {
         if (lane == 0) { double y[5]; sb_spl_eval(A.spl, t, y, nullptr); sb_initial(t, k, y, A.P, U); } // natural order
         __syncwarp();
         for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
@@ -788,10 +838,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
             for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = (A.saveat[isave] == t) ? u[i] : NAN;
             isave++;
         }
-        SbController ctl; ctl.init();
-        double dt = 0;
+        }
         if (tend > t) {
-            int jt = sb_interval(A.tb, t); // knot interval of the current time
+            if (!resume) {
+            jt = sb_interval(A.tb, t); // knot interval of the current time
             jt = sb_basis_at(S, A.tb, t, jt, kp, bs, bdv, lane);
             __syncwarp();
             sb_eval_f<false>(S, bs, u, f0, lane); nf++;
@@ -815,10 +865,21 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
                 __syncwarp();
             }
+            }
             int jend = jt;       // interval of t + dt after the step (becomes jt on accept)
-            bool moved = false;  // t advanced since f0, dT and the slot-0 basis were evaluated
-            for (int it = 0;; it++) {
+            bool moved = resume; // t advanced since f0, dT and the slot-0 basis were evaluated
+            for (int it = it0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
+                if (quota > 0 && moved && it - it0 >= quota) { // park: publish the continuation record
+                    double* c = A.cont + (size_t)mode * SB_CONT;
+                    for (int i = lane; i < SB_N; i += SB_WARP) c[i] = u[i];
+                    if (lane == 0) {
+                        c[SB_N] = t; c[SB_N + 1] = dt; c[SB_N + 2] = ctl.qold; c[SB_N + 3] = ctl.q11; c[SB_N + 4] = isave; c[SB_N + 5] = jt; c[SB_N + 6] = it;
+                        c[SB_N + 7] = (double)naccept; c[SB_N + 8] = (double)nreject; c[SB_N + 9] = (double)nf; c[SB_N + 10] = (double)nsolve;
+                    }
+                    parked = true;
+                    break;
+                }
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
@@ -960,9 +1021,16 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 moved = true;
             }
         }
+        if (parked) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(A.flags + mode, 1);
+            continue;
+        }
         for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
         if (usave) for (; isave < A.nsave; isave++) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
         if (lane == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
+        if (quota > 0 && lane == 0) atomicExch(A.flags + mode, 2);
         __syncwarp();
     }
 }
@@ -1060,15 +1128,17 @@ int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy
 
 // Perturbation solve over nk modes (reference solvept, src/solve.jl:543-569).  All array arguments are DEVICE pointers.
 // dorder may be NULL (natural order).  dqueue: one int, zeroed by this call.  nctas <= 0: fill the GPU.
-int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
-                const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
-                int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace) {
+static int sb_solvept_impl(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                           const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                           int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace,
+                           const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags) {
     if (nk <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SbSolveArgs A;
     A.P = dP; A.spl = SbSpline{nb, dt, dy, ddy}; A.tb = SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab};
     A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.tend = tend; A.nsave = dusave ? nsave : 0; A.saveat = dsaveat;
     A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue; A.trace = dtrace; A.ntrace = ntrace;
+    A.items = ditems; A.ibeg = dibeg; A.cont = dcont; A.flags = dflags;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
     static int occ = 0, nsm = 0;
     if (!occ) {
@@ -1079,9 +1149,46 @@ int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, co
         if (occ < 1) occ = 1;
     }
     int grid = nctas > 0 ? nctas : std::min((nk + SB_WARPS_PER_CTA - 1) / SB_WARPS_PER_CTA, nsm * occ);
+    if (ditems) {
+        // static schedule: one list per warp; a continuation item spins on a flag set by the warp that runs the first piece,
+        // which is the FIRST item of its list -- so every list must be resident from the start
+        if (nlists <= 0 || nlists > nsm * occ * SB_WARPS_PER_CTA || nlists % SB_WARPS_PER_CTA) return -3;
+        grid = nlists / SB_WARPS_PER_CTA;
+        SB_CUDA_CHECK(cudaMemsetAsync(dflags, 0, sizeof(int) * nk, st));
+    }
     sb_integrate_kernel<<<grid, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
+}
+
+int sbm_solvept(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace) {
+    return sb_solvept_impl(dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, nctas,
+                           stream, dtrace, ntrace, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+// Same solve under a static schedule built by the host from a cost model (McNaughton's wrap-around rule: the modes are laid end to
+// end in units of estimated attempts and cut into `nlists` equal chunks, one per resident warp; a mode that straddles a cut runs
+// its first attempts as the FIRST item of the next warp's list and is finished as the LAST item of the previous one).
+// ditems[nitems][3] = (mode, quota, cont); dibeg[nlists + 1]; dcont: nk * sbm_cont_stride() doubles; dflags: nk ints.
+int sbm_solvept_sched(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                      const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol, double abstol, int maxiters, double* dusave, double* duend,
+                      int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags, void* stream) {
+    if (!ditems || !dibeg || !dcont || !dflags) return -1;
+    return sb_solvept_impl(dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, nullptr, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, 0,
+                           stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags);
+}
+int sbm_cont_stride(void) { return SB_CONT; }
+int sbm_warps_per_cta(void) { return SB_WARPS_PER_CTA; }
+// number of integrator warps that can be resident at once on the current device (= the number of lists of a static schedule)
+int sbm_resident_warps(void) {
+    int dev, nsm, occ;
+    SB_CUDA_CHECK(cudaGetDevice(&dev));
+    SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
+    return nsm * occ * SB_WARPS_PER_CTA;
 }
 
 int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, double tau, int nk, const double* dks, const double* du, double* dout, void* stream) {

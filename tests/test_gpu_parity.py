@@ -369,3 +369,25 @@ def test_adaptive_matter_spectrum_matches_oracle_tree(sb, oracle, prob5, bg5, ob
     assert np.abs(P / Po - 1).max() < 1e-4
     Pd = sb.spectrum_matter(prob5, ks, bgsol=bg5, kτini=0.0)
     assert np.abs(P / Pd - 1).max() < 1e-12
+
+
+def test_static_schedule_is_bit_identical_to_queue(sb, prob5, bg5):
+    """The static preemptive schedule (sbm_solvept_sched: modes parked after a quota of attempts and resumed by another warp)
+    must reproduce the atomic-queue solve bit for bit -- states, dense output, step counters -- for good and for bad cost
+    estimates, including modes that finish inside their first piece and quotas that split every mode."""
+    ks = np.linspace(0.5, 400.0, 300)
+    taus = np.geomspace(1e-3, bg5.tau0 * 0.999, 40)
+    ref = sb.solvept(prob5, bg5, ks, saveat=taus)
+    att = ref.stats[:, 0] + ref.stats[:, 1]
+    rng = np.random.default_rng(3)
+    nres = sb.resident_warps(prob5)
+    assert nres >= 148
+    for cost in (sb.ModeCostModel(ks, att), att * rng.uniform(0.3, 3.0, len(ks)), np.full(len(ks), 50.0)):
+        s = sb.solvept(prob5, bg5, ks, saveat=taus, cost=cost)
+        assert s.success
+        assert np.array_equal(s.uend, ref.uend)
+        assert np.array_equal(s.usave, ref.usave, equal_nan=True)
+        assert np.array_equal(s.stats, ref.stats)
+    # schedule with many more modes than lists and forced splitting: exercise waits and early finishes through the raw item lists
+    items, ibeg, T = sb.build_schedule(att.astype(float), 64, min_piece=1)
+    assert (items[:, 2] == 1).sum() >= 32

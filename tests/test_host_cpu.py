@@ -229,3 +229,40 @@ def test_adaptive_refinement_rule(sb):
         sb.refine_grid(lambda ks: np.sin(1e4 * ks)[:, None, None], np.array([1.0, 10.0]), atol=1e-6)
     with pytest.raises(ValueError):
         sb.refine_grid(lin, np.array([1.0]))
+
+
+def test_build_schedule_covers_every_mode_once_and_balances():
+    """Host logic of the static preemptive schedule: every mode appears exactly once as a first piece / whole item, every split
+    mode has exactly one continuation placed at the END of the previous list while its first piece is the FIRST item of the next
+    one (so a continuation can never wait on a warp that has not started), and the simulated makespan is within 3 % of Σ/warps."""
+    import symboltz.jl_b200 as sb
+    rng = np.random.default_rng(0)
+    k = np.linspace(0.01, 2000, 2019)
+    cost = 160 + 2440 * (k / 2000) ** 0.55 + rng.normal(0, 5, len(k))
+    W = 1184
+    items, ibeg, T = sb.build_schedule(cost, W)
+    first = items[items[:, 2] == 0]
+    assert sorted(first[:, 0].tolist()) == list(range(len(k)))
+    conts = items[items[:, 2] == 1]
+    assert len(set(conts[:, 0].tolist())) == len(conts)
+    assert set(conts[:, 0]) == set(first[first[:, 1] > 0, 0])
+    fin = {}
+    for w in range(W):
+        lst = items[ibeg[w]:ibeg[w + 1]]
+        assert (lst[:-1, 2] == 0).all()            # a continuation is only ever the last item
+        assert (lst[1:, 1] == 0).all()             # a quota (first piece) only ever the first item
+        if len(lst) and lst[0, 1] > 0:
+            assert w > 0 and items[ibeg[w] - 1, 0] == lst[0, 0] and items[ibeg[w] - 1, 2] == 1
+            fin[lst[0, 0]] = lst[0, 1]
+    end = np.zeros(W)
+    for w in range(W):
+        t = 0.0
+        for m, q, c in items[ibeg[w]:ibeg[w + 1]]:
+            t = t + min(q, cost[m]) if (c == 0 and q > 0) else t + cost[m] if c == 0 else max(t, fin[m]) + cost[m] - fin[m]
+        end[w] = t
+    assert end.max() <= 1.03 * cost.sum() / W
+    # degenerate inputs
+    items, ibeg, _ = sb.build_schedule(np.ones(3), 8)
+    assert len(items) == 3 and ibeg[-1] == 3
+    m = sb.ModeCostModel(k, cost)
+    assert np.abs(m(k) / cost - 1).max() < 0.2
