@@ -68,6 +68,29 @@ int sbm_solvept_sched(const double* dP, int nb, const double* dt, const double* 
                       const double* dtab, int nk, const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems,
                       const int* dibeg, int nlists, double* dcont, int* dflags, void* stream);
+/* One background cosmology as the integrator sees it (device pointers; 112 bytes, natural C layout). */
+typedef struct {
+    const double* P;              /* [npar] parameters incl. tau0, kappa0 */
+    int nb;                       /* spline knots */
+    const double *t, *y, *dy;     /* [nb], [nb][5], [nb][5] */
+    int tb_nb, msub, nlut;        /* beta-table: knots (= nb), sub-intervals per knot interval, look-up size */
+    double s0, inv_dsl;           /* lut[q] = knot interval containing exp(s0 + q / inv_dsl) */
+    const double* tb_t;           /* = t */
+    const int* lut;               /* [nlut] */
+    const double* tab;            /* [(nb-1)*msub + 1][2][NBETA], from sbm_build_table */
+    double tend;                  /* end of the integration (tau0) */
+    const double* saveat;         /* [nsave] or NULL */
+} sbm_cosmo_t;
+
+/* Perturbation solve of a BATCH of cosmologies in one launch: mode i belongs to cosmology dcosmo_of[i] (replaces the serial outer
+ * loop `for theta: spectrum_matter(probgen(theta), ks)` of docs/src/forecasting.md:56-59 / SURVEY 8b "batched variants with leading
+ * ncosmo dimension").  dcosmos: device array of ncosmo sbm_cosmo_t.  dorder (queue order, may be NULL) or a static schedule
+ * (ditems/dibeg/nlists/dcont/dflags as in sbm_solvept_sched; all NULL/0 for the queue).  Results per mode are bit-identical to
+ * sbm_solvept on that mode's cosmology. */
+int sbm_solvept_batch(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
+                      double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg,
+                      int nlists, double* dcont, int* dflags, void* stream);
+int sbm_cosmo_bytes(void);
 int sbm_cont_stride(void);
 int sbm_resident_warps(void);
 int sbm_warps_per_cta(void);

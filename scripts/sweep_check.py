@@ -14,9 +14,13 @@ u = (rng.permuted(np.tile(np.arange(nc), (7, 1)), axis=1).T + rng.random((nc, 7)
 th = lo + (hi - lo) * u
 th[:, 1] /= th[:, 0] ** 2; th[:, 2] /= th[:, 0] ** 2   # Ωc h², Ωb h² -> Ωc, Ωb
 ks = sb.loggrid(1e-4, 1.0, length=256) / sb.k0
-t = time.time(); P, info = sb.spectrum_matter_sweep(prob, names, th, ks, return_info=True); dt = time.time() - t
-t = time.time(); P, info = sb.spectrum_matter_sweep(prob, names, th, ks, return_info=True); dt = time.time() - t
-print(f"{nc} cosmologies x {len(ks)} modes: {dt:.2f} s wall (host backgrounds included) -> {nc*len(ks)/dt:.0f} k-modes/s; failures {info}")
+sb.spectrum_matter_sweep(prob, names, th[:8], ks)  # warm-up (library load, allocator)
+for chunk in ([int(a) for a in sys.argv[2:]] or [32]):
+    torch.cuda.synchronize(); t = time.time(); P, info = sb.spectrum_matter_sweep(prob, names, th, ks, chunk=chunk, return_info=True); dt = time.time() - t
+    if os.environ.get("SB_TIMELINE"):
+        _, inf = sb.spectrum_matter_sweep(prob, names, th, ks, chunk=chunk, return_info="timeline", nslots=int(os.environ.get("SB_SLOTS", 2)))
+        for ev in inf["timeline"]: print("   %-7s slot %d  %7.1f -> %7.1f ms" % (ev[0], ev[1], 1e3 * ev[2], 1e3 * ev[3]))
+    print(f"{nc} cosmologies x {len(ks)} modes, {chunk} cosmologies per launch: {dt:.2f} s wall (host backgrounds included, {os.cpu_count()} cores) -> {nc*len(ks)/dt:.0f} k-modes/s; {info}")
 upd = sb.parameter_updater(prob, names)
 for i in (0, nc // 2):
     Pi = sb.spectrum_matter(upd(th[i]), ks)

@@ -16,6 +16,7 @@ by build.py; if they (or a GPU) are missing the calls raise -- there is no CPU f
 """
 import ctypes as C
 import math
+import time
 import warnings
 
 import numpy as np
@@ -140,6 +141,12 @@ def _cptr(a):
     if isinstance(a, torch.Tensor):
         return C.c_void_p(a.data_ptr())
     return a.ctypes.data_as(C.c_void_p)
+
+
+def _h2d(a, dev):
+    """Asynchronous upload through pinned memory (a pageable copy would first synchronise the stream, i.e. wait for kernels that are
+    themselves waiting for SM slots held by a running persistent launch)."""
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
 
 
 def _require_cuda():
@@ -434,6 +441,165 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         for i in np.nonzero(sol.retcode != 0)[0]:  # warn, don't throw (src/solve.jl:557-560)
             warnings.warn(f"Perturbation (mode k = {ks[i]}) solution failed with return code {RETCODES.get(int(sol.retcode[i]))}.\nCheck the parameters and precision settings!")
     return sol
+
+
+# sbm_cosmo_t (include/symboltz_b200.h): natural C layout, 112 bytes
+COSMO_DTYPE = np.dtype({"names": ["P", "nb", "t", "y", "dy", "tb_nb", "msub", "nlut", "s0", "inv_dsl", "tb_t", "lut", "tab", "tend", "saveat"],
+                        "formats": ["u8", "i4", "u8", "u8", "u8", "i4", "i4", "i4", "f8", "f8", "u8", "u8", "u8", "f8", "u8"],
+                        "offsets": [0, 8, 16, 24, 32, 40, 44, 48, 56, 64, 72, 80, 88, 96, 104], "itemsize": 112})
+
+
+def cosmo_record(bgsol, msub=16, dsave=None):
+    """The sbm_cosmo_t of a background solution (uploads knots and builds its Î²-table on first use)."""
+    d = bgsol.device(msub)
+    r = np.zeros((), dtype=COSMO_DTYPE)
+    nb = len(bgsol.t)
+    r["P"], r["nb"], r["t"], r["y"], r["dy"] = d["P"].data_ptr(), nb, d["t"].data_ptr(), d["y"].data_ptr(), d["dy"].data_ptr()
+    r["tb_nb"], r["msub"], r["nlut"], r["s0"], r["inv_dsl"] = nb, d["msub"], d["nlut"], d["s0"], 1.0 / d["dsl"]
+    r["tb_t"], r["lut"], r["tab"], r["tend"] = d["t"].data_ptr(), d["lut"].data_ptr(), d["tab"].data_ptr(), bgsol.tau0
+    r["saveat"] = 0 if dsave is None else dsave.data_ptr()
+    return r
+
+
+class CosmoArena:
+    """Reusable staging for a batch of background cosmologies: one pinned host buffer and ONE host->device copy for all knots and
+    parameters, one for the interval look-ups, one Î²-table buffer -- instead of five small uploads and a 9 MB allocation per
+    cosmology.  `load` returns the sbm_cosmo_t records; the per-cosmology device views stay valid until the next `load`."""
+
+    NLUT = 4096
+
+    def __init__(self):
+        self.h_f = self.d_f = self.h_i = self.d_i = self.d_tab = None
+        self.views = []
+
+    @staticmethod
+    def _grow(t, n, **kw):
+        return t if t is not None and t.numel() >= n else torch.empty(int(n * 1.25) + 64, **kw)
+
+    def load(self, bgsols, msub=16):
+        prob = bgsols[0].prob
+        dev = torch.device("cuda")
+        npar, NB = prob.npar, prob.NBETA
+        nbs = np.array([len(b.t) for b in bgsols])
+        fo = np.concatenate([[0], np.cumsum(npar + 11 * nbs)])          # doubles: P | t | y | dy per cosmology
+        to = np.concatenate([[0], np.cumsum(((nbs - 1) * msub + 1) * 2 * NB)])
+        nc = len(bgsols)
+        self.h_f = self._grow(self.h_f, fo[-1], dtype=torch.float64, pin_memory=True)
+        self.d_f = self._grow(self.d_f, fo[-1], dtype=torch.float64, device=dev)
+        self.h_i = self._grow(self.h_i, nc * self.NLUT, dtype=torch.int32, pin_memory=True)
+        self.d_i = self._grow(self.d_i, nc * self.NLUT, dtype=torch.int32, device=dev)
+        self.d_tab = self._grow(self.d_tab, to[-1], dtype=torch.float64, device=dev)
+        hf, hi = self.h_f.numpy(), self.h_i.numpy()
+        recs = np.zeros(nc, dtype=COSMO_DTYPE)
+        self.views = []
+        q = np.arange(self.NLUT)
+        for i, b in enumerate(bgsols):
+            nb, o = int(nbs[i]), int(fo[i])
+            hf[o:o + npar] = b.P
+            hf[o + npar:o + npar + nb] = b.t
+            hf[o + npar + nb:o + npar + 6 * nb] = b.y.ravel()
+            hf[o + npar + 6 * nb:o + npar + 11 * nb] = b.dy.ravel()
+            s0 = math.log(b.t[0])
+            dsl = (math.log(b.t[-1]) - s0) / self.NLUT
+            hi[i * self.NLUT:(i + 1) * self.NLUT] = np.clip(np.searchsorted(b.t, np.exp(s0 + dsl * q), side="right") - 1, 0, nb - 2)
+            dP, dt, dy, ddy = (self.d_f[o:o + npar], self.d_f[o + npar:o + npar + nb], self.d_f[o + npar + nb:o + npar + 6 * nb], self.d_f[o + npar + 6 * nb:o + npar + 11 * nb])
+            tab = self.d_tab[int(to[i]):int(to[i + 1])]
+            lut = self.d_i[i * self.NLUT:(i + 1) * self.NLUT]
+            self.views.append(dict(P=dP, t=dt, y=dy, dy=ddy, tab=tab, lut=lut, nb=nb))
+            r = recs[i]
+            r["P"], r["nb"], r["t"], r["y"], r["dy"] = dP.data_ptr(), nb, dt.data_ptr(), dy.data_ptr(), ddy.data_ptr()
+            r["tb_nb"], r["msub"], r["nlut"], r["s0"], r["inv_dsl"] = nb, msub, self.NLUT, s0, 1.0 / dsl
+            r["tb_t"], r["lut"], r["tab"], r["tend"] = dt.data_ptr(), lut.data_ptr(), tab.data_ptr(), b.tau0
+        self.d_f[:fo[-1]].copy_(self.h_f[:fo[-1]], non_blocking=True)
+        self.d_i[:nc * self.NLUT].copy_(self.h_i[:nc * self.NLUT], non_blocking=True)
+        for v in self.views:
+            rc = prob.lib.sbm_build_table(_cptr(v["P"]), C.c_int(v["nb"]), _cptr(v["t"]), _cptr(v["y"]), _cptr(v["dy"]), C.c_int(msub), _cptr(v["tab"]), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_build_table failed with code {rc}")
+        return recs
+
+
+class BatchSolution:
+    """Result of `solvept_batch`: flat device arrays over all (cosmology, mode) pairs + per-cosmology views."""
+
+    def __init__(self, sols, offsets, d_uend, d_usave, d_retcode, d_stats, keep):
+        self.sols, self.offsets, self.d_uend, self.d_usave, self.d_retcode, self.d_stats, self._keep = sols, offsets, d_uend, d_usave, d_retcode, d_stats, keep
+
+    def __len__(self):
+        return len(self.sols)
+
+    def __getitem__(self, i):
+        return self.sols[i]
+
+    @property
+    def success(self):
+        return bool((self.d_retcode == 0).all().item())
+
+
+def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, cost=None, arena=None):
+    """Perturbation solve of several cosmologies (same model structure) in ONE integrator launch over all (cosmology, mode)
+    pairs, ordered by descending k across cosmologies (SURVEY Â§8b batched variant; the reference runs one `solvept` per
+    cosmology, docs/src/forecasting.md:56-59).  bgsols: BackgroundSolutions; ks: one array for all, or one array per cosmology;
+    saveat: None, or one array of save times per cosmology (equal lengths).  Per-mode results are bit-identical to `solvept` on that
+    cosmology.  cost: optional vectorised callable ks -> estimated attempts, switches to the static preemptive schedule."""
+    _require_cuda()
+    nc = len(bgsols)
+    prob = bgsols[0].prob
+    if any(b.prob.N != prob.N or b.prob.lib._name != prob.lib._name for b in bgsols):
+        raise ValueError("solvept_batch: all cosmologies must share one model structure")
+    ks_list = [np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64) for k in (ks if isinstance(ks, (list, tuple)) else [ks] * nc)]
+    if len(ks_list) != nc:
+        raise ValueError("solvept_batch: need one k-array per cosmology")
+    f = ptivini if callable(ptivini) else (lambda k: ptivini)
+    offsets = np.concatenate([[0], np.cumsum([len(k) for k in ks_list])]).astype(np.int64)
+    nk = int(offsets[-1])
+    kall = np.concatenate(ks_list)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tini = np.concatenate([np.array([min(max(f(k), b.t[0]), b.t[-1]) if k == k else b.t[0] for k in kk], dtype=np.float64) for b, kk in zip(bgsols, ks_list)])
+    cosmo_of = np.repeat(np.arange(nc, dtype=np.int32), [len(k) for k in ks_list])
+    order = np.argsort(-np.nan_to_num(kall, nan=0.0), kind="stable").astype(np.int32)
+    dev = torch.device("cuda")
+    ns = 0
+    dsaves = [None] * nc
+    if saveat is not None:
+        saveat = [np.ascontiguousarray(sv, dtype=np.float64) for sv in saveat]
+        ns = len(saveat[0])
+        if len(saveat) != nc or any(len(sv) != ns for sv in saveat):
+            raise ValueError("solvept_batch: need one saveat array per cosmology, all of the same length")
+        dsv = _h2d(np.stack(saveat), dev)
+        dsaves = [dsv[i] for i in range(nc)]
+    arena = arena if arena is not None else CosmoArena()
+    recs = arena.load(bgsols, msub)  # uploads knots, builds the Î²-tables (same kernel and node layout as BackgroundSolution.device)
+    for i in range(nc):
+        recs[i]["saveat"] = 0 if dsaves[i] is None else dsaves[i].data_ptr()
+    dcos = _h2d(np.frombuffer(recs.tobytes(), dtype=np.uint8).reshape(nc, COSMO_DTYPE.itemsize).copy(), dev)
+    dkt = _h2d(np.concatenate([kall, tini]), dev)
+    dks, dtini = dkt[:nk], dkt[nk:]
+    dcof, dorder = _h2d(cosmo_of, dev), _h2d(order, dev)
+    N = prob.N
+    uend = torch.empty((nk, N), dtype=torch.float64, device=dev)
+    usave = torch.empty((nk, ns, N), dtype=torch.float64, device=dev) if ns else None
+    retcode = torch.empty(nk, dtype=torch.int32, device=dev)
+    stats = torch.empty((nk, 4), dtype=torch.int64, device=dev)
+    queue = torch.zeros(1, dtype=torch.int32, device=dev)
+    ditems = dibeg = dcont = dflags = None
+    nlists = 0
+    if cost is not None and nk > 0:
+        wpc = int(prob.lib.sbm_warps_per_cta())
+        nlists = max(wpc, min(resident_warps(prob), nk) // wpc * wpc)
+        items, ibeg, _ = build_schedule(np.nan_to_num(np.asarray(cost(kall) if callable(cost) else cost, dtype=np.float64) * np.ones(nk), nan=1.0), nlists)
+        ditems, dibeg = _h2d(items, dev), _h2d(ibeg, dev)
+        dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
+        dflags = torch.zeros(nk, dtype=torch.int32, device=dev)
+    rc = prob.lib.sbm_solvept_batch(C.c_int(nc), _cptr(dcos), C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dcof), _cptr(dorder), C.c_int(ns), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                    _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream())
+    if rc < 0:
+        raise RuntimeError(f"sbm_solvept_batch failed with code {rc}")
+    sols = []
+    for i, b in enumerate(bgsols):
+        a, e = int(offsets[i]), int(offsets[i + 1])
+        sols.append(PerturbationSolution(b.prob, b, ks_list[i], tini[a:e], None if saveat is None else saveat[i], uend[a:e], None if usave is None else usave[a:e], retcode[a:e], stats[a:e], dks[a:e]))
+    return BatchSolution(sols, offsets, uend, usave, retcode, stats, keep=(arena, dcos, dkt, dcof, dorder, queue, ditems, dibeg, dcont, dflags, dsaves))
 
 
 class CosmologySolution:
@@ -1046,12 +1212,14 @@ class CMBPlan:
         return self.download()
 
 
-def spectrum_matter_sweep(prob, names, thetas, ks, nstreams=8, nthreads=None, kÏ„ini=1e-2, Ï„inimax=1e-4, reltol=1e-5, abstol=1e-5, return_info=False):
+def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kÏ„ini=1e-2, Ï„inimax=1e-4, reltol=1e-5, abstol=1e-5, return_info=False, cost=None, msub=16, nslots=2):
     """P(k) for a batch of cosmologies Î¸ â†¦ parameter_updater(prob, names)(Î¸) (BASELINE config 4: emulator / MCMC sweeps;
     the reference runs a serial outer loop of `spectrum_matter(probgen(Î¸), ks)`, docs/src/forecasting.md:56-59).
-    Host background solves run on a thread pool (the ctypes calls release the GIL); every cosmology's perturbation solve is an
-    independent launch round-robined over `nstreams` CUDA streams, so several cosmologies share the GPU concurrently.
-    thetas: [ncosmo, len(names)].  Returns P[ncosmo, nk] (NaN rows where the background failed)."""
+    Host background solves run on a thread pool (the ctypes calls release the GIL).  The perturbation solves of `chunk` cosmologies
+    go into ONE integrator launch over all their (cosmology, mode) pairs (`solvept_batch`), so the resident warps are kept busy by
+    a single descending-k queue instead of one short launch per cosmology; consecutive chunks alternate between two CUDA streams
+    (uploads and table builds of chunk c+1 overlap the solve of chunk c, whose tail is filled by the next launch).
+    thetas: [ncosmo, len(names)].  Returns P[ncosmo, nk] (NaN rows where the background failed); bit-identical to single calls."""
     import concurrent.futures as cf
     import os
     _require_cuda()
@@ -1059,6 +1227,7 @@ def spectrum_matter_sweep(prob, names, thetas, ks, nstreams=8, nthreads=None, kÏ
     ks = np.ascontiguousarray(ks, dtype=np.float64)
     upd = parameter_updater(prob, names)
     nthreads = nthreads or os.cpu_count()
+    n, nk = len(thetas), len(ks)
 
     def host(theta):
         p = upd(theta)
@@ -1066,28 +1235,64 @@ def spectrum_matter_sweep(prob, names, thetas, ks, nstreams=8, nthreads=None, kÏ
             warnings.simplefilter("ignore")
             return p, solvebg(p)
 
-    streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    out = np.full((len(thetas), len(ks)), np.nan)
-    pending, nfail = [], 0
+    streams = [torch.cuda.Stream() for _ in range(nslots)]
+    out = np.full((n, nk), np.nan)
+    info = dict(background_failures=0, mode_failures=0, launches=0)
+    timeline, tstart = [], time.perf_counter()
     f = lambda k: min(kÏ„ini / k, Ï„inimax) if k > 0 else Ï„inimax
+    inflight = [None] * nslots
+    arenas = [CosmoArena() for _ in range(nslots)]
+
+    def finish(slot):
+        job = inflight[slot]
+        if job is None:
+            return
+        idx, probs, bgs, batch, dm, h_dm, h_rc, ev = job
+        t_ = time.perf_counter()
+        ev.synchronize()
+        timeline.append(("wait", slot, t_ - tstart, time.perf_counter() - tstart))
+        dmh = h_dm.numpy().reshape(len(idx), nk)
+        for j, i in enumerate(idx):
+            out[i] = spectrum_primordial(ks, probs[j]) * dmh[j] ** 2
+        info["mode_failures"] += int((h_rc.numpy() != 0).sum())  # read from the pinned copy: a kernel on another stream would queue behind the persistent CTAs
+        inflight[slot] = None
+
     with cf.ThreadPoolExecutor(nthreads) as pool:
-        for i, (p, bg) in enumerate(pool.map(host, thetas)):
-            if not bg.success:
-                nfail += 1
+        results = pool.map(host, thetas)
+        for c, c0 in enumerate(range(0, n, chunk)):
+            slot = c % nslots
+            finish(slot)
+            t_ = time.perf_counter()
+            group = [next(results) for _ in range(min(chunk, n - c0))]
+            timeline.append(("gather", slot, t_ - tstart, time.perf_counter() - tstart))
+            t_ = time.perf_counter()
+            idx = [c0 + j for j, (p, bg) in enumerate(group) if bg.success]
+            info["background_failures"] += len(group) - len(idx)
+            if not idx:
                 continue
-            with torch.cuda.stream(streams[i % nstreams]):
-                sol = solvept(p, bg, ks, ptivini=f, reltol=reltol, abstol=abstol, warn=False, sync=False)
-                d = bg.device()
-                dm = torch.empty(len(ks), dtype=torch.float64, device=sol.d_uend.device)
-                rc = p.lib.sbm_delta_m(_cptr(d["P"]), C.c_int(len(bg.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_double(bg.tau0), C.c_int(len(ks)), _cptr(sol.d_ks), _cptr(sol.d_uend), _cptr(dm), _stream())
-                if rc != 0:
-                    raise RuntimeError(f"sbm_delta_m failed with code {rc}")
-            pending.append((i, p, sol, dm))
-    torch.cuda.synchronize()
-    nbad = 0
-    for i, p, sol, dm in pending:
-        out[i] = spectrum_primordial(ks, p) * dm.cpu().numpy() ** 2
-        nbad += int((sol.retcode != 0).sum())
+            probs, bgs = [group[i - c0][0] for i in idx], [group[i - c0][1] for i in idx]
+            with torch.cuda.stream(streams[slot]):
+                batch = solvept_batch(bgs, ks, ptivini=f, reltol=reltol, abstol=abstol, msub=msub, cost=cost, arena=arenas[slot])
+                dm = torch.empty(len(idx) * nk, dtype=torch.float64, device=batch.d_uend.device)
+                for j, (p, bg, sol) in enumerate(zip(probs, bgs, batch.sols)):
+                    d = arenas[slot].views[j]
+                    rc = p.lib.sbm_delta_m(_cptr(d["P"]), C.c_int(len(bg.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_double(bg.tau0), C.c_int(nk), _cptr(sol.d_ks), _cptr(sol.d_uend),
+                                           _cptr(dm[j * nk:(j + 1) * nk]), _stream())
+                    if rc != 0:
+                        raise RuntimeError(f"sbm_delta_m failed with code {rc}")
+                h_dm = torch.empty(len(idx) * nk, dtype=torch.float64, pin_memory=True)
+                h_dm.copy_(dm, non_blocking=True)
+                h_rc = torch.empty(len(idx) * nk, dtype=torch.int32, pin_memory=True)
+                h_rc.copy_(batch.d_retcode, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            info["launches"] += 1
+            inflight[slot] = (idx, probs, bgs, batch, dm, h_dm, h_rc, ev)
+            timeline.append(("launch", slot, t_ - tstart, time.perf_counter() - tstart))
+    for slot in range(nslots):
+        finish((c + 1 + slot) % nslots)
+    if return_info == "timeline":
+        info["timeline"] = timeline
     if return_info:
-        return out, dict(background_failures=nfail, mode_failures=nbad)
+        return out, info
     return out

@@ -264,16 +264,25 @@ struct SbTable {
     const double* tab;       // [(nb-1)·msub + 1][2][NBETA]
 };
 
-struct SbSolveArgs {
+// One background cosmology as the integrator sees it.  Layout = sbm_cosmo_t of include/symboltz_b200.h (112 bytes).
+struct SbCosmo {
     const double* P;
     SbSpline spl;
     SbTable tb;
+    double tend;
+    const double* saveat; // [nsave] save times (may be null when nsave = 0)
+};
+static_assert(sizeof(SbCosmo) == 112, "SbCosmo must match sbm_cosmo_t");
+#define SB_COSMO_DOUBLES 14
+
+struct SbSolveArgs {
+    SbCosmo c0;            // the cosmology of a single-cosmology launch
+    const SbCosmo* cosmos; // batched launch (sbm_solvept_batch): device array of cosmologies and the cosmology index of each mode
+    const int* cosmo_of;
     int nk;
     const double *ks, *tini;
     const int* order;
-    double tend;
     int nsave;
-    const double* saveat;
     double reltol, abstol;
     int maxiters;
     double *usave, *uend;
@@ -305,7 +314,8 @@ struct SbSolveArgs {
 #define SB_SM_BS (SB_SM_ZQ + SB_N)
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
 #define SB_SM_KP (SB_SM_BD + SB_NB)
-#define SB_SM_DOUBLES (SB_SM_KP + 8 + 48)
+#define SB_SM_COSMO (SB_SM_KP + 8 + 48)  // batched launches: the current mode's SbCosmo
+#define SB_SM_DOUBLES (SB_SM_COSMO + 16)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
 #ifndef SB_MINBLOCKS
@@ -747,12 +757,15 @@ __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, co
 
 // Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
 // queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
+// BATCH: every mode carries its own cosmology (A.cosmos[A.cosmo_of[mode]], staged in shared memory per mode) -- one launch over
+// the (cosmology, mode) pairs of a parameter sweep; otherwise the single cosmology A.c0 is read from the kernel parameters.
+template <bool BATCH>
 #ifdef SB_NOLB
 __global__ void sb_integrate_kernel
 #else
 __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_integrate_kernel
 #endif
-    (SbSolveArgs A) {
+    (const __grid_constant__ SbSolveArgs A) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31;
 #if SB_WARPS_PER_CTA == 1
@@ -765,6 +778,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
     const double reltol = A.reltol, abstol = A.abstol;
     SbLane S;
     S.load(lane);
+    const SbCosmo& CC = *(BATCH ? reinterpret_cast<const SbCosmo*>(sm + SB_SM_COSMO) : &A.c0);
 
     int item = 0, item_end = 0;
     if (A.items) { item = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5)]; item_end = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5) + 1]; }
@@ -786,9 +800,15 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
             if (qi >= A.nk) break;
             mode = A.order ? A.order[qi] : qi;
         }
+        if (BATCH) {
+            __syncwarp();
+            const double* src = reinterpret_cast<const double*>(A.cosmos + A.cosmo_of[mode]);
+            if (lane < SB_COSMO_DOUBLES) sm[SB_SM_COSMO + lane] = src[lane];
+            __syncwarp();
+        }
         const double k = A.ks[mode];
         double t = A.tini[mode];
-        const double tend = A.tend;
+        const double tend = CC.tend;
         long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
         int rc = SB_RC_SUCCESS, isave = 0;
         double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
@@ -830,19 +850,19 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
             naccept = (long long)__ldcg(c + SB_N + 7); nreject = (long long)__ldcg(c + SB_N + 8); nf = (long long)__ldcg(c + SB_N + 9); nsolve = (long long)__ldcg(c + SB_N + 10);
             __syncwarp();
         } else {
-        if (lane == 0) { double y[5]; sb_spl_eval(A.spl, t, y, nullptr); sb_initial(t, k, y, A.P, U); } // natural order
+        if (lane == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
         __syncwarp();
         for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
         __syncwarp();
-        while (isave < A.nsave && A.saveat[isave] <= t) { // save points at (or before) the start
-            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = (A.saveat[isave] == t) ? u[i] : NAN;
+        while (isave < A.nsave && CC.saveat[isave] <= t) { // save points at (or before) the start
+            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = (CC.saveat[isave] == t) ? u[i] : NAN;
             isave++;
         }
         }
         if (tend > t) {
             if (!resume) {
-            jt = sb_interval(A.tb, t); // knot interval of the current time
-            jt = sb_basis_at(S, A.tb, t, jt, kp, bs, bdv, lane);
+            jt = sb_interval(CC.tb, t); // knot interval of the current time
+            jt = sb_basis_at(S, CC.tb, t, jt, kp, bs, bdv, lane);
             __syncwarp();
             sb_eval_f<false>(S, bs, u, f0, lane); nf++;
             sb_eval_dT(S, bs, bdv, u, dT, lane);
@@ -854,7 +874,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
                 dt0 = fmin(dt0, dtmax);
                 for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
-                sb_basis_at(S, A.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
+                sb_basis_at(S, CC.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
                 __syncwarp();
                 sb_eval_f<false>(S, bs + SB_NB, U, K, lane); nf++;
                 double d2 = 0;
@@ -883,7 +903,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
-                jend = sb_basis_batch(S, A.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
+                jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
                 __syncwarp();
                 if (moved) { sb_eval_f<false>(S, bs, u, f0, lane); nf++; sb_eval_dT(S, bs, bdv, u, dT, lane); moved = false; }
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
@@ -994,14 +1014,14 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                 naccept++;
                 const double dtnew = ctl.accept(dt, q, EEst);
                 const double tn = last ? tend : t + dt;
-                if (isave < A.nsave && A.saveat[isave] <= tn) { // dense output (4th order), vectors stored over dT, f0, Zp
+                if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order), vectors stored over dT, f0, Zp
                     for (int i = lane; i < SB_N; i += SB_WARP) {
                         double a1 = 0, a2 = 0, a3 = 0;
                         for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
                         dT[i] = a1; f0[i] = a2; Zp[i] = a3;
                     }
-                    while (isave < A.nsave && A.saveat[isave] <= tn) {
-                        double ts = A.saveat[isave];
+                    while (isave < A.nsave && CC.saveat[isave] <= tn) {
+                        double ts = CC.saveat[isave];
                         if (ts == tn) { for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = U[i] + K[7 * SB_N + i]; }
                         else {
                             double th = (ts - t) / dt, t1 = 1 - th;
@@ -1131,12 +1151,13 @@ int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy
 static int sb_solvept_impl(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
                            const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
                            int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace,
-                           const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags) {
+                           const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags, const SbCosmo* dcosmos = nullptr, const int* dcosmo_of = nullptr) {
     if (nk <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SbSolveArgs A;
-    A.P = dP; A.spl = SbSpline{nb, dt, dy, ddy}; A.tb = SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab};
-    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.tend = tend; A.nsave = dusave ? nsave : 0; A.saveat = dsaveat;
+    A.c0 = SbCosmo{dP, SbSpline{nb, dt, dy, ddy}, SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab}, tend, dsaveat};
+    A.cosmos = dcosmos; A.cosmo_of = dcosmo_of;
+    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = dusave ? nsave : 0;
     A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue; A.trace = dtrace; A.ntrace = ntrace;
     A.items = ditems; A.ibeg = dibeg; A.cont = dcont; A.flags = dflags;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
@@ -1144,9 +1165,12 @@ static int sb_solvept_impl(const double* dP, int nb, const double* dt, const dou
     if (!occ) {
         int dev; SB_CUDA_CHECK(cudaGetDevice(&dev));
         SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
-        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
-        if (occ < 1) occ = 1;
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+        SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+        int occ_b = 0;
+        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<false>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
+        SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, sb_integrate_kernel<true>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
+        occ = std::max(1, std::min(occ, occ_b));
     }
     int grid = nctas > 0 ? nctas : std::min((nk + SB_WARPS_PER_CTA - 1) / SB_WARPS_PER_CTA, nsm * occ);
     if (ditems) {
@@ -1156,7 +1180,8 @@ static int sb_solvept_impl(const double* dP, int nb, const double* dt, const dou
         grid = nlists / SB_WARPS_PER_CTA;
         SB_CUDA_CHECK(cudaMemsetAsync(dflags, 0, sizeof(int) * nk, st));
     }
-    sb_integrate_kernel<<<grid, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES, st>>>(A);
+    if (dcosmos) sb_integrate_kernel<true><<<grid, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES, st>>>(A);
+    else sb_integrate_kernel<false><<<grid, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
 }
@@ -1179,6 +1204,19 @@ int sbm_solvept_sched(const double* dP, int nb, const double* dt, const double* 
     return sb_solvept_impl(dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, nullptr, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, 0,
                            stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags);
 }
+// One launch over the (cosmology, mode) pairs of a parameter sweep (SURVEY §8b "batched variants with leading ncosmo dimension";
+// the reference loops `spectrum_matter(probgen(θ), ks)` serially, docs/src/forecasting.md:56-59).  dcosmos: device array of ncosmo
+// sbm_cosmo_t; dcosmo_of[nk]: cosmology of each mode; dorder: queue order (NULL = natural), or a static schedule (ditems != NULL).
+// dusave (optional): [nk][nsave][N] with every cosmology supplying its own nsave save times.
+int sbm_solvept_batch(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol, double abstol,
+                      int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags,
+                      void* stream) {
+    if (ncosmo <= 0 || !dcosmos || !dcosmo_of) return -1;
+    if (ditems && (!dibeg || !dcont || !dflags)) return -1;
+    return sb_solvept_impl(nullptr, 0, nullptr, nullptr, nullptr, 1, 1, 0.0, 1.0, nullptr, nullptr, nk, dks, dtini, dorder, 0.0, nsave, nullptr, reltol, abstol, maxiters, dusave, duend, dretcode, dstats,
+                           dqueue, 0, stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags, (const SbCosmo*)dcosmos, dcosmo_of);
+}
+int sbm_cosmo_bytes(void) { return (int)sizeof(SbCosmo); }
 int sbm_cont_stride(void) { return SB_CONT; }
 int sbm_warps_per_cta(void) { return SB_WARPS_PER_CTA; }
 // number of integrator warps that can be resident at once on the current device (= the number of lists of a static schedule)
@@ -1186,8 +1224,8 @@ int sbm_resident_warps(void) {
     int dev, nsm, occ;
     SB_CUDA_CHECK(cudaGetDevice(&dev));
     SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
-    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<false>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
     return nsm * occ * SB_WARPS_PER_CTA;
 }
 

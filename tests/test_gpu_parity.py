@@ -236,7 +236,7 @@ def test_w0wa_and_massive_neutrino_variants_run(sb, oracle):
 
 
 def test_parameter_sweep_matches_single_calls(sb):
-    """BASELINE config 4 (batched cosmologies): the multi-stream sweep reproduces individual spectrum_matter calls bit for bit,
+    """BASELINE config 4 (batched cosmologies): the batched-launch sweep (solvept_batch: one integrator launch per chunk of cosmologies) reproduces individual spectrum_matter calls bit for bit,
     and reports failures instead of raising (reference semantics: warn, don't throw)."""
     M = sb.w0waCDM(lmax=10)
     prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
@@ -244,8 +244,8 @@ def test_parameter_sweep_matches_single_calls(sb):
     rng = np.random.default_rng(0)
     th = np.array([0.6736, 0.2645, -0.9, 0.1]) * (1 + 0.05 * (rng.random((6, 4)) - 0.5))
     ks = sb.loggrid(1e-4, 1.0, length=24) / sb.k0
-    P, info = sb.spectrum_matter_sweep(prob, names, th, ks, nstreams=3, return_info=True)
-    assert info == dict(background_failures=0, mode_failures=0) and np.isfinite(P).all()
+    P, info = sb.spectrum_matter_sweep(prob, names, th, ks, chunk=4, return_info=True)  # 2 launches: 4 + 2 cosmologies
+    assert info == dict(background_failures=0, mode_failures=0, launches=2) and np.isfinite(P).all()
     upd = sb.parameter_updater(prob, names)
     for i in (0, 3, 5):
         assert np.array_equal(P[i], sb.spectrum_matter(upd(th[i]), ks))
@@ -282,7 +282,7 @@ def test_stability_latin_hypercube(sb):
         rng = np.random.default_rng(1)
         u = (rng.permuted(np.tile(np.arange(n), (len(names), 1)), axis=1).T + rng.random((n, len(names)))) / n
         P, info = sb.spectrum_matter_sweep(prob, names, fid * (0.5 + u), np.array([1.0, 10.0, 100.0, 1000.0]), return_info=True)
-        assert info == dict(background_failures=0, mode_failures=0) and np.isfinite(P).all() and (P > 0).all()
+        assert info["background_failures"] == 0 and info["mode_failures"] == 0 and np.isfinite(P).all() and (P > 0).all()
 
 
 def test_lensing_spectrum_vs_class_and_oracle(sb, oracle, prob5, bg5, obg_same):
@@ -391,3 +391,28 @@ def test_static_schedule_is_bit_identical_to_queue(sb, prob5, bg5):
     # schedule with many more modes than lists and forced splitting: exercise waits and early finishes through the raw item lists
     items, ibeg, T = sb.build_schedule(att.astype(float), 64, min_piece=1)
     assert (items[:, 2] == 1).sum() >= 32
+
+
+def test_batched_cosmologies_bit_identical_to_single_solves(sb, prob5, bg5):
+    """sbm_solvept_batch: one launch over the (cosmology, mode) pairs of three different cosmologies with ragged k-arrays and
+    per-cosmology save times equals three separate solvept calls bit for bit (states, dense output, counters, retcodes, including a
+    failing k = 0 mode), under the queue and under the static preemptive schedule."""
+    M = sb.ΛCDM(lmax=5)
+    bgs, kss, svs = [bg5], [np.array([0.0, 1.0, 30.0, 200.0])], [np.geomspace(1e-3, bg5.tau0 * 0.99, 12)]
+    for f, ks in ((1.1, np.geomspace(0.3, 300, 9)), (0.9, np.array([5.0, 500.0]))):
+        pars = sb.parameters_Planck18(M)
+        pars["Omega_c"] *= f
+        b = sb.solvebg(sb.CosmologyProblem(M, pars))
+        bgs.append(b); kss.append(ks); svs.append(np.geomspace(2e-3, b.tau0 * 0.98, 12))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        singles = [sb.solvept(b.prob, b, k, saveat=sv) for b, k, sv in zip(bgs, kss, svs)]
+    for cost in (None, lambda k: 100 + 3 * np.nan_to_num(k)):
+        batch = sb.solvept_batch(bgs, kss, saveat=svs, cost=cost)
+        assert len(batch) == 3 and not batch.success  # the k = 0 mode fails, as in the reference (runtests.jl:358-361)
+        for one, got in zip(singles, batch.sols):
+            assert np.array_equal(one.retcode, got.retcode)
+            assert np.array_equal(one.uend, got.uend, equal_nan=True)
+            assert np.array_equal(one.usave, got.usave, equal_nan=True)
+            assert np.array_equal(one.stats, got.stats)
