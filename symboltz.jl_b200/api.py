@@ -1296,3 +1296,94 @@ def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτi
     if return_info:
         return out, info
     return out
+
+
+def spectrum_cmb_batch(modes, probs, jl, normalization="Cl", kinterp=None, direct=False, dkt0=math.pi, ntau=300, taucut=1e-2, bgsols=None, ptopts=None, nthreads=None,
+                       return_info=False):
+    """C_l^{AB} (A, B ∈ {T, E}) of several cosmologies sharing one model structure: the perturbation solves of ALL cosmologies go
+    into one integrator launch (`solvept_batch`, each cosmology with its own τ-grid), followed per cosmology by the source, line-of-
+    sight and C_l kernels of `spectrum_cmb` (reference: a serial loop over `spectrum_cmb(modes, probgen(θ), jl)`,
+    docs/src/forecasting.md:56-59).  Per cosmology the result is bit-identical to `spectrum_cmb(modes, prob, jl, ...)`.
+    Returns [ncosmo, nl, nmodes] (NaN where the background failed)."""
+    import concurrent.futures as cf
+    import os
+    _require_cuda()
+    modes = [modes] if isinstance(modes, str) else list(modes)
+    for m in modes:
+        if len(m) != 2 or m[0] not in "TE" or m[1] not in "TE":
+            raise ValueError(f"spectrum_cmb_batch handles the T and E modes only, got {m}")
+    if bgsols is None:
+        def host(p):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return solvebg(p)
+        with cf.ThreadPoolExecutor(nthreads or os.cpu_count()) as pool:
+            bgsols = list(pool.map(host, probs))
+    kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
+    good = [i for i, b in enumerate(bgsols) if b.success]
+    out = np.full((len(probs), len(jl.l), len(modes)), np.nan)
+    if not good:
+        return (out, dict(background_failures=len(probs), mode_failures=0)) if return_info else out
+    grids = [cmb_grids(bgsols[i], kinterp.minimum(), kinterp.maximum(), dkt0, ntau, taucut) for i in good]
+    ks_list = [g[0] if direct else kinterp.xs for g in grids]
+    arena = CosmoArena()
+    batch = solvept_batch([bgsols[i] for i in good], ks_list, saveat=[g[1] for g in grids], arena=arena, **dict(ptopts or {}))
+    dev = batch.d_uend.device
+    cls = []
+    for j, i in enumerate(good):
+        prob, bg, sol, v = probs[i], bgsols[i], batch.sols[j], arena.views[j]
+        ks_fine, taus = grids[j]
+        nk, nt = len(sol.ks), len(taus)
+        dS = torch.empty((nk, 2, nt), dtype=torch.float64, device=dev)
+        scratch = torch.empty(nt * prob.lib.sbm_srcbg_stride(), dtype=torch.float64, device=dev)
+        dtaus = _h2d(taus, dev)
+        rc = prob.lib.sbm_sources(_cptr(v["P"]), C.c_int(v["nb"]), _cptr(v["t"]), _cptr(v["y"]), _cptr(v["dy"]), C.c_int(nt), _cptr(dtaus), _cptr(scratch), C.c_int(nk), _cptr(sol.d_ks),
+                                  _cptr(sol.d_usave), _cptr(dS), C.c_int(1), C.c_int(2), C.c_double(bg.taurec), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbm_sources failed with code {rc}")
+        theta = los_integrate(SourceGrid(dS, sol.ks, taus, sol), jl, ks_fine=ks_fine, kinterp=None if direct else kinterp)
+        cls.append(spectrum_cmb_from_theta(theta, modes, spectrum_primordial(ks_fine, prob), jl.l, ks_fine, normalization))
+    allcl = torch.stack(cls).cpu().numpy()  # [ngood, nmodes, nl]
+    for j, i in enumerate(good):
+        out[i] = allcl[j].T
+    if return_info:
+        return out, dict(background_failures=len(probs) - len(good), mode_failures=int((batch.d_retcode != 0).sum().item()))
+    return out
+
+
+def _central_log_points(theta0, relstep):
+    """2p points of a central difference in ln θ (reference test: FiniteDiff central, relstep 1e-3 on log-parameters, runtests.jl:375,401).
+    Step per parameter h_j = relstep·max(|ln θ_j|, 1)... FiniteDiff uses relstep·|x| with an absolute floor; parameters may be negative
+    (w0), so the log is taken of |θ| and the sign restored."""
+    theta0 = np.asarray(theta0, dtype=np.float64)
+    x = np.log(np.abs(theta0))
+    h = relstep * np.maximum(np.abs(x), 1.0)
+    pts = []
+    for j in range(len(x)):
+        for sgn in (+1, -1):
+            y = x.copy()
+            y[j] += sgn * h[j]
+            pts.append(np.sign(theta0) * np.exp(y))
+    return np.array(pts), h
+
+
+def sensitivity_matter(prob, names, ks, relstep=1e-3, **kw):
+    """∂ln P(k)/∂ln θ_j by central differences over a batched launch of the 2p perturbed cosmologies (BASELINE config 5's
+    quantity; the reference obtains it with ForwardDiff duals through the whole solve and tests it against exactly this
+    finite difference, runtests.jl:363-376).  Returns [nk, p]."""
+    th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
+    pts, h = _central_log_points(th0, relstep)
+    P = spectrum_matter_sweep(prob, names, pts, ks, chunk=len(pts), **kw)
+    L = np.log(P)
+    return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
+
+
+def sensitivity_cmb(mode, prob, names, jl, relstep=1e-3, normalization="Dl", **kw):
+    """∂ln C_l^{mode}/∂ln θ_j by central differences, all 2p cosmologies in one batched launch (BASELINE config 5; reference
+    ForwardDiff.jacobian of log D_l vs FiniteDiff, runtests.jl:391-406).  Returns [nl, p]."""
+    th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
+    pts, h = _central_log_points(th0, relstep)
+    upd = parameter_updater(prob, names)
+    Cl = spectrum_cmb_batch([mode], [upd(t) for t in pts], jl, normalization=normalization, **kw)[:, :, 0]
+    L = np.log(np.abs(Cl))
+    return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)

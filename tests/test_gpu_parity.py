@@ -416,3 +416,47 @@ def test_batched_cosmologies_bit_identical_to_single_solves(sb, prob5, bg5):
             assert np.array_equal(one.uend, got.uend, equal_nan=True)
             assert np.array_equal(one.usave, got.usave, equal_nan=True)
             assert np.array_equal(one.stats, got.stats)
+
+
+def test_batched_cmb_spectra_bit_identical_to_single_calls(sb, prob5, bg5):
+    """spectrum_cmb_batch (one integrator launch for all cosmologies, each with its own τ-grid and fine-k grid) equals
+    spectrum_cmb per cosmology bit for bit."""
+    ls = np.array([2, 10, 50, 200, 600, 1000])
+    M = sb.ΛCDM(lmax=5)
+    probs = [prob5]
+    for f in (1.05, 0.93):
+        pars = sb.parameters_Planck18(M)
+        pars["Omega_c"] *= f
+        pars["h"] *= 2 - f
+        probs.append(sb.CosmologyProblem(M, pars))
+    jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * 4.0)
+    Cb, info = sb.spectrum_cmb_batch(["TT", "EE", "TE"], probs, jl, return_info=True)
+    assert info == dict(background_failures=0, mode_failures=0) and Cb.shape == (3, len(ls), 3)
+    for i, p in enumerate(probs):
+        assert np.array_equal(Cb[i], sb.spectrum_cmb(["TT", "EE", "TE"], p, jl))
+
+
+def test_sensitivities_known_answers_and_oracle(sb, oracle, prob5):
+    """BASELINE config 5's quantity ∂ln P/∂ln θ, ∂ln D_l/∂ln θ from batched central differences (the reference's own check of its
+    ForwardDiff result, runtests.jl:363-406: FiniteDiff central, relstep 1e-3, atol 1e-3 for P(k) and 1.0 for D_l^TT).
+    Exact answers: ∂ln P/∂ln(ln 10¹⁰As) = ln 10¹⁰As, ∂ln P/∂ln ns = ns·ln(k/k_pivot); Ω_c, Ω_b columns against the same central
+    difference of the CPU oracle (own background solves)."""
+    ks = np.array([3.0, 30.0, 150.0, 600.0])
+    names = ["Omega_c", "Omega_b", "ln_As1e10", "ns"]
+    J = sb.sensitivity_matter(prob5, names, ks)
+    pars = prob5.pars
+    kp = prob5.derived["kpivot"]  # pivot 0.05/Mpc in H0/c (src/models/inflation.jl:6)
+    assert np.abs(J[:, 2] - pars["ln_As1e10"]).max() < 1e-5
+    assert np.abs(J[:, 3] - pars["ns"] * np.log(ks / kp)).max() < 1e-4
+    def olog(**over):
+        p = oracle.planck18(lmax=5, **over)
+        return np.log(oracle.spectrum_matter(oracle.Background(p), ks)[0])
+    for j, n in enumerate(names[:2]):
+        x = np.log(pars[n]); h = 1e-3 * max(abs(x), 1.0)
+        fd = (olog(**{n: np.exp(x + h)}) - olog(**{n: np.exp(x - h)})) / (2 * h)
+        assert np.abs(J[:, j] - fd).max() < 1e-3, (n, J[:, j], fd)
+    ls = np.array([25, 100, 400, 1000])
+    jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * 4.0)
+    Jc = sb.sensitivity_cmb("TT", prob5, ["Omega_c", "ln_As1e10"], jl)
+    assert Jc.shape == (4, 2) and np.abs(Jc[:, 1] - pars["ln_As1e10"]).max() < 1e-5
+    assert (np.abs(Jc[:, 0]) < 5).all() and Jc[0, 0] * Jc[-1, 0] != 0
