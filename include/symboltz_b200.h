@@ -37,6 +37,12 @@ const char* sbm_key(void);
  * Returns nb, or -1 if cap is too small. */
 int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info);
 
+/* The same background solve for n cosmologies in one kernel launch, one thread per cosmology (parameter sweeps: the reference
+ * calls solvebg once per θ on the host, docs/src/forecasting.md:56-59 -> src/solve.jl:427-435).
+ * dP [n][NPAR] device (the kappa0 and tau0 slots are filled in), dt [n][cap], dy / ddy [n][cap][5], dinfo [n][8] (layout of
+ * sbm_solvebg's info, two spare), dnb [n] = knots of each cosmology or -1 if cap was too small.  Asynchronous on `stream`. */
+int sbm_solvebg_batch(int n, double* dP, double tini, double tmax, double reltol, double abstol, int cap, double* dt, double* dy, double* ddy, double* dinfo, int* dnb, void* stream);
+
 /* Build the β-table (Jacobian basis functions on the knot-aligned grid) on the device from the uploaded knots.
  * dtab must hold ((nb-1)*msub + 1) * 2 * NBETA doubles.  (replaces the in-RHS spline evaluation `splvalue`,
  * src/utils.jl:135-140, 203-209) */

@@ -289,6 +289,51 @@ def solvebg(prob, reltol=1e-7, abstol=1e-7):
     return sol
 
 
+def solvebg_batch(probs, reltol=1e-7, abstol=1e-7, cap=4096, warn=True):
+    """Background solves of many cosmologies sharing one model structure in ONE kernel launch, one thread per cosmology
+    (`sbm_solvebg_batch`; SURVEY §8f rank 1: in a parameter sweep the reference calls `solvebg` once per θ on the host,
+    src/solve.jl:427-435 via docs/src/forecasting.md:56-59).  The device runs the same __host__ __device__ solver as `solvebg`
+    (Rodas5P, "today" callback, τrec); results agree with the host solve to the solver tolerance, not bit for bit (the device
+    exp/pow/log differ from glibc's in the last place, which moves the adaptive step sequence).
+    Returns a list of BackgroundSolution (knots downloaded in one copy)."""
+    _require_cuda()
+    probs = list(probs)
+    if not probs:
+        return []
+    p0 = probs[0]
+    if any((p.M.lmax, p.M.nx, p.M.w0wa) != (p0.M.lmax, p0.M.nx, p0.M.w0wa) or p.ivspan != p0.ivspan for p in probs):
+        raise ValueError("solvebg_batch: all problems must share the model structure and ivspan")
+    n, npar = len(probs), p0.npar
+    dev = torch.device("cuda")
+    hP = torch.from_numpy(np.stack([p.P for p in probs])).pin_memory()
+    dP = hP.to(dev, non_blocking=True)
+    dt = torch.empty((n, cap), dtype=torch.float64, device=dev)
+    dy = torch.empty((n, cap, 5), dtype=torch.float64, device=dev)
+    ddy = torch.empty((n, cap, 5), dtype=torch.float64, device=dev)
+    dinfo = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    dnb = torch.empty(n, dtype=torch.int32, device=dev)
+    p0.lib.sbm_solvebg_batch.restype = C.c_int
+    rc = p0.lib.sbm_solvebg_batch(C.c_int(n), _cptr(dP), C.c_double(p0.ivspan[0]), C.c_double(p0.ivspan[1]), C.c_double(reltol), C.c_double(abstol), C.c_int(cap),
+                                  _cptr(dt), _cptr(dy), _cptr(ddy), _cptr(dinfo), _cptr(dnb), _stream())
+    if rc != 0:
+        raise RuntimeError(f"sbm_solvebg_batch failed with code {rc}")
+    nb = dnb.cpu().numpy()
+    info = dinfo.cpu().numpy()
+    if (nb <= 0).any():
+        bad = np.nonzero(nb <= 0)[0]
+        raise RuntimeError(f"background solve produced no knots (or more than cap = {cap}) for cosmologies {bad[:8].tolist()}")
+    m = int(nb.max())
+    t, y, d = dt[:, :m].cpu().numpy(), dy[:, :m].cpu().numpy(), ddy[:, :m].cpu().numpy()  # one strided copy each, only the used part
+    sols = []
+    for i, p in enumerate(probs):
+        k = int(nb[i])
+        sol = BackgroundSolution(p, t[i, :k].copy(), y[i, :k].copy(), d[i, :k].copy(), info[i])
+        if warn and not sol.success:
+            warnings.warn(f"Background solution {i} failed with return code {RETCODES.get(sol.retcode)}.\nCheck the parameters and precision settings!")
+        sols.append(sol)
+    return sols
+
+
 class PerturbationSolution:
     def __init__(self, prob, bgsol, ks, tini, saveat, uend, usave, retcode, stats, dks):
         self.prob, self.bg, self.ks, self.tini, self.saveat = prob, bgsol, ks, tini, saveat
@@ -1212,13 +1257,17 @@ class CMBPlan:
         return self.download()
 
 
-def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτini=1e-2, τinimax=1e-4, reltol=1e-5, abstol=1e-5, return_info=False, cost=None, msub=16, nslots=2):
+def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτini=1e-2, τinimax=1e-4, reltol=1e-5, abstol=1e-5, return_info=False, cost=None, msub=16, nslots=2,
+                          background="host"):
     """P(k) for a batch of cosmologies θ ↦ parameter_updater(prob, names)(θ) (BASELINE config 4: emulator / MCMC sweeps;
     the reference runs a serial outer loop of `spectrum_matter(probgen(θ), ks)`, docs/src/forecasting.md:56-59).
     Host background solves run on a thread pool (the ctypes calls release the GIL).  The perturbation solves of `chunk` cosmologies
     go into ONE integrator launch over all their (cosmology, mode) pairs (`solvept_batch`), so the resident warps are kept busy by
     a single descending-k queue instead of one short launch per cosmology; consecutive chunks alternate between two CUDA streams
     (uploads and table builds of chunk c+1 overlap the solve of chunk c, whose tail is filled by the next launch).
+    background = "device": all background solves run first in one `solvebg_batch` launch (one thread per cosmology) instead of the
+    host thread pool -- for boxes with few host cores per GPU; P(k) then agrees with the host-background result to the background
+    tolerance (≈1e-6), not bit for bit.
     thetas: [ncosmo, len(names)].  Returns P[ncosmo, nk] (NaN rows where the background failed); bit-identical to single calls."""
     import concurrent.futures as cf
     import os
@@ -1257,8 +1306,14 @@ def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτi
         info["mode_failures"] += int((h_rc.numpy() != 0).sum())  # read from the pinned copy: a kernel on another stream would queue behind the persistent CTAs
         inflight[slot] = None
 
+    if background not in ("host", "device"):
+        raise ValueError("background must be 'host' or 'device'")
     with cf.ThreadPoolExecutor(nthreads) as pool:
-        results = pool.map(host, thetas)
+        if background == "device":
+            dprobs = [upd(t) for t in thetas]
+            results = iter(zip(dprobs, solvebg_batch(dprobs, warn=False)))
+        else:
+            results = pool.map(host, thetas)
         for c, c0 in enumerate(range(0, n, chunk)):
             slot = c % nslots
             finish(slot)

@@ -68,31 +68,42 @@ SB_HD static inline void sb_spl_eval(const SbSpline& s, double tau, double* y, d
     }
 }
 
-// ================================================================================================ HOST: background
+// ================================================================================================ background (host + device)
 // Small dense Rodas5P for the 5 background unknowns with the analytic Jacobian from the generator
-// (reference: Rodas5P + RFLUFactorization, reltol = abstol = 1e-7, src/solve.jl:313-325, 382).
+// (reference: Rodas5P + RFLUFactorization, reltol = abstol = 1e-7, src/solve.jl:313-325, 382).  The solver is one
+// __host__ __device__ function: sbm_solvebg runs it on the host for one cosmology, sb_solvebg_kernel runs one thread per
+// cosmology for parameter sweeps (sbm_solvebg_batch).
+#ifdef __CUDA_ARCH__
+#define SB_BG_A cA
+#define SB_BG_C cC
+#define SB_BG_H cH
+#else
+#define SB_BG_A hA
+#define SB_BG_C hC
+#define SB_BG_H hH
+#endif
 namespace bgsolve {
-static bool lu5(double* A, int* piv) {
+SB_HD static inline bool lu5(double* A, int* piv) {
     const int n = 5;
     for (int k = 0; k < n; k++) {
         int p = k; double m = fabs(A[k * n + k]);
         for (int i = k + 1; i < n; i++) if (fabs(A[i * n + k]) > m) { m = fabs(A[i * n + k]); p = i; }
         piv[k] = p;
         if (!(m > 0)) return false;
-        if (p != k) for (int j = 0; j < n; j++) std::swap(A[k * n + j], A[p * n + j]);
+        if (p != k) for (int j = 0; j < n; j++) { const double x = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = x; }
         for (int i = k + 1; i < n; i++) { double l = A[i * n + k] / A[k * n + k]; A[i * n + k] = l; for (int j = k + 1; j < n; j++) A[i * n + j] -= l * A[k * n + j]; }
     }
     return true;
 }
-static void lusolve5(const double* A, const int* piv, double* b) {
+SB_HD static inline void lusolve5(const double* A, const int* piv, double* b) {
     const int n = 5;
-    for (int k = 0; k < n; k++) if (piv[k] != k) std::swap(b[k], b[piv[k]]);
+    for (int k = 0; k < n; k++) if (piv[k] != k) { const double x = b[k]; b[k] = b[piv[k]]; b[piv[k]] = x; }
     for (int i = 1; i < n; i++) for (int j = 0; j < i; j++) b[i] -= A[i * n + j] * b[j];
     for (int i = n - 1; i >= 0; i--) { for (int j = i + 1; j < n; j++) b[i] -= A[i * n + j] * b[j]; b[i] /= A[i * n + i]; }
 }
 struct Step {
     double ks[8][5], unew[5], K[3][5];
-    bool run(const double* P, const double* u, double dt) {
+    SB_HD bool run(const double* P, const double* u, double dt) {
         double f0[5], J[25], W[25], U[5], du[5]; int piv[5];
         sb_bg_rhs_jac(u, P, f0, J);
         double dg = 1.0 / (SB_R5_GAMMA * dt);
@@ -102,31 +113,32 @@ struct Step {
         for (int s = 0; s < 8; s++) {
             const double* fs = f0;
             if (s > 0) {
-                if (s <= 5) for (int i = 0; i < 5; i++) { double v = u[i]; for (int j = 0; j < s; j++) v += hA[s][j] * ks[j][i]; U[i] = v; }
+                if (s <= 5) for (int i = 0; i < 5; i++) { double v = u[i]; for (int j = 0; j < s; j++) v += SB_BG_A[s][j] * ks[j][i]; U[i] = v; }
                 else for (int i = 0; i < 5; i++) U[i] += ks[s - 1][i];
                 sb_bg_rhs(U, P, du); fs = du;
             }
-            for (int i = 0; i < 5; i++) { double v = fs[i]; for (int j = 0; j < s; j++) v += hC[s][j] / dt * ks[j][i]; ks[s][i] = v; } // autonomous: dT = 0
+            for (int i = 0; i < 5; i++) { double v = fs[i]; for (int j = 0; j < s; j++) v += SB_BG_C[s][j] / dt * ks[j][i]; ks[s][i] = v; } // autonomous: dT = 0
             lusolve5(W, piv, ks[s]);
         }
         for (int i = 0; i < 5; i++) {
             unew[i] = U[i] + ks[7][i];
-            for (int q = 0; q < 3; q++) { double s = 0; for (int j = 0; j < 8; j++) s += hH[q][j] * ks[j][i]; K[q][i] = s; }
+            for (int q = 0; q < 3; q++) { double s = 0; for (int j = 0; j < 8; j++) s += SB_BG_H[q][j] * ks[j][i]; K[q][i] = s; }
         }
         return true;
     }
-    void interp(const double* u0, const double* u1, double th, double* out) const {
+    SB_HD void interp(const double* u0, const double* u1, double th, double* out) const {
         for (int i = 0; i < 5; i++) out[i] = (1 - th) * u0[i] + th * (u1[i] + (1 - th) * (K[0][i] + th * (K[1][i] + th * K[2][i])));
     }
-    void dinterp(const double* u0, const double* u1, double th, double dt, double* out) const {
+    SB_HD void dinterp(const double* u0, const double* u1, double th, double dt, double* out) const {
         for (int i = 0; i < 5; i++) out[i] = (K[0][i] + th * (-2 * K[0][i] + 2 * K[1][i] + th * (-3 * K[1][i] + 3 * K[2][i] - 4 * th * K[2][i])) - u0[i] + u1[i]) / dt;
     }
 };
-static double errnorm(const double* k8, const double* u0, const double* u1, double abstol, double reltol) {
+SB_HD static inline double errnorm(const double* k8, const double* u0, const double* u1, double abstol, double reltol) {
     double s = 0;
     for (int i = 0; i < 5; i++) { double r = k8[i] / (abstol + reltol * fmax(fabs(u0[i]), fabs(u1[i]))); s += r * r; }
     return sqrt(s / 5);
 }
+SB_HD static inline double hubble_residual(const double* P, double aa, double tini) { double yy[5] = {aa, 0, 1, 1, 0}, g[5]; sb_bg_rhs(yy, P, g); return g[0] * tini / aa - 1.0; }
 } // namespace bgsolve
 
 // PI step controller with OrdinaryDiffEq's defaults for an order-5 method (β1 = 7/50, β2 = 2/25, γ = 0.9, q ∈ [1/5, 10], qoldinit 1e-4)
@@ -143,32 +155,25 @@ struct SbController {
     SB_HD double reject(double dt) { return dt / fmin(5.0, q11 / 0.9); }
 };
 
-extern "C" {
-
-// out[0..15] = N, NPAR, NBETA, NB, LMAX, NX, W0WA, NNZ_FULL, FLOPS_F, FLOPS_LU, FLOPS_SOLVE, NLEVELS, NBLOCKS, P_KAPPA0, P_TAU0, NSLOT
-int sbm_info(int* out) {
-    int v[16] = {SB_N, SB_NPAR, SB_NBETA, SB_NB, SB_LMAX, SB_NX, SB_W0WA, SB_NNZ_FULL, SB_FLOPS_F, SB_FLOPS_LU, SB_FLOPS_SOLVE, SB_NLEVELS, SB_NBLOCKS, SB_P_KAPPA0, SB_P_TAU0, SB_NSLOT};
-    memcpy(out, v, sizeof(v));
-    return 0;
-}
-const char* sbm_key(void) { return SB_MODEL_KEY; }
-
-// Background solve on the host.  Returns the number of spline knots, or -1 if cap is too small.
+namespace bgsolve {
+// The background solve proper.  Knots (t, y, y') are written straight into the caller's arrays (capacity cap); returns the number
+// of knots, or -1 if cap is too small / the solve failed before its first accepted step.
 // info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
-int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info) {
-    using namespace bgsolve;
+SB_HD static inline int solve(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* T, double* Y, double* DY, double* info) {
     // a(τini) from ℋ = 1/τ (reference src/models/cosmologies.jl:76), Newton on ȧ τ / a − 1
     double a = sqrt(P[3] + P[4]) * tini;
     for (int it = 0; it < 100; it++) {
-        auto F = [&](double aa) { double yy[5] = {aa, 0, 1, 1, 0}, g[5]; sb_bg_rhs(yy, P, g); return g[0] * tini / aa - 1.0; };
-        double f = F(a), h = a * 1e-7, fp = (F(a + h) - F(a - h)) / (2 * h), an = a - f / fp;
+        double f = hubble_residual(P, a, tini), h = a * 1e-7, fp = (hubble_residual(P, a + h, tini) - hubble_residual(P, a - h, tini)) / (2 * h), an = a - f / fp;
         bool done = fabs(an - a) <= 1e-15 * fabs(a);
         a = an;
         if (done) break;
     }
     double u[5] = {a, 0, 1, 1, 0};
-    std::vector<double> T, Y, DY;
-    T.push_back(tini); Y.insert(Y.end(), u, u + 5);
+    int nT = 0, nD = 0; // knots with (t, y) written / with y' written (the first y' comes from the first accepted step)
+    bool over = false;
+#define SB_BG_PUSH_TY(tt_, u_) do { if (nT < cap) { T[nT] = (tt_); for (int i_ = 0; i_ < 5; i_++) Y[5 * nT + i_] = (u_)[i_]; nT++; } else over = true; } while (0)
+#define SB_BG_PUSH_D(d_) do { if (nD < cap) { for (int i_ = 0; i_ < 5; i_++) DY[5 * nD + i_] = (d_)[i_]; nD++; } else over = true; } while (0)
+    SB_BG_PUSH_TY(tini, u);
     Step S; SbController ctl; ctl.init();
     // automatic initial step (Hairer), as in OrdinaryDiffEq
     double dt;
@@ -191,6 +196,7 @@ int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double
     double tau0 = 0, kappa0 = 0;
     for (long it = 0;; it++) {
         if (it >= 100000) { rc = SB_RC_MAXITERS; break; }
+        if (over) break;
         if (tt + dt > tmax) dt = tmax - tt;
         if (!S.run(P, u, dt)) { rc = SB_RC_UNSTABLE; break; }
         double EEst = errnorm(S.ks[7], u, S.unew, abstol, reltol);
@@ -199,37 +205,74 @@ int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double
         if (EEst > 1) { nrej++; dt = ctl.reject(dt); if (dt < 1e-14 * tt) { rc = SB_RC_DTMIN; break; } continue; }
         nacc++;
         double dtnew = ctl.accept(dt, q, EEst), d[5];
-        if (first) { S.dinterp(u, S.unew, 0.0, dt, d); DY.insert(DY.end(), d, d + 5); first = false; }
+        if (first) { S.dinterp(u, S.unew, 0.0, dt, d); SB_BG_PUSH_D(d); first = false; }
         if (S.unew[0] - 1.0 >= 0) { // "today" callback: right-root of a − 1 on the dense output (src/solve.jl:158-202)
             double lo = 0, hi = 1, tmp[5];
             for (int b = 0; b < 200; b++) { double mid = 0.5 * (lo + hi); if (mid == lo || mid == hi) break; S.interp(u, S.unew, mid, tmp); if (tmp[0] - 1.0 >= 0) hi = mid; else lo = mid; }
             double uend[5], dend[5]; S.interp(u, S.unew, hi, uend);
             double dtr = hi * dt, tr = tt + dtr;
-            Step S2; // dense-output vectors of the shortened step (what OrdinaryDiffEq recomputes after moving t)
-            if (S2.run(P, u, dtr)) S2.dinterp(u, uend, 1.0, dtr, dend); else sb_bg_rhs(uend, P, dend);
-            T.push_back(tr); Y.insert(Y.end(), uend, uend + 5); DY.insert(DY.end(), dend, dend + 5);
+            // dense-output vectors of the shortened step (what OrdinaryDiffEq recomputes after moving t); S is not needed any more
+            if (S.run(P, u, dtr)) S.dinterp(u, uend, 1.0, dtr, dend); else sb_bg_rhs(uend, P, dend);
+            SB_BG_PUSH_TY(tr, uend); SB_BG_PUSH_D(dend);
             tau0 = tr; kappa0 = uend[1];
             break;
         }
         S.dinterp(u, S.unew, 1.0, dt, d);
-        tt += dt; memcpy(u, S.unew, sizeof(u));
-        T.push_back(tt); Y.insert(Y.end(), u, u + 5); DY.insert(DY.end(), d, d + 5);
+        tt += dt;
+        for (int i = 0; i < 5; i++) u[i] = S.unew[i];
+        SB_BG_PUSH_TY(tt, u); SB_BG_PUSH_D(d);
         if (tt >= tmax) { tau0 = tt; kappa0 = u[1]; break; }
         dt = dtnew;
     }
-    int nb = (int)T.size();
+#undef SB_BG_PUSH_TY
+#undef SB_BG_PUSH_D
+    const int nb = nT;
     // τrec: knot of maximal visibility over solver steps (src/solve.jl:183-189)
     double vmax = -1, taurec = tau0;
     for (int i = 0; i < nb; i++) { double g[5]; sb_bg_rhs(&Y[5 * i], P, g); double v = -g[1] * exp(-(Y[5 * i + 1] - kappa0)); if (v > vmax) { vmax = v; taurec = T[i]; } }
     info[0] = tau0; info[1] = kappa0; info[2] = taurec; info[3] = rc; info[4] = (double)nacc; info[5] = (double)nrej;
-    if (nb > cap || (int)DY.size() != 5 * nb) return -1;
-    memcpy(t, T.data(), nb * sizeof(double)); memcpy(y, Y.data(), 5 * nb * sizeof(double)); memcpy(dy, DY.data(), 5 * nb * sizeof(double));
+    if (over || nD != nb) return -1;
     return nb;
+}
+} // namespace bgsolve
+
+extern "C" {
+
+// out[0..15] = N, NPAR, NBETA, NB, LMAX, NX, W0WA, NNZ_FULL, FLOPS_F, FLOPS_LU, FLOPS_SOLVE, NLEVELS, NBLOCKS, P_KAPPA0, P_TAU0, NSLOT
+int sbm_info(int* out) {
+    int v[16] = {SB_N, SB_NPAR, SB_NBETA, SB_NB, SB_LMAX, SB_NX, SB_W0WA, SB_NNZ_FULL, SB_FLOPS_F, SB_FLOPS_LU, SB_FLOPS_SOLVE, SB_NLEVELS, SB_NBLOCKS, SB_P_KAPPA0, SB_P_TAU0, SB_NSLOT};
+    memcpy(out, v, sizeof(v));
+    return 0;
+}
+const char* sbm_key(void) { return SB_MODEL_KEY; }
+
+// Background solve on the host.  Returns the number of spline knots, or -1 if cap is too small.
+// info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
+int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info) {
+    return bgsolve::solve(P, tini, tmax, reltol, abstol, cap, t, y, dy, info);
 }
 
 } // extern "C"
 
 // ================================================================================================ DEVICE
+// Batched background solve: one thread per cosmology.  A parameter sweep has hundreds to thousands of
+// independent 5-unknown stiff solves of ≈10³ steps each; the threads of a warp run the same step loop (divergence only in the
+// accept/reject tails and the step counts), the working set (stage vectors, 5×5 factors) lives in registers/local memory.
+// P[c] gets kappa0 and tau0 filled in (callback semantics, src/solve.jl:183-189) so that the perturbation launch can follow on
+// the same stream without a host round trip.
+__global__ void __launch_bounds__(32) sb_solvebg_kernel(int n, double* __restrict__ P, double tini, double tmax, double reltol, double abstol, int cap, double* __restrict__ t, double* __restrict__ y,
+                                                         double* __restrict__ dy, double* __restrict__ info, int* __restrict__ nb) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double* Pc = P + (size_t)c * SB_NPAR;
+    double inf[6];
+    const int r = bgsolve::solve(Pc, tini, tmax, reltol, abstol, cap, t + (size_t)c * cap, y + (size_t)c * cap * 5, dy + (size_t)c * cap * 5, inf);
+    nb[c] = r;
+    for (int j = 0; j < 6; j++) info[(size_t)c * 8 + j] = inf[j];
+    info[(size_t)c * 8 + 6] = 0; info[(size_t)c * 8 + 7] = 0;
+    Pc[SB_P_KAPPA0] = inf[1]; Pc[SB_P_TAU0] = inf[0];
+}
+
 // β-table.  The background spline is piecewise cubic on the solver's knots, so β_m(y(τ)) is smooth only *between* knots:
 // every knot interval [t_j, t_{j+1}] is subdivided uniformly into msub sub-intervals; node n = j·msub + s sits at
 // τ = t_j + s·(t_{j+1} − t_j)/msub and stores β_m and dβ_m/dτ (exact, chain rule through the spline derivative).
@@ -1138,6 +1181,17 @@ int sbm_smem_bytes(void) { return SB_SM_BYTES; }
 int sbm_srcbg_stride(void) { return SB_SRCBG_STRIDE; }
 
 // dtab: ((nb-1)·msub + 1)·2·NBETA doubles
+// Batched background solve on the device: dP [n][NPAR] (kappa0/tau0 slots are filled in), outputs dt [n][cap], dy/ddy [n][cap][5],
+// dinfo [n][8] (tau0, kappa0, taurec, retcode, naccept, nreject, 0, 0), dnb [n] (knots, or -1 if cap was too small).
+int sbm_solvebg_batch(int n, double* dP, double tini, double tmax, double reltol, double abstol, int cap, double* dt, double* dy, double* ddy, double* dinfo, int* dnb, void* stream) {
+    if (n <= 0) return 0;
+    if (cap < 2) return -1;
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_solvebg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0)); // local-memory working set: all of L1
+    sb_solvebg_kernel<<<(n + 31) / 32, 32, 0, (cudaStream_t)stream>>>(n, dP, tini, tmax, reltol, abstol, cap, dt, dy, ddy, dinfo, dnb);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, double* dtab, void* stream) {
     SbSpline spl{nb, dt, dy, ddy};
     int nnode = (nb - 1) * msub + 1;

@@ -460,3 +460,44 @@ def test_sensitivities_known_answers_and_oracle(sb, oracle, prob5):
     Jc = sb.sensitivity_cmb("TT", prob5, ["Omega_c", "ln_As1e10"], jl)
     assert Jc.shape == (4, 2) and np.abs(Jc[:, 1] - pars["ln_As1e10"]).max() < 1e-5
     assert (np.abs(Jc[:, 0]) < 5).all() and Jc[0, 0] * Jc[-1, 0] != 0
+
+
+def test_device_background_batch_matches_host_solver(sb, oracle):
+    """`solvebg_batch` (one thread per cosmology, the same __host__ __device__ Rodas5P as the host `solvebg`) against
+    the host solver on a seeded w0waCDM hypercube and against the oracle's own background.  The adaptive step sequences differ in the
+    last place (device vs glibc exp/pow), so the comparison is at the solver tolerance (reltol = 1e-7): τ0, κ0 to 2e-6 relative, the
+    splined unknowns to 2e-6 of their range, τrec to one solver step; P(k) downstream to 1e-5 (a tenth of the north-star 1e-4)."""
+    M = sb.w0waCDM(lmax=10)
+    prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+    names = ["h", "Omega_c", "Omega_b", "w0", "wa"]
+    rng = np.random.default_rng(7)
+    lo, hi = np.array([0.6, 0.22, 0.044, -1.2, -0.3]), np.array([0.8, 0.32, 0.056, -0.8, 0.3])
+    th = lo + (hi - lo) * rng.random((40, 5))
+    upd = sb.parameter_updater(prob, names)
+    probs = [upd(t) for t in th]
+    dev = sb.solvebg_batch(probs)
+    assert len(dev) == 40 and all(b.success for b in dev)
+    for i in (0, 7, 19, 39):
+        h = sb.solvebg(probs[i])
+        d = dev[i]
+        assert abs(d.tau0 / h.tau0 - 1) < 2e-6 and abs(d.kappa0 / h.kappa0 - 1) < 2e-6
+        assert abs(len(d.t) - len(h.t)) <= max(3, len(h.t) // 50)  # same scheme, same controller: (almost) the same number of steps
+        assert d.P[prob.iP_tau0] == d.tau0 and d.P[prob.iP_kappa0] == d.kappa0
+        j = np.searchsorted(h.t, d.taurec)
+        assert h.t[max(j - 2, 0)] <= h.taurec <= h.t[min(j + 2, len(h.t) - 1)]
+        taus = np.exp(np.linspace(np.log(h.t[0] * 1.001), np.log(min(h.tau0, d.tau0) * 0.999), 400))
+        yh = np.array([h.spline(t)[0] for t in taus]); yd = np.array([d.spline(t)[0] for t in taus])
+        scale = np.abs(yh).max(axis=0)
+        assert (np.abs(yd - yh).max(axis=0) / scale).max() < 2e-6
+    # the oracle's independent background (ΛCDM fiducial): τ0 and κ0
+    M5 = sb.ΛCDM(lmax=5)
+    p5 = sb.CosmologyProblem(M5, sb.parameters_Planck18(M5))
+    d5 = sb.solvebg_batch([p5])[0]
+    obg = oracle.Background(oracle.planck18(lmax=5))
+    assert abs(d5.tau0 / obg.tau0 - 1) < 1e-5 and abs(d5.kappa0 / obg.kappa0 - 1) < 1e-5
+    # downstream: the sweep with device backgrounds reproduces the host-background sweep
+    ks = sb.loggrid(1e-4, 1.0, length=16) / sb.k0
+    Ph, ih = sb.spectrum_matter_sweep(prob, names, th[:6], ks, chunk=6, return_info=True)
+    Pd, id_ = sb.spectrum_matter_sweep(prob, names, th[:6], ks, chunk=6, return_info=True, background="device")
+    assert ih["mode_failures"] == 0 and id_["mode_failures"] == 0 and id_["background_failures"] == 0
+    assert np.abs(Pd / Ph - 1).max() < 1e-5
