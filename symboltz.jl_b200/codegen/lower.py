@@ -447,7 +447,61 @@ def generate(m: Model):
     nat = []
     for b in top_blocks:
         nat += b
-    for p in sorted(allpaths, key=lambda p: -max(len(L.rows[v]) for v in p)):
+    ordered = sorted(allpaths, key=lambda p: -max(len(L.rows[v]) for v in p))
+    # Bank-aware tie-break.  In the path sweeps lane = path and the lanes address shared memory at (end of path) − q, so two
+    # paths whose ends are congruent modulo 16 doubles (= 32 banks) serialise every access they make together.  Paths with the
+    # same key are interchangeable as far as the ELL widths go: permute them so that the ends (weight 2: both substitution
+    # sweeps) and the starts (weight 1: the factorisation sweep) of the phase-0 paths collide as little as possible.
+    p0ids = {id(p) for p in paths0}
+
+    def _cost(seq):
+        pos, ends, starts = len(nat), [], []
+        for p in seq:
+            if id(p) in p0ids:
+                starts.append((pos % 16, len(p)))
+                ends.append(((pos + len(p) - 1) % 16, len(p)))
+            pos += len(p)
+        c = 0
+        for lst, w in ((ends, 2), (starts, 1)):
+            for a in range(len(lst)):
+                for b in range(a):
+                    if lst[a][0] == lst[b][0]:
+                        c += w * min(lst[a][1], lst[b][1])
+        return c
+
+    import random
+    rng = random.Random(12345)
+    keys = [-max(len(L.rows[v]) for v in p) for p in ordered]
+    classes = [[i for i in range(len(ordered)) if keys[i] == k] for k in sorted(set(keys))]
+    classes = [c for c in classes if len(c) > 1]
+    best, bestc = list(ordered), _cost(ordered)
+    if classes and bestc > 0:
+        for restart in range(20):
+            cur = list(ordered)
+            if restart:
+                for c in classes:
+                    perm = c[:]
+                    rng.shuffle(perm)
+                    vals = [ordered[i] for i in perm]
+                    for i, v in zip(c, vals):
+                        cur[i] = v
+            curc = _cost(cur)
+            for it in range(4000):
+                c = rng.choice(classes)
+                i, j = rng.sample(c, 2)
+                cur[i], cur[j] = cur[j], cur[i]
+                nc = _cost(cur)
+                if nc <= curc:
+                    curc = nc
+                else:
+                    cur[i], cur[j] = cur[j], cur[i]
+                if curc == 0:
+                    break
+            if curc < bestc:
+                best, bestc = list(cur), curc
+            if bestc == 0:
+                break
+    for p in best:
         nat += p
     assert sorted(nat) == list(range(N)) and N <= 1022
     # roles of the J_local entries in this schedule: 0 diag, 1 "up" (row child, col parent), 2 "lo" (row parent, col child),

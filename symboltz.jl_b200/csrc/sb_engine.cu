@@ -366,6 +366,12 @@ struct SbSolveArgs {
 #endif
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
+#ifndef SB_Z3
+#define SB_Z3 1
+#endif
+#ifndef SB_KEEP_MAX
+#define SB_KEEP_MAX 24 // doubles per lane that sb_bsolve may hold across its top step (see KEEP there)
+#endif
 // packed schedule fields (generator: lower.py).  SB_IDXBITS = 8 when N <= 254 and NB <= 255 (byte extraction), else 10 (N <= 1022).
 #if SB_IDXBITS == 8
 #define SB_E_COL(ix) ((ix) & 255u)
@@ -697,23 +703,46 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
 // warp-synchronous steps: forward along the phase-0 paths (registers) | top: root paths forward + backward, top blocks =
 // gather the children's terms, exchange by shuffles, mat-vec with the explicit inverse | backward along the phase-0 paths.
 template <int NR>
-__device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[NR], const double* di, const double* up, const double* mm, const double* blk, int lane) {
+__device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[NR], const double* __restrict__ di, const double* __restrict__ up, const double* __restrict__ mm, const double* __restrict__ blk, int lane) {
+    // KEEP: the forward-substitution results of the phase-0 paths stay in registers across the top step (the shared-memory data
+    // path is the busiest unit of this kernel: this saves the store and the reload of every interior path vertex); only the last
+    // vertex of a path, which the owner of its parent gathers, is stored.  Positions are counted from the END of the path
+    // (q = 0 is the last vertex) in both sweeps, so the register arrays of the two sweeps line up for paths of any length.
+    constexpr bool KEEP = (SB_PR * SB_PL * NR <= SB_KEEP_MAX);
+    double fw[KEEP ? SB_PR : 1][KEEP ? NR : 1][KEEP ? SB_PL : 1];
 #pragma unroll
     for (int rd = 0; rd < SB_PR; rd++) {
-        // The recurrence runs unpredicated over the longest path length: past the end of a shorter path (or on a lane without a
-        // path) it reads neighbouring shared-memory values and computes garbage that is never stored.  This keeps the dependent
-        // DFMA chain free of predicated register moves and lets all loads issue from one base register.
+        // The recurrence runs unpredicated over the longest path length with predicated loads: past the end of a shorter path
+        // (or on a lane without a path) it computes zeros that are never stored.  This keeps the dependent DFMA chain free of
+        // predicated register moves and lets all loads issue from one base register.
         const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
-        const double* mmp = mm + start;
+        if (KEEP) {
+            const int end = start + len - 1;
+            const double* mme = mm + end;
 #pragma unroll
-        for (int a = 0; a < NR; a++) {
-            double* rp = rr[a] + start;
-            double av[SB_PL];
-            double acc = rp[0];
+            for (int a = 0; a < NR; a++) {
+                double* re = rr[a] + end;
+                double acc = 0.0;
 #pragma unroll
-            for (int pos = 1; pos < SB_PL; pos++) { const bool in = pos < len; const double m_ = in ? mmp[pos - 1] : 0.0, r_ = in ? rp[pos] : 0.0; acc = fma(-m_, acc, r_); av[pos] = acc; }
+                for (int q = SB_PL - 1; q >= 0; q--) { // first vertex of the path: no predecessor, acc is still 0 and the result is r itself
+                    const double m_ = (q + 1 < len) ? mme[-q - 1] : 0.0, r_ = (q < len) ? re[-q] : 0.0;
+                    acc = fma(-m_, acc, r_);
+                    fw[rd][a][q] = acc;
+                }
+                if (len > 1) re[0] = fw[rd][a][0];
+            }
+        } else {
+            const double* mmp = mm + start;
 #pragma unroll
-            for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
+            for (int a = 0; a < NR; a++) {
+                double* rp = rr[a] + start;
+                double av[SB_PL];
+                double acc = rp[0];
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) { const bool in = pos < len; const double m_ = in ? mmp[pos - 1] : 0.0, r_ = in ? rp[pos] : 0.0; acc = fma(-m_, acc, r_); av[pos] = acc; }
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
+            }
         }
     }
     __syncwarp();
@@ -781,7 +810,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             double xs[SB_PL];
             double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
 #pragma unroll
-            for (int q = 0; q < SB_PL; q++) { const bool in = q < len; const double u_ = in ? upe[-q] : 0.0, r_ = in ? re[-q] : 0.0, d_ = in ? die[-q] : 0.0; xv = fma(-u_, xv, r_ * d_); xs[q] = xv; }
+            for (int q = 0; q < SB_PL; q++) { const bool in = q < len; const double u_ = in ? upe[-q] : 0.0, r_ = KEEP ? fw[KEEP ? rd : 0][KEEP ? a : 0][KEEP ? q : 0] : (in ? re[-q] : 0.0), d_ = in ? die[-q] : 0.0; xv = fma(-u_, xv, r_ * d_); xs[q] = xv; }
 #pragma unroll
             for (int q = 0; q < SB_PL; q++) if (q < len) re[-q] = xs[q];
         }
@@ -956,9 +985,20 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                     const int i = r * 32 + lane;
                     if (i < SB_N) { Zp[i] = S.pqc[2 * r] * bs[SB_LO16(S.pqi[r])]; Zq[i] = S.pqc[2 * r + 1] * bs[SB_HI16(S.pqi[r])]; }
                 }
+#if SB_Z3
+                { // the stage-1 right-hand side f0 + dt·d1·dT does not depend on Z: its solve rides along with the two Woodbury columns
+                    const double hd0 = dt * cd[0];
+#pragma unroll
+                    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) K[i] = f0[i] + hd0 * dT[i]; }
+                }
+                __syncwarp();
+                { double* const zz[3] = {Zp, Zq, K}; sb_bsolve<3>(S, zz, di, up, mm, blk, lane); }
+                nsolve += 3;
+#else
                 __syncwarp();
                 { double* const zz[2] = {Zp, Zq}; sb_bsolve<2>(S, zz, di, up, mm, blk, lane); }
                 nsolve += 2;
+#endif
                 double m11, m12, m21, m22;
                 sb_hub_dots(S, bs, Zp, m11, m21, lane);
                 sb_hub_dots(S, bs, Zq, m12, m22, lane);
@@ -1032,9 +1072,13 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_in
                         __syncwarp();
                         sb_eval_f<true>(S, bs + cslot[s] * SB_NB, U, ks, lane, Racc, hd_, dT); nf++;
                     } else {
+#if SB_Z3
+                        continue; // solved together with Z
+#else
 #pragma unroll
                         for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) ks[i] = f0[i] + hd_ * dT[i]; }
                         __syncwarp();
+#endif
                     }
                     { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); } nsolve++;
                 }
