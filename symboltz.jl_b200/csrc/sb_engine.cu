@@ -724,8 +724,14 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
                 double* re = rr[a] + end;
                 double acc = 0.0;
 #pragma unroll
-                for (int q = SB_PL - 1; q >= 0; q--) { // first vertex of the path: no predecessor, acc is still 0 and the result is r itself
-                    const double m_ = (q + 1 < len) ? mme[-q - 1] : 0.0, r_ = (q < len) ? re[-q] : 0.0;
+                for (int q = SB_PL - 1; q >= 0; q--) {
+                    // Unconditional loads: positions before the first vertex of a shorter path (and lanes without a path) read
+                    // neighbouring shared-memory values (always inside the CTA's allocation: the arrays swept here start at least 2N
+                    // doubles into it) and compute garbage that is never stored; the accumulator is cleared at the first vertex,
+                    // which has no predecessor, so the garbage does not reach the path.  (A predicated load costs four
+                    // instructions -- load, clear, two moves -- which made this sweep a fifth of the kernel's instruction count.)
+                    const double m_ = mme[-q - 1], r_ = re[-q];
+                    if (q + 1 >= len) acc = 0.0;
                     acc = fma(-m_, acc, r_);
                     fw[rd][a][q] = acc;
                 }
@@ -739,7 +745,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
                 double av[SB_PL];
                 double acc = rp[0];
 #pragma unroll
-                for (int pos = 1; pos < SB_PL; pos++) { const bool in = pos < len; const double m_ = in ? mmp[pos - 1] : 0.0, r_ = in ? rp[pos] : 0.0; acc = fma(-m_, acc, r_); av[pos] = acc; }
+                for (int pos = 1; pos < SB_PL; pos++) { acc = fma(-mmp[pos - 1], acc, rp[pos]); av[pos] = acc; } // past the end of the path: garbage, never stored
 #pragma unroll
                 for (int pos = 1; pos < SB_PL; pos++) if (pos < len) rp[pos] = av[pos];
             }
@@ -810,7 +816,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             double xs[SB_PL];
             double xv = (par == SB_NOPAR) ? 0.0 : rr[a][par];
 #pragma unroll
-            for (int q = 0; q < SB_PL; q++) { const bool in = q < len; const double u_ = in ? upe[-q] : 0.0, r_ = KEEP ? fw[KEEP ? rd : 0][KEEP ? a : 0][KEEP ? q : 0] : (in ? re[-q] : 0.0), d_ = in ? die[-q] : 0.0; xv = fma(-u_, xv, r_ * d_); xs[q] = xv; }
+            for (int q = 0; q < SB_PL; q++) { const double r_ = KEEP ? fw[KEEP ? rd : 0][KEEP ? a : 0][KEEP ? q : 0] : re[-q]; xv = fma(-upe[-q], xv, r_ * die[-q]); xs[q] = xv; } // q >= len: garbage, never stored
 #pragma unroll
             for (int q = 0; q < SB_PL; q++) if (q < len) re[-q] = xs[q];
         }

@@ -266,3 +266,33 @@ def test_build_schedule_covers_every_mode_once_and_balances():
     assert len(items) == 3 and ibeg[-1] == 3
     m = sb.ModeCostModel(k, cost)
     assert np.abs(m(k) / cost - 1).max() < 0.2
+
+
+def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
+    """The integrator's relabelled state order (codegen/lower.py): sb_nat is a permutation of the natural order, every elimination path is a
+    contiguous index range inside [0, N), paths do not overlap, and the bank-aware tie-break leaves at most a handful of (path, path)
+    pairs whose ends are congruent modulo 16 doubles (each such pair costs one extra shared-memory wavefront per access)."""
+    import re
+    for M in (sb.ΛCDM(lmax=10), sb.w0waCDM(lmax=10), sb.ΛCDM(lmax=5)):
+        prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+        so, info = sb.build.build_model(M.lmax, M.nx, M.w0wa)
+        text = open(os.path.join(os.path.dirname(so), "sb_model_gen.h")).read()
+
+        def arr(name):
+            m = re.search(name + r"\[[^\]]*\]\s*=\s*\{([^}]*)\}", text)
+            return [int(x.strip().rstrip("u"), 0) for x in m.group(1).split(",") if x.strip()]
+
+        N = prob.N
+        assert sorted(arr("sb_nat")) == list(range(N))
+        bits8 = "#define SB_IDXBITS 8" in text
+        heads = arr("sb_path_head")
+        covered, ends = set(), []
+        for v in heads:
+            start, ln = (v & 255, (v >> 8) & 255) if bits8 else (v & 4095, (v >> 12) & 255)
+            if ln:
+                rng_ = set(range(start, start + ln))
+                assert start + ln <= N and not (rng_ & covered)
+                covered |= rng_
+                ends.append(((start + ln - 1) % 16, ln))
+        weight = sum(min(a[1], b[1]) for i, a in enumerate(ends) for b in ends[:i] if a[0] == b[0])
+        assert weight <= 6, (M, weight, ends)
