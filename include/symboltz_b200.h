@@ -99,6 +99,7 @@ int sbm_solvept_batch(int ncosmo, const void* dcosmos, int nk, const double* dks
 int sbm_cosmo_bytes(void);
 int sbm_cont_stride(void);
 int sbm_resident_warps(void);
+int sbm_resident_warps_batch(void); /* resident warps of the batched instantiation (its launch bounds are a separate build knob) */
 int sbm_warps_per_cta(void);
 
 /* Total-matter gauge-invariant overdensity Δm(τ, k_i) from states du[nk][N] (replaces the observed-function evaluation

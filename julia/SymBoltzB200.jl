@@ -55,4 +55,38 @@ function solvept_b200(lib, P, bgsol, ks, ptivini; reltol = 1e-5, abstol = 1e-5, 
     return (; uend = reshape(Array(duend), N, nk), usave = ns > 0 ? reshape(Array(dusave), N, ns, nk) : nothing, retcode = ret, stats = reshape(Array(dstats), 4, nk))
 end
 
+"""
+Parameter sweep (docs/src/forecasting.md:56-59: `for θ in θs; spectrum_matter(probgen(θ), ks); end`) as three library calls:
+all backgrounds in one kernel (`sbm_solvebg_batch`, one thread per cosmology), one β-table per cosmology (`sbm_build_table`), and
+ONE integrator launch over all (cosmology, mode) pairs (`sbm_solvept_batch`).  `Ps` is the npar × n matrix of parameter vectors
+(`parameter_vector` without κ0/τ0: the device fills them in).  Mirrors `spectrum_matter_sweep(..., background = "device")` of api.py.
+"""
+function sweep_b200(lib, Ps::Matrix{Float64}, ks; cap = 4096, msub = 16, nbeta, reltol = 1e-5, abstol = 1e-5, maxiters = 100_000, N = 84)
+    n = size(Ps, 2); nk = length(ks)
+    dP = CuArray(Ps); dt = CUDA.zeros(Float64, cap, n); dy = CUDA.zeros(Float64, 5, cap, n); ddy = CUDA.zeros(Float64, 5, cap, n)
+    dinfo = CUDA.zeros(Float64, 8, n); dnb = CUDA.zeros(Int32, n)
+    rc = ccall((:sbm_solvebg_batch, lib), Cint, (Cint, CuPtr{Float64}, Cdouble, Cdouble, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, Ptr{Cvoid}),
+               n, dP, 1e-6, 100.0, 1e-7, 1e-7, cap, dt, dy, ddy, dinfo, dnb, C_NULL)
+    rc == 0 || error("sbm_solvebg_batch failed ($rc)")
+    nb = Array(dnb); info = Array(dinfo)                       # τ0 = info[1, c], κ0 = info[2, c], retcode = info[4, c]
+    # one sbm_cosmo_t (112 bytes, layout in the header) per cosmology: pointers into the batch arrays, β-table, interval look-up
+    recs = Vector{UInt8}(undef, 112n); tabs = CuArray{Float64}[]; luts = CuArray{Int32}[]
+    for c in 1:n
+        ts = Array(view(dt, 1:nb[c], c)); nlut = 4096; s0 = log(ts[begin]); dsl = (log(ts[end]) - s0) / nlut
+        push!(luts, CuArray(Int32.(clamp.(searchsortedlast.(Ref(ts), exp.(s0 .+ dsl .* (0:nlut-1))) .- 1, 0, nb[c] - 2))))
+        push!(tabs, CUDA.zeros(Float64, ((nb[c] - 1) * msub + 1) * 2 * nbeta))
+        pP, pt, py, pd = pointer(dP, 1 + (c - 1) * size(Ps, 1)), pointer(dt, 1 + (c - 1) * cap), pointer(dy, 1 + (c - 1) * 5cap), pointer(ddy, 1 + (c - 1) * 5cap)
+        ccall((:sbm_build_table, lib), Cint, (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, CuPtr{Float64}, Ptr{Cvoid}), pP, nb[c], pt, py, pd, msub, tabs[end], C_NULL)
+        write_cosmo_record!(recs, c, pP, nb[c], pt, py, pd, msub, nlut, s0, 1 / dsl, pointer(luts[end]), pointer(tabs[end]), info[1, c])   # field by field, as CosmoArena.load does
+    end
+    dcos = CuArray(recs); kall = repeat(Float64.(ks), n); dks = CuArray(kall)
+    dtini = CuArray(repeat(clamp.(min.(1e-2 ./ ks, 1e-4), 1e-6, Inf), n)); dcof = CuArray(Int32.(repeat(0:n-1; inner = nk))); dorder = CuArray(Int32.(sortperm(kall; rev = true) .- 1))
+    duend = CUDA.zeros(Float64, N, nk * n); dret = CUDA.zeros(Int32, nk * n); dstats = CUDA.zeros(Int64, 4, nk * n); dqueue = CUDA.zeros(Int32, 1)
+    rc = ccall((:sbm_solvept_batch, lib), Cint, (Cint, CuPtr{UInt8}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int32}, Cint, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64},
+                CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, CuPtr{Int32}, CuPtr{Int32}, Cint, CuPtr{Float64}, CuPtr{Int32}, Ptr{Cvoid}),
+               n, dcos, nk * n, dks, dtini, dcof, dorder, 0, reltol, abstol, maxiters, CU_NULL, duend, dret, dstats, dqueue, CU_NULL, CU_NULL, 0, CU_NULL, CU_NULL, C_NULL)
+    rc >= 0 || error("sbm_solvept_batch failed ($rc)")
+    return reshape(Array(duend), N, nk, n), reshape(Array(dret), nk, n)    # Δm and P(k) follow with sbm_delta_m per cosmology
+end
+
 end # module

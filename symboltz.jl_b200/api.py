@@ -427,8 +427,9 @@ class ModeCostModel:
         return np.interp(np.asarray(ks, dtype=np.float64), self.kn, self.cn)
 
 
-def resident_warps(prob):
-    return int(prob.lib.sbm_resident_warps())
+def resident_warps(prob, batch=False):
+    """Warps the integrator keeps resident on this GPU (= lists of a static schedule); `batch`: of the batched instantiation."""
+    return int(prob.lib.sbm_resident_warps_batch() if batch else prob.lib.sbm_resident_warps())
 
 
 def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None):
@@ -631,7 +632,7 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
     nlists = 0
     if cost is not None and nk > 0:
         wpc = int(prob.lib.sbm_warps_per_cta())
-        nlists = max(wpc, min(resident_warps(prob), nk) // wpc * wpc)
+        nlists = max(wpc, min(resident_warps(prob, batch=True), nk) // wpc * wpc)
         items, ibeg, _ = build_schedule(np.nan_to_num(np.asarray(cost(kall) if callable(cost) else cost, dtype=np.float64) * np.ones(nk), nan=1.0), nlists)
         ditems, dibeg = _h2d(items, dev), _h2d(ibeg, dev)
         dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)

@@ -364,6 +364,13 @@ struct SbSolveArgs {
 #ifndef SB_MINBLOCKS
 #define SB_MINBLOCKS 8
 #endif
+// Warps per SM come in steps of four (each of the four sub-partitions holds 16 K registers): 8 warps up to 255 registers, 12 up
+// to 168.  Measured (profiles/integrate_r1.md): 12 warps with 168 registers (150-360 B of spills) gain 4 % on a long uniform
+// queue but lose 30 % of single-mode latency, and the config-4 sweep (chunked launches with tails) is 8-14 % SLOWER -- so both
+// instantiations run 8 warps with all the registers.  The batched instantiation keeps its own knob.
+#ifndef SB_MINBLOCKS_BATCH
+#define SB_MINBLOCKS_BATCH 8
+#endif
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
 #ifndef SB_Z3
@@ -841,7 +848,7 @@ template <bool BATCH>
 #ifdef SB_NOLB
 __global__ void sb_integrate_kernel
 #else
-__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, SB_MINBLOCKS) sb_integrate_kernel
+__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCKS_BATCH : SB_MINBLOCKS) sb_integrate_kernel
 #endif
     (const __grid_constant__ SbSolveArgs A) {
     extern __shared__ double sm_all[];
@@ -1265,7 +1272,7 @@ static int sb_solvept_impl(const double* dP, int nb, const double* dt, const dou
     A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue; A.trace = dtrace; A.ntrace = ntrace;
     A.items = ditems; A.ibeg = dibeg; A.cont = dcont; A.flags = dflags;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
-    static int occ = 0, nsm = 0;
+    static int occ = 0, occb = 0, nsm = 0;
     if (!occ) {
         int dev; SB_CUDA_CHECK(cudaGetDevice(&dev));
         SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -1274,13 +1281,13 @@ static int sb_solvept_impl(const double* dP, int nb, const double* dt, const dou
         int occ_b = 0;
         SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<false>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
         SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, sb_integrate_kernel<true>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
-        occ = std::max(1, std::min(occ, occ_b));
+        occ = std::max(1, occ); occb = std::max(1, occ_b);
     }
-    int grid = nctas > 0 ? nctas : std::min((nk + SB_WARPS_PER_CTA - 1) / SB_WARPS_PER_CTA, nsm * occ);
+    int grid = nctas > 0 ? nctas : std::min((nk + SB_WARPS_PER_CTA - 1) / SB_WARPS_PER_CTA, nsm * (dcosmos ? occb : occ));
     if (ditems) {
         // static schedule: one list per warp; a continuation item spins on a flag set by the warp that runs the first piece,
         // which is the FIRST item of its list -- so every list must be resident from the start
-        if (nlists <= 0 || nlists > nsm * occ * SB_WARPS_PER_CTA || nlists % SB_WARPS_PER_CTA) return -3;
+        if (nlists <= 0 || nlists > nsm * (dcosmos ? occb : occ) * SB_WARPS_PER_CTA || nlists % SB_WARPS_PER_CTA) return -3;
         grid = nlists / SB_WARPS_PER_CTA;
         SB_CUDA_CHECK(cudaMemsetAsync(dflags, 0, sizeof(int) * nk, st));
     }
@@ -1330,6 +1337,14 @@ int sbm_resident_warps(void) {
     SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
     SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<false>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
+    return nsm * occ * SB_WARPS_PER_CTA;
+}
+int sbm_resident_warps_batch(void) {
+    int dev, nsm, occ;
+    SB_CUDA_CHECK(cudaGetDevice(&dev));
+    SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<true>, SB_WARP * SB_WARPS_PER_CTA, SB_SM_BYTES));
     return nsm * occ * SB_WARPS_PER_CTA;
 }
 
