@@ -373,6 +373,12 @@ struct SbSolveArgs {
 #endif
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
+#ifndef SB_GJ_REDUX
+#define SB_GJ_REDUX 1
+#endif
+#ifndef SB_GJ_INPLACE
+#define SB_GJ_INPLACE 1
+#endif
 #ifndef SB_Z3
 #define SB_Z3 1
 #endif
@@ -674,6 +680,51 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
             if (i >= nb) { di[S.tv] = 1.0 / dj; up[S.tv] = 0; }
         }
+#if SB_GJ_INPLACE
+        // In-place Gauss-Jordan: the column of the pivot is overwritten by the corresponding column of the inverse, so only the
+        // SB_TOPMAX entries of the pivot row travel per step (the augmented form [A | I] moves twice as many).  Rows are not
+        // exchanged: lane `who` simply acts as row kx, which leaves the inverse with its columns in pivot order -- column kx of the
+        // register row is column p_kx (= who of step kx) of the inverse; the scatter at the end undoes that.
+        double Ar[SB_TOPMAX];
+#pragma unroll
+        for (int j = 0; j < SB_TOPMAX; j++) Ar[j] = (i == j) ? ((i < nb) ? dj : 1.0) : ((i < nb && j < nb) ? blk[off + i * nb + j] : 0.0);
+        int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
+        unsigned perm = 0; // who of every step, 3 bits each
+        const int base = lane & ~7;
+#pragma unroll
+        for (int kx = 0; kx < SB_TOPMAX; kx++) {
+#if SB_GJ_REDUX && SB_NTOP == 1
+            // one top block (lanes 0..4): a single full-warp REDUX on the high word of |a| (exponent + 16 mantissa bits; the lower
+            // row wins a tie; candidates that agree to 1.5e-5 relative are equally good pivots).  (A REDUX per 8-lane group, which
+            // several blocks would need, measured slower than the shuffle search below.)
+            unsigned key = 0;
+            if (myrow < 0 && i < SB_TOPMAX && bb == 0) key = (((unsigned)__double2hiint(Ar[kx]) & 0x7FFFFFF0u)) | (unsigned)(8 - i);
+            const int who = 8 - (int)(__reduce_max_sync(SB_FULL, key) & 15u);
+#else
+            double best = (myrow < 0 && i < SB_TOPMAX) ? fabs(Ar[kx]) : -1.0; int who = i;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
+#endif
+            const bool isp = (i == who);
+            if (isp) myrow = kx;
+            perm |= (unsigned)who << (3 * kx);
+            const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
+            const double inv = 1.0 / piv;
+            const double l = isp ? 0.0 : Ar[kx];
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) {
+                if (j == kx) continue;
+                const double pa = __shfl_sync(SB_FULL, Ar[j], base + who) * inv;
+                if (isp) Ar[j] = pa; else Ar[j] -= l * pa;
+            }
+            Ar[kx] = isp ? inv : -l * inv;
+        }
+        if (bb < SB_NTOP && myrow >= 0 && myrow < nb) {
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) { const int pj = (perm >> (3 * j)) & 7; if (pj < nb) blk[off + myrow * nb + pj] = Ar[j]; }
+        }
+    }
+#else
         double Ar[SB_TOPMAX], Ir[SB_TOPMAX];
 #pragma unroll
         for (int j = 0; j < SB_TOPMAX; j++) {
@@ -703,6 +754,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             for (int j = 0; j < SB_TOPMAX; j++) if (j < nb) blk[off + myrow * nb + j] = Ir[j];
         }
     }
+#endif
     __syncwarp();
 }
 
