@@ -373,6 +373,9 @@ struct SbSolveArgs {
 #endif
 #define SB_SM_BYTES (SB_SM_BYTES_WARP * SB_WARPS_PER_CTA)
 #define SB_NBR ((SB_NB + 31) / 32)
+#ifndef SB_TOPFAST
+#define SB_TOPFAST 1
+#endif
 #ifndef SB_GJ_REDUX
 #define SB_GJ_REDUX 1
 #endif
@@ -432,6 +435,7 @@ struct SbLane {
     unsigned ph[SB_PR], pk[SB_PR]; // owned phase-0 elimination paths (contiguous index ranges): start|len<<8|parent<<16, first-vertex children
     unsigned rh[SB_TR + 1], rk[SB_TR + 1]; // owned multi-vertex root paths (the part of the top that is neither in a block nor a single vertex)
     unsigned tv, dk;           // top vertex owned by this lane (block member: lane = block*8+row, or single root) and its forest children
+    unsigned dkz;              // dk with absent children replaced by a top-block vertex (its multiplier mm is always 0): unconditional gathers
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
     __device__ __forceinline__ void load(int lane) {
 #pragma unroll
@@ -447,6 +451,12 @@ struct SbLane {
 #pragma unroll
         for (int q = 0; q < SB_TR; q++) { rh[q] = sb_root_head[q * 32 + lane]; rk[q] = sb_root_kids[q * 32 + lane]; }
         dk = sb_top_kids[lane]; tv = sb_top_vert[lane];
+        {
+            const unsigned z = sb_top_vert[0];
+            dkz = 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const unsigned kid = (unsigned)SB_KID(dk, c); dkz |= (kid == SB_NOKID ? z : kid) << (SB_IDXBITS == 8 ? 8 * c : 10 * c); }
+        }
 #pragma unroll
         for (int r = 0; r < SB_NBR; r++) { int m = r * 32 + lane; bp[r] = (m < SB_NB) ? sb_basis_pack[m] : 0u; }
     }
@@ -834,6 +844,38 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             }
         }
     }
+#if SB_TOPFAST && SB_NTOP == 1
+    { // top vertices, one top block of SB_TOPMAX rows on lanes 0..SB_TOPMAX-1 and single roots on the lanes after the block group.
+      // No predicated loads (four instructions each): absent children point at a top-block vertex, whose multiplier mm is always 0;
+      // the block row and the single-root pivot are loaded by every top lane and the unused one is dropped by a select.
+        const int i = lane & 7, base = lane & ~7;
+        const bool mine = S.tv != SB_NOKID, inblk = lane < SB_TOPMAX;
+        double g[NR], brow[SB_TOPMAX];
+#pragma unroll
+        for (int a = 0; a < NR; a++) g[a] = 0;
+        double dtv = 0;
+        if (mine) {
+            dtv = di[S.tv];
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) brow[j] = blk[i * SB_TOPMAX + j]; // single roots: values of the neighbouring array, dropped below
+#pragma unroll
+            for (int a = 0; a < NR; a++) {
+                double ga = rr[a][S.tv];
+#pragma unroll
+                for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dkz, c); ga = fma(-mm[ch], rr[a][ch], ga); }
+                g[a] = ga;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+            double xm = 0;
+#pragma unroll
+            for (int j = 0; j < SB_TOPMAX; j++) xm = fma(brow[j], __shfl_sync(SB_FULL, g[a], base + j), xm);
+            const double xi = inblk ? xm : g[a] * dtv; // single root: forward and backward substitution are one division by the pivot
+            if (mine) rr[a][S.tv] = xi;
+        }
+    }
+#else
     { // top vertices: block members (lane = block*8 + row) and single roots gather their children's terms in one pass
         const int bb = lane >> 3, i = lane & 7, base = lane & ~7;
         int nb = 0, off = 0;
@@ -862,6 +904,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
             if (mine) rr[a][S.tv] = xi;
         }
     }
+#endif
     __syncwarp();
 #pragma unroll
     for (int rd = 0; rd < SB_PR; rd++) {
