@@ -21,11 +21,31 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the B200 path cannot be built (there is no CPU fallback)")
 
 
+def _digest(sources):
+    import hashlib
+    h = hashlib.sha1()
+    for s in sources:
+        with open(s, "rb") as f:
+            h.update(hashlib.sha1(f.read()).digest())
+    return h.hexdigest()
+
+
 def _newer(target, sources):
+    """Is `target` an up-to-date build of `sources`?  Decided by a content hash stamped next to the target (file times do not
+    survive every way a tree gets copied to a GPU box; a needless rebuild there costs minutes of GPU time), with the
+    modification times as the fallback for targets built before the stamps existed."""
     if not os.path.exists(target):
         return False
+    stamp = target + ".stamp"
+    if os.path.exists(stamp):
+        return open(stamp).read().strip() == _digest(sources)
     t = os.path.getmtime(target)
     return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _stamp(target, sources):
+    with open(target + ".stamp", "w") as f:
+        f.write(_digest(sources))
 
 
 def model_key(lmax, nx, w0wa):
@@ -52,10 +72,12 @@ def build_model(lmax=10, nx=4, w0wa=False, force=False, verbose=False):
         with open(hdr, "w") as f:
             f.write(text)
         json.dump(info, open(meta, "w"))
+        _stamp(hdr, gen_srcs)
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", d, "-I", CSRC, "-o", so, c_srcs[0], c_srcs[1]]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    _stamp(so, gen_srcs + c_srcs)
     return so, json.load(open(meta))
 
 
@@ -69,6 +91,7 @@ def build_los(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    _stamp(so, [src])
     return so
 
 
