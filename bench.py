@@ -25,7 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-NCU_DRAM_BYTES_PER_LAUNCH = 17267456 + 344568576  # ncu --set full capture of the statically scheduled sb_integrate_kernel launch at the bench size (profiles/integrate_r1.md, r1k)
+NCU_DRAM_BYTES_PER_LAUNCH = 18081792 + 345558528  # ncu --set full capture of the statically scheduled sb_integrate_kernel launch at the bench size (profiles/integrate_r1.md, r1o)
 FP64_PEAK_TFLOPS = 33.84  # measured on this pool's B200 with scripts/fp64_peak.cu (profiles/fp64_peak_r1.txt); MEASURED_PEAKS.json has no FP64 figure
 
 
@@ -214,7 +214,7 @@ def main():
                "e2e": {"value": e2e, "unit": "k-modes/s", "h2d_bytes_per_step": plan.h2d_bytes, "d2h_bytes_per_step": plan.d2h_bytes},
                "gpu_launches": plan.launches_resident * args.steps,
                "roofline": {"kernel": "sb_integrate_kernel", "bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/integrate_r1.md, r1k): 17.3 MB read + 344.6 MB written = the saved states usave[2019][300][82] f64 (397 MB algorithmic)",
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/integrate_r1.md, r1o): 18.1 MB read + 345.6 MB written = the saved states usave[2019][300][82] f64 (397 MB algorithmic)",
                             "peak_source": "measured DFMA peak, scripts/fp64_peak.cu (FP64 kernel: neither HBM nor tensor bound; MEASURED_PEAKS.json has no FP64 entry)",
                             "kernel_ms": 1e3 * float(t_kernel.mean()), "algorithmic_flops_per_launch": flops,
                             "attempted_steps_per_launch": float(stats[:, 0].sum() + stats[:, 1].sum())},
