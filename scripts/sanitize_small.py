@@ -1,0 +1,23 @@
+"""Tiny workload for compute-sanitizer (memcheck / racecheck): a few modes through the integrator (queue, static schedule and batched launch),
+the source kernels and the LOS/C_l kernels."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import symboltz.jl_b200 as sb
+for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10)):
+    prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+    bg = sb.solvebg(prob)
+    ks = np.array([0.5, 20.0, 300.0, 1500.0])
+    P = sb.spectrum_matter(prob, ks, bgsol=bg)
+    cost = sb.ModeCostModel(ks, np.array([300.0, 500.0, 1200.0, 2500.0]), nknots=3) if hasattr(sb, "ModeCostModel") else None
+    f = lambda k: min(1e-2 / k, 1e-4)
+    s1 = sb.solvept(prob, bg, ks, ptivini=f)
+    s2 = sb.solvept(prob, bg, ks, ptivini=f, cost=np.array([300.0, 500.0, 1200.0, 2500.0]))
+    b = sb.solvept_batch([bg, bg], ks, ptivini=f)
+    torch.cuda.synchronize()
+    print(M, "P(k)", P, "sched == queue", np.array_equal(s1.uend, s2.uend), "batch == queue", np.array_equal(b.sols[1].uend, s1.uend))
+ls = np.array([10, 100, 1000])
+jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * bg.tau0)
+print(sb.spectrum_cmb(["TT", "EE"], prob, jl, bgsol=bg)[:, 0])
+d = sb.solvebg_batch([prob, prob])
+print("device bg tau0", d[0].tau0, bg.tau0)
