@@ -48,6 +48,9 @@ def _stamp(target, sources):
         f.write(_digest(sources))
 
 
+_FRESH = {}
+
+
 def model_key(lmax, nx, w0wa):
     return f"l{lmax}_x{nx}_{'w0wa' if w0wa else 'lcdm'}"
 
@@ -55,6 +58,8 @@ def model_key(lmax, nx, w0wa):
 def build_model(lmax=10, nx=4, w0wa=False, force=False, verbose=False):
     """Generate + compile the per-model engine. Returns (path to .so, info dict)."""
     key = model_key(lmax, nx, w0wa)
+    if not force and key in _FRESH:  # checked once per process: parameter sweeps construct thousands of problems of one model
+        return _FRESH[key]
     d = os.path.join(BUILD_DIR, key)
     so = os.path.join(d, f"libsbm_{key}.so")
     hdr = os.path.join(d, "sb_model_gen.h")
@@ -62,7 +67,8 @@ def build_model(lmax=10, nx=4, w0wa=False, force=False, verbose=False):
     gen_srcs = [os.path.join(_HERE, "codegen", f) for f in ("model.py", "lower.py")]
     c_srcs = [os.path.join(CSRC, f) for f in ("sb_engine.cu", "sb_debug.cpp", "sb_rodas.h")]
     if not force and _newer(so, gen_srcs + c_srcs) and os.path.exists(meta):
-        return so, json.load(open(meta))
+        _FRESH[key] = (so, json.load(open(meta)))
+        return _FRESH[key]
     os.makedirs(d, exist_ok=True)
     if force or not (_newer(hdr, gen_srcs) and os.path.exists(meta)):
         from .codegen.model import Model
@@ -78,7 +84,8 @@ def build_model(lmax=10, nx=4, w0wa=False, force=False, verbose=False):
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     _stamp(so, gen_srcs + c_srcs)
-    return so, json.load(open(meta))
+    _FRESH[key] = (so, json.load(open(meta)))
+    return _FRESH[key]
 
 
 def build_los(force=False, verbose=False):
