@@ -111,3 +111,19 @@ def build_all(force=False, verbose=False):
     for m in DEFAULT_MODELS:
         out.append(build_model(force=force, verbose=verbose, **m)[0])
     return out
+
+
+if __name__ == "__main__":  # python -m symboltz.jl_b200.build [--lmax 10 --nx 4 --w0wa] : what a non-Python host runs at CosmologyProblem time
+    import argparse
+    ap = argparse.ArgumentParser(description="generate + compile the per-model engine (cached); prints the path of the shared library")
+    ap.add_argument("--lmax", type=int, default=10)
+    ap.add_argument("--nx", type=int, default=4)
+    ap.add_argument("--w0wa", action="store_true")
+    ap.add_argument("--all", action="store_true", help="build the default model set and the line-of-sight library")
+    ap.add_argument("--force", action="store_true")
+    a = ap.parse_args()
+    if a.all:
+        print("\n".join(build_all(force=a.force, verbose=True)))
+    else:
+        print(build_model(a.lmax, a.nx, a.w0wa, force=a.force, verbose=True)[0])
+        print(build_los(force=a.force))

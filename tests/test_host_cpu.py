@@ -296,3 +296,23 @@ def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
                 ends.append(((start + ln - 1) % 16, ln))
         weight = sum(min(a[1], b[1]) for i, a in enumerate(ends) for b in ends[:i] if a[0] == b[0])
         assert weight <= 6, (M, weight, ends)
+
+
+def test_build_cli_and_freshness_stamps(sb, prob5, tmp_path):
+    """`python -m symboltz.jl_b200.build` (what a non-Python host runs at CosmologyProblem time) prints the cached
+    library; freshness is decided by a content hash of the sources, not by file times."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-m", "symboltz.jl_b200.build", "--lmax", "5"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    so = out.stdout.strip().splitlines()[0]
+    assert os.path.exists(so) and so.endswith("libsbm_l5_x4_lcdm.so") and os.path.exists(so + ".stamp")
+    src = tmp_path / "a.txt"
+    tgt = tmp_path / "a.out"
+    src.write_text("one")
+    tgt.write_text("built")
+    sb.build._stamp(str(tgt), [str(src)])
+    os.utime(src, None)  # newer file time, same content: still fresh
+    assert sb.build._newer(str(tgt), [str(src)])
+    src.write_text("two")
+    assert not sb.build._newer(str(tgt), [str(src)])
