@@ -36,6 +36,16 @@ def _worker(rank, world, port, out):
     dist.all_reduce(part)
     ref = np.einsum("k,lk,lk->l", ck, theta[0], theta[1])
     assert np.allclose(part.numpy(), ref, rtol=1e-13)
+    # cosmology sharding of a parameter sweep (config 4): strided ownership, exact gather of the per-rank P(k) rows, NaN rows kept
+    n = 11
+    mine = sb.shard_rows(n, rank, world)
+    assert np.array_equal(mine, np.arange(rank, n, world))
+    P_all = rng.standard_normal((n, 5))
+    P_all[3] = np.nan  # a cosmology whose background failed
+    got = sb.gather_rows(P_all[mine], mine, n)
+    assert np.array_equal(got, P_all, equal_nan=True)
+    cnt = sb.gather_rows(np.array([[rank + 1.0, 10.0 * (rank + 1)]]), [rank], world).sum(axis=0)
+    assert cnt.tolist() == [3.0, 30.0]
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
