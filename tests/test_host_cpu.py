@@ -271,9 +271,10 @@ def test_build_schedule_covers_every_mode_once_and_balances():
 def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
     """The integrator's relabelled state order (codegen/lower.py): sb_nat is a permutation of the natural order, every elimination path is a
     contiguous index range inside [0, N), paths do not overlap, and the bank-aware tie-break leaves at most a handful of (path, path)
-    pairs whose ends are congruent modulo 16 doubles (each such pair costs one extra shared-memory wavefront per access)."""
+    pairs of the same half-warp whose ends are congruent modulo 16 doubles (each such pair costs one extra shared-memory wavefront per
+    access).  With more paths than residues (nx = 8) or path lengths that are multiples of 16 (lmax = 32) collisions remain; only the layout is checked there."""
     import re
-    for M in (sb.ΛCDM(lmax=10), sb.w0waCDM(lmax=10), sb.ΛCDM(lmax=5)):
+    for M in (sb.ΛCDM(lmax=10), sb.w0waCDM(lmax=10), sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10, nx=8), sb.ΛCDM(lmax=32)):
         prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
         so, info = sb.build.build_model(M.lmax, M.nx, M.w0wa)
         text = open(os.path.join(os.path.dirname(so), "sb_model_gen.h")).read()
@@ -287,15 +288,16 @@ def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
         bits8 = "#define SB_IDXBITS 8" in text
         heads = arr("sb_path_head")
         covered, ends = set(), []
-        for v in heads:
+        for slot, v in enumerate(heads):
             start, ln = (v & 255, (v >> 8) & 255) if bits8 else (v & 4095, (v >> 12) & 255)
             if ln:
                 rng_ = set(range(start, start + ln))
                 assert start + ln <= N and not (rng_ & covered)
                 covered |= rng_
-                ends.append(((start + ln - 1) % 16, ln))
-        weight = sum(min(a[1], b[1]) for i, a in enumerate(ends) for b in ends[:i] if a[0] == b[0])
-        assert weight <= 6, (M, weight, ends)
+                ends.append(((slot % 32) // 16, (start + ln - 1) % 16, ln))  # 64-bit accesses are served per half-warp
+        weight = sum(min(a[2], b[2]) for i, a in enumerate(ends) for b in ends[:i] if a[:2] == b[:2])
+        if M.lmax <= 10 and M.nx == 4:  # the models of BASELINE configs 1, 2 and 4 (16-17 paths: they can be kept apart)
+            assert weight <= 6, (M, weight, ends)
 
 
 def test_build_cli_and_freshness_stamps(sb, prob5, tmp_path):
