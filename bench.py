@@ -169,19 +169,22 @@ def main():
     sampler.start()
     time.sleep(0.3)  # let the first nvidia-smi query get in flight; all samples are taken while the timed steps run
     # ---- device-resident timing: CUDA events per step on the launching stream, L2 flushed between steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(args.steps)]
     barrier()
-    for a, b, c in ev:
+    for a, b, c, d in ev:
         flush.fill_(1.0)
         a.record()
         plan.solve()
         b.record()
         plan.sources()
+        d.record()
         plan.los_cl()
         c.record()
     barrier()
-    t_step = np.array([a.elapsed_time(c) for a, b, c in ev]) * 1e-3
-    t_kernel = np.array([a.elapsed_time(b) for a, b, c in ev]) * 1e-3
+    t_step = np.array([a.elapsed_time(c) for a, b, c, d in ev]) * 1e-3
+    t_kernel = np.array([a.elapsed_time(b) for a, b, c, d in ev]) * 1e-3
+    t_src = np.array([b.elapsed_time(d) for a, b, c, d in ev]) * 1e-3
+    t_los = np.array([d.elapsed_time(c) for a, b, c, d in ev]) * 1e-3
     stats = plan.d_stats.cpu().numpy()
     ok = bool((plan.d_ret.cpu().numpy() == 0).all())
     # ---- end-to-end timing through the public plan API: pinned host -> device, all kernels, C_l back on the host
@@ -205,6 +208,16 @@ def main():
     e2e = world * nmodes * args.steps / T_e2e
     if rank == 0:
         flops = step_flops(prob, stats, plan.nk * plan.nt)
+        src_bytes = float(plan.nk * plan.nt * (prob.N + 2) * 8)
+        hbm_peak, hbm_src = 6452.8, "fallback: SURVEY 8d figure"
+        try:
+            mp_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            cand = [v for k, v in mp_.items() if isinstance(v, (int, float)) and "hbm" in k.lower() and "sustain" in k.lower()] or \
+                   [v for k, v in mp_.items() if isinstance(v, (int, float)) and "hbm" in k.lower()]
+            if cand:
+                hbm_peak, hbm_src = float(cand[0]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
         achieved = flops / float(t_kernel.mean()) / 1e12
         out = {"metric": "k-modes/s (LCDM perturbations -> C_l TT/EE/TE, l<=2500)", "value": value, "unit": "k-modes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * T_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -218,6 +231,12 @@ def main():
                             "peak_source": "measured DFMA peak, scripts/fp64_peak.cu (FP64 kernel: neither HBM nor tensor bound; MEASURED_PEAKS.json has no FP64 entry)",
                             "kernel_ms": 1e3 * float(t_kernel.mean()), "algorithmic_flops_per_launch": flops,
                             "attempted_steps_per_launch": float(stats[:, 0].sum() + stats[:, 1].sum())},
+               # the S(tau,k) stage (north star: achieved HBM GB/s of the source traffic): sb_srcbg_kernel + sb_source_kernel read the saved
+               # states usave[nk][nt][N] once and write S[nk][2][nt]; algorithmic bytes per step over the event time of the two launches
+               "roofline_sources": {"kernel": "sb_srcbg_kernel + sb_source_kernel", "bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_source": hbm_src,
+                                    "algorithmic_bytes_per_step": src_bytes, "kernel_ms": 1e3 * float(t_src.mean()), "achieved": src_bytes / float(t_src.mean()) / 1e9,
+                                    "frac": src_bytes / float(t_src.mean()) / 1e9 / hbm_peak},
+               "los_cl_ms": 1e3 * float(t_los.mean()),
                "clocks": sampler.summary()}
         # CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on the host cores
         if world == 1:
