@@ -160,10 +160,16 @@ int sbl_cl(int nl, int nk, int k0, int k1, const double* dck, const double* dThe
  * src/observables/fourier.jl:232-247) */
 int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, double* dSf, void* stream);
 
+/* FP64 roofline denominator measured on the device the library runs on: independent DFMA chains on every SM, best of `reps`
+ * launches of `iters` iterations, result in TFLOP/s through *tflops (host pointer).  Blocking.  (no reference counterpart:
+ * measurement support for bench.py's `roofline`, SURVEY 8d "denominator = measured DFMA peak") */
+int sbl_dfma_peak(int iters, int reps, double* tflops, void* stream);
+
 /* One-call HOST-buffer variant of k-interpolation + line of sight + C_l: builds the j_l table on the reference's grid
  * (range(0, xmax, length = trunc(xmax/dx)), tabulated up to xcut), uploads ks[nk], Bw[nk][nc] (NULL: Sc is already on the fine
  * grid), Sc[nc or nk][nS][nt], chi[nt], wt[nt], ls[nl], ck[nk], the mode pairs, runs sbl_los + sbl_cl and downloads
- * Cl[nmodes][nl] and, if Theta != NULL, Theta[nS][nl][nk].  Blocking.
+ * Cl[nmodes][nl] and, if Theta != NULL, Theta[nS][nl][nk].  Blocking.  Returns -4 if the table (cut at xcut) does not reach
+ * max(ks)·max(chi) (the reference asserts jl.x[end] >= kmax·τmax, src/observables/angular.jl:110-116).
  * (replaces the body of spectrum_cmb(modes, prob, jl, ls), src/observables/angular.jl:293-340, after source_grid) */
 int sbl_cmb_host(int nk, const double* ks, int nc, const double* Bw, const double* Sc, int nS, int nt, const double* chi, const double* wt, int nl, const int* ls, double dx,
                  double xmax, double xcut, const double* ck, int nmodes, const int* modeA, const int* modeB, int l_limber, double* Cl, double* Theta);

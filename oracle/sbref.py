@@ -258,9 +258,22 @@ def chebyshev_interp_matrix(ys_coarse, ys_fine):
 class SphericalBesselCache:
     """src/observables/angular.jl:9-48 (uniform-x table of j_l and j_l', cubic Hermite evaluation)."""
 
-    def __init__(self, ls, xmax=None, dx=2 * np.pi / 15, xcut=None):
-        """xcut: only tabulate x <= xcut (same grid points as the full table; saves memory, angular.jl:18-25)."""
-        from scipy.special import spherical_jn
+    def __init__(self, ls, xmax=None, dx=2 * np.pi / 15, xcut=None, nthreads=None):
+        """xcut: only tabulate x <= xcut (same grid points as the full table; saves memory, angular.jl:18-25).
+        nthreads: the scipy ufunc releases the GIL, so the table is filled by a thread pool over blocks of x (default: all cores)."""
+        from scipy.special import spherical_jn as _sj
+        import concurrent.futures as cf
+        import os
+        nthreads = nthreads or len(os.sched_getaffinity(0))
+
+        def spherical_jn(l, x):  # l: [nl, 1], x: [1, nx] -> [nl, nx], blocks of x in parallel
+            xs_ = x[0]
+            if nthreads <= 1 or len(xs_) < 4096:
+                return _sj(l, x)
+            cuts = np.linspace(0, len(xs_), 4 * nthreads + 1).astype(int)
+            with cf.ThreadPoolExecutor(nthreads) as pool:
+                parts = list(pool.map(lambda ab: _sj(l, xs_[None, ab[0]:ab[1]]), zip(cuts[:-1], cuts[1:])))
+            return np.concatenate(parts, axis=1)
         self.l = np.asarray(ls)
         xmax = 20 * self.l[-1] if xmax is None else xmax
         n = int(xmax / dx)
@@ -382,16 +395,26 @@ def spectrum_cmb_from_theta(ThA, ThB, P0s, ls, ks, normalization="Cl"):
     return Cl
 
 
-def spectrum_cmb(modes, bg, jl, normalization="Cl", kmin=1e-2, kmax=2e3, order=60, dkt0=np.pi, ntau=300, taucut=1e-2,
-                 direct=False, reltol=1e-5, abstol=1e-5, nthreads=0, return_all=False):
-    """Mirror of spectrum_cmb(modes, prob, jl) for T/E modes (src/observables/angular.jl:260-341).
-    direct=True solves every fine k instead of interpolating from the Chebyshev nodes."""
-    ls = np.asarray(jl.l)
-    tau0 = bg.tau0
-    ks_fine = lingrid(kmin, kmax, step=dkt0 / tau0)
+def cmb_grids(bg, kmin=1e-2, kmax=2e3, dkt0=np.pi, ntau=300, taucut=1e-2):
+    """Fine k-grid and τ-grid of spectrum_cmb (src/observables/angular.jl:275-290)."""
+    ks_fine = lingrid(kmin, kmax, step=dkt0 / bg.tau0)
     ts = bg.t[bg.t >= taucut]
     taus = ts[0] + (ts[-1] - ts[0]) * cosgrid(0.0, 1.0, length=ntau)
     taus[-1] = ts[-1]
+    return ks_fine, taus
+
+
+def spectrum_cmb(modes, bg, jl, normalization="Cl", kmin=1e-2, kmax=2e3, order=60, dkt0=np.pi, ntau=300, taucut=1e-2,
+                 direct=False, reltol=1e-5, abstol=1e-5, nthreads=0, return_all=False, ks=None):
+    """Mirror of spectrum_cmb(modes, prob, jl) for T/E modes (src/observables/angular.jl:260-341).
+    direct=True solves every fine k instead of interpolating from the Chebyshev nodes.
+    ks: solve exactly these (ascending) wavenumbers directly and use them as the k-quadrature grid (bounded samples of the
+    direct workload for the CPU baseline timing in bench.py)."""
+    ls = np.asarray(jl.l)
+    tau0 = bg.tau0
+    ks_fine, taus = cmb_grids(bg, kmin, kmax, dkt0, ntau, taucut)
+    if ks is not None:
+        ks_fine, direct = np.ascontiguousarray(ks, dtype=float), True
     ks_coarse = ks_fine if direct else chebpoints(order, kmin, kmax)
     sol = solvept(bg, ks_coarse, ptivini=-np.inf, saveat=taus, reltol=reltol, abstol=abstol, nthreads=nthreads)
     S = sources(bg, ks_coarse, taus, sol["usave"])  # [nk, nτ, 6]

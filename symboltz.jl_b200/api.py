@@ -319,15 +319,18 @@ def solvebg_batch(probs, reltol=1e-7, abstol=1e-7, cap=4096, warn=True):
         raise RuntimeError(f"sbm_solvebg_batch failed with code {rc}")
     nb = dnb.cpu().numpy()
     info = dinfo.cpu().numpy()
-    if (nb <= 0).any():
-        bad = np.nonzero(nb <= 0)[0]
-        raise RuntimeError(f"background solve produced no knots (or more than cap = {cap}) for cosmologies {bad[:8].tolist()}")
-    m = int(nb.max())
+    m = max(int(nb.max()), 2)
     t, y, d = dt[:, :m].cpu().numpy(), dy[:, :m].cpu().numpy(), ddy[:, :m].cpu().numpy()  # one strided copy each, only the used part
     sols = []
     for i, p in enumerate(probs):
         k = int(nb[i])
-        sol = BackgroundSolution(p, t[i, :k].copy(), y[i, :k].copy(), d[i, :k].copy(), info[i])
+        if k <= 0:  # no knots, or more than `cap`: a failed solution (retcode MaxIters) like the host path reports, not an exception for the whole batch
+            inf = info[i].copy()
+            inf[3] = inf[3] if inf[3] != 0 else 1
+            k = 2
+            sol = BackgroundSolution(p, np.array([p.ivspan[0], p.ivspan[1]]), np.full((2, 5), np.nan), np.full((2, 5), np.nan), inf)
+        else:
+            sol = BackgroundSolution(p, t[i, :k].copy(), y[i, :k].copy(), d[i, :k].copy(), info[i])
         if warn and not sol.success:
             warnings.warn(f"Background solution {i} failed with return code {RETCODES.get(sol.retcode)}.\nCheck the parameters and precision settings!")
         sols.append(sol)
@@ -582,12 +585,14 @@ class BatchSolution:
         return bool((self.d_retcode == 0).all().item())
 
 
-def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, cost=None, arena=None):
+def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, cost=None, arena=None, max_lists=None):
     """Perturbation solve of several cosmologies (same model structure) in ONE integrator launch over all (cosmology, mode)
     pairs, ordered by descending k across cosmologies (SURVEY §8b batched variant; the reference runs one `solvept` per
     cosmology, docs/src/forecasting.md:56-59).  bgsols: BackgroundSolutions; ks: one array for all, or one array per cosmology;
     saveat: None, or one array of save times per cosmology (equal lengths).  Per-mode results are bit-identical to `solvept` on that
-    cosmology.  cost: optional vectorised callable ks -> estimated attempts, switches to the static preemptive schedule."""
+    cosmology.  cost: optional vectorised callable ks -> estimated attempts, switches to the static preemptive schedule; every list of
+    a static schedule must be resident from the start of the launch, so callers that keep several scheduled launches in flight
+    (the sweep's stream slots) pass max_lists = resident warps / launches in flight."""
     _require_cuda()
     nc = len(bgsols)
     prob = bgsols[0].prob
@@ -632,7 +637,8 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
     nlists = 0
     if cost is not None and nk > 0:
         wpc = int(prob.lib.sbm_warps_per_cta())
-        nlists = max(wpc, min(resident_warps(prob, batch=True), nk) // wpc * wpc)
+        nres = resident_warps(prob, batch=True)
+        nlists = max(wpc, min(nres if max_lists is None else min(nres, int(max_lists)), nk) // wpc * wpc)
         items, ibeg, _ = build_schedule(np.nan_to_num(np.asarray(cost(kall) if callable(cost) else cost, dtype=np.float64) * np.ones(nk), nan=1.0), nlists)
         ditems, dibeg = _h2d(items, dev), _h2d(ibeg, dev)
         dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
@@ -1101,8 +1107,9 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
 class CMBPlan:
     """Preallocated, allocation-free execution plan for the C_l hot path of one cosmology:
     (H2D knots) -> β-table -> perturbation solve (saveat) -> sources -> [k-interp +] LOS -> C_l -> (D2H C_l).
-    Used by bench.py for the device-resident number (`run`) and the end-to-end number (`run_e2e`), and handy for sweeps:
-    every launch goes to torch's current stream, so a sequence of plans can be captured in a CUDA graph."""
+    Used by bench.py for the device-resident number (`run`) and the end-to-end number (`run_e2e`).  `stage(bg)` re-targets the plan
+    at another cosmology with the same grid sizes (knots, fine k, times) -- it restages every cosmology-dependent array, not only
+    the knots; `upload()` must run once before the first `run()`.  Every launch goes to torch's current stream."""
 
     def __init__(self, prob, bg, jl, modes=("TT", "EE", "TE"), direct=True, kinterp=None, dkt0=math.pi, ntau=300, taucut=1e-2,
                  reltol=1e-5, abstol=1e-5, maxiters=100000, msub=16, normalization="Cl"):
@@ -1112,23 +1119,31 @@ class CMBPlan:
         self.kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
         dev = torch.device("cuda")
         self.dev = dev
-        self.ks_fine, self.taus = cmb_grids(bg, self.kinterp.minimum(), self.kinterp.maximum(), dkt0, ntau, taucut)
-        self.ks_solve = self.ks_fine if direct else self.kinterp.xs
-        nk, nkf, nt, N, nl = len(self.ks_solve), len(self.ks_fine), len(self.taus), prob.N, len(jl.l)
+        self._grid_opts = (dkt0, ntau, taucut)
+        ks_fine, taus = cmb_grids(bg, self.kinterp.minimum(), self.kinterp.maximum(), dkt0, ntau, taucut)
+        nkf, nt, N, nl = len(ks_fine), len(taus), prob.N, len(jl.l)
+        nk = nkf if direct else len(self.kinterp.xs)
         self.nk, self.nkf, self.nt, self.nl = nk, nkf, nt, nl
         self.nb = len(bg.t)
-        # pinned host staging for the per-cosmology inputs: knots (t, y, dy) and parameters
-        self.h_in = torch.empty(self.nb * 11 + prob.npar, dtype=torch.float64).pin_memory()
+        # pinned host staging for the per-cosmology inputs: knots (t, y, dy), parameters, and the grids that move with the cosmology
+        # (fine k: step π/τ0; saved times and χ = τ0 − τ; trapezoid weights; C_l k-weights incl. P0; start times; interval look-up)
+        self.nlut = 4096
+        self._seg = dict(t=self.nb, y=5 * self.nb, dy=5 * self.nb, P=prob.npar, ks=nk, tini=nk, ksf=nkf, taus=nt, chi=nt, wt=nt, ck=nkf)
+        self._off, o = {}, 0
+        for name, n in self._seg.items():
+            self._off[name] = (o, o + n)
+            o += n
+        self.h_in = torch.empty(o, dtype=torch.float64).pin_memory()
         self.d_in = torch.empty_like(self.h_in, device=dev)
+        self.h_lut = torch.empty(self.nlut, dtype=torch.int32).pin_memory()
+        self.d_lut = torch.empty(self.nlut, dtype=torch.int32, device=dev)
+        dv = lambda name: self.d_in[self._off[name][0]:self._off[name][1]]
+        self.d_ks, self.d_tini, self.d_ksf, self.d_taus, self.d_chi, self.d_wt, self.d_ck = dv("ks"), dv("tini"), dv("ksf"), dv("taus"), dv("chi"), dv("wt"), dv("ck")
+        self.d_Bw = None if direct else torch.empty((nkf, nk), dtype=torch.float64, device=dev)
         self.stage(bg)
-        tini = np.full(nk, bg.t[0])
-        order = np.argsort(-self.ks_solve, kind="stable").astype(np.int32)
+        order = np.argsort(-self.ks_solve, kind="stable").astype(np.int32)  # ascending grids of fixed length: the order does not depend on the cosmology
         f64 = dict(dtype=torch.float64, device=dev)
-        self.d_ks, self.d_tini, self.d_order = torch.from_numpy(self.ks_solve.copy()).to(dev), torch.from_numpy(tini).to(dev), torch.from_numpy(order).to(dev)
-        self.d_ksf = torch.from_numpy(self.ks_fine).to(dev)
-        self.d_taus = torch.from_numpy(self.taus).to(dev)
-        self.d_chi = torch.from_numpy(self.taus[-1] - self.taus).to(dev)
-        self.d_wt = torch.from_numpy(_trapz_weights(self.taus)).to(dev)
+        self.d_order = torch.from_numpy(order).to(dev)
         self.d_usave = torch.empty((nk, nt, N), **f64)
         self.d_uend = torch.empty((nk, N), **f64)
         self.d_ret = torch.empty(nk, dtype=torch.int32, device=dev)
@@ -1137,21 +1152,15 @@ class CMBPlan:
         self.d_S = torch.empty((nk, 2, nt), **f64)
         self.d_srcbg = torch.empty(nt * prob.lib.sbm_srcbg_stride(), **f64)
         self.d_theta = torch.zeros((2, nl, nkf), **f64)
-        self.d_Bw = None if direct else torch.from_numpy(self.kinterp.matrix(self.ks_fine)).to(dev)
-        w = natural_spline_weights(np.concatenate([[0.0], self.ks_fine]))[1:]
-        self.d_ck = torch.from_numpy(w * (2 / math.pi) * self.ks_fine**2 * spectrum_primordial(self.ks_fine, prob)).to(dev)
         self.d_mA = torch.tensor([_MODE_IDX[m[0]] for m in self.modes], dtype=torch.int32, device=dev)
         self.d_mB = torch.tensor([_MODE_IDX[m[1]] for m in self.modes], dtype=torch.int32, device=dev)
         self.d_Cl = torch.empty((len(self.modes), nl), **f64)
         self.h_Cl = torch.empty((len(self.modes), nl), dtype=torch.float64).pin_memory()
         nnode = (self.nb - 1) * msub + 1
         self.d_tab = torch.empty((nnode, 2, prob.NBETA), **f64)
-        self.nlut = 4096
-        self.h_lut = torch.empty(self.nlut, dtype=torch.int32).pin_memory()
-        self.d_lut = torch.empty(self.nlut, dtype=torch.int32, device=dev)
-        self._lut(bg)
         self.h2d_bytes = self.h_in.numel() * 8 + self.h_lut.numel() * 4
         self.d2h_bytes = self.h_Cl.numel() * 8
+        self.fused, self.src_flops = False, 0
         self.launches_resident, self.launches_e2e = 5, 6
         self.cost_model, self.d_items = None, None
 
@@ -1172,27 +1181,38 @@ class CMBPlan:
         self.d_flags = torch.zeros(self.nk, dtype=torch.int32, device=self.dev)
         return model
 
-    def stage(self, bg):
-        """Copy a background solution (same number of knots) into the pinned staging buffer."""
+    def stage(self, bg, prob=None):
+        """Stage a cosmology (a background solution with the plan's number of knots and grid sizes) into the pinned buffers:
+        knots and parameters AND everything derived from them -- the fine k-grid (step π/τ0), the saved times, χ = τ0 − τ, the
+        trapezoid weights, the C_l k-weights (P0 depends on As, ns, h), the start times and the interval look-up of the β-table.
+        `upload()` then moves all of it in two copies.  Raises if the grid sizes differ from the plan's (build a new plan)."""
+        prob = prob if prob is not None else bg.prob
         if len(bg.t) != self.nb:
             raise ValueError("plan was built for a different number of background knots")
-        nb = self.nb
+        dkt0, ntau, taucut = self._grid_opts
+        ks_fine, taus = cmb_grids(bg, self.kinterp.minimum(), self.kinterp.maximum(), dkt0, ntau, taucut)
+        if len(ks_fine) != self.nkf or len(taus) != self.nt:
+            raise ValueError(f"plan was built for {self.nkf} fine wavenumbers and {self.nt} times; this cosmology needs {len(ks_fine)} and {len(taus)}")
+        if self.jl.xend < ks_fine[-1] * (taus[-1] - taus[0]):
+            raise ValueError("jl.x[end] < kmax*τmax")  # reference assertion (src/observables/angular.jl:110-116); the kernel would clamp silently
+        self.ks_fine, self.taus = ks_fine, taus
+        self.ks_solve = ks_fine if self.direct else self.kinterp.xs
+        w = natural_spline_weights(np.concatenate([[0.0], ks_fine]))[1:]
+        vals = dict(t=bg.t, y=bg.y.ravel(), dy=bg.dy.ravel(), P=bg.P, ks=self.ks_solve, tini=np.full(self.nk, bg.t[0]), ksf=ks_fine, taus=taus, chi=taus[-1] - taus,
+                    wt=_trapz_weights(taus), ck=w * (2 / math.pi) * ks_fine**2 * spectrum_primordial(ks_fine, prob))
         h = self.h_in.numpy()
-        h[:nb] = bg.t
-        h[nb:6 * nb] = bg.y.ravel()
-        h[6 * nb:11 * nb] = bg.dy.ravel()
-        h[11 * nb:] = bg.P
-        self.tau0, self.s0, self.dsl = bg.tau0, math.log(bg.t[0]), (math.log(bg.t[-1]) - math.log(bg.t[0])) / 4096
+        for name, v in vals.items():
+            a, b = self._off[name]
+            h[a:b] = v
+        self.tau0, self.s0, self.dsl = bg.tau0, math.log(bg.t[0]), (math.log(bg.t[-1]) - math.log(bg.t[0])) / self.nlut
+        self.h_lut.numpy()[:] = np.clip(np.searchsorted(bg.t, np.exp(self.s0 + self.dsl * np.arange(self.nlut)), side="right") - 1, 0, self.nb - 2).astype(np.int32)
+        if self.d_Bw is not None:  # barycentric weights coarse -> fine k (the fine grid moves with τ0)
+            self.d_Bw.copy_(torch.from_numpy(self.kinterp.matrix(ks_fine)))
         self._bg = bg
 
-    def _lut(self, bg):
-        lut = np.clip(np.searchsorted(bg.t, np.exp(self.s0 + self.dsl * np.arange(self.nlut)), side="right") - 1, 0, self.nb - 2).astype(np.int32)
-        self.h_lut.numpy()[:] = lut
-
     def _views(self):
-        nb = self.nb
-        d = self.d_in
-        return d[11 * nb:], d[:nb], d[nb:6 * nb], d[6 * nb:11 * nb]
+        v = lambda name: self.d_in[self._off[name][0]:self._off[name][1]]
+        return v("P"), v("t"), v("y"), v("dy")
 
     def upload(self):
         """H2D of the staged inputs + β-table build."""
@@ -1204,6 +1224,12 @@ class CMBPlan:
             raise RuntimeError(f"sbm_build_table failed with code {rc}")
 
     def solve(self):
+        """Perturbation solve of all modes up to the sources S(τ,k) on the device."""
+        self._integrate()
+        if not self.fused:
+            self.sources()
+
+    def _integrate(self):
         P, t, y, dy = self._views()
         lib = self.prob.lib
         if self.d_items is not None:
@@ -1238,9 +1264,8 @@ class CMBPlan:
             raise RuntimeError(f"sbl_cl failed with code {rc}")
 
     def run(self):
-        """Device-resident pass: solve -> sources -> LOS -> C_l (inputs and β-table already in HBM)."""
+        """Device-resident pass: solve (-> sources) -> LOS -> C_l (inputs and β-table already in HBM)."""
         self.solve()
-        self.sources()
         self.los_cl()
 
     def download(self):
@@ -1296,7 +1321,8 @@ def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτi
     import os
     import torch.distributed as dist
     _require_cuda()
-    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    thetas = np.asarray(thetas, dtype=np.float64)
+    thetas = thetas.reshape(0, len(names)) if thetas.size == 0 else np.atleast_2d(thetas)
     ks = np.ascontiguousarray(ks, dtype=np.float64)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -1332,6 +1358,9 @@ def _spectrum_matter_sweep_local(prob, names, thetas, ks, chunk=32, nthreads=Non
             return p, solvebg(p)
 
     streams = [torch.cuda.Stream() for _ in range(nslots)]
+    # up to `nslots` launches are in flight at once; a statically scheduled launch needs ALL its lists resident from the start
+    # (continuation items wait for a flag set by the first item of another list), so each gets an equal share of the resident warps
+    max_lists = None if cost is None else max(1, resident_warps(prob, batch=True) // nslots)
     out = np.full((n, nk), np.nan)
     info = dict(background_failures=0, mode_failures=0, launches=0)
     timeline, tstart = [], time.perf_counter()
@@ -1374,7 +1403,7 @@ def _spectrum_matter_sweep_local(prob, names, thetas, ks, chunk=32, nthreads=Non
                 continue
             probs, bgs = [group[i - c0][0] for i in idx], [group[i - c0][1] for i in idx]
             with torch.cuda.stream(streams[slot]):
-                batch = solvept_batch(bgs, ks, ptivini=f, reltol=reltol, abstol=abstol, msub=msub, cost=cost, arena=arenas[slot])
+                batch = solvept_batch(bgs, ks, ptivini=f, reltol=reltol, abstol=abstol, msub=msub, cost=cost, arena=arenas[slot], max_lists=max_lists)
                 dm = torch.empty(len(idx) * nk, dtype=torch.float64, device=batch.d_uend.device)
                 for j, (p, bg, sol) in enumerate(zip(probs, bgs, batch.sols)):
                     d = arenas[slot].views[j]
@@ -1391,8 +1420,8 @@ def _spectrum_matter_sweep_local(prob, names, thetas, ks, chunk=32, nthreads=Non
             info["launches"] += 1
             inflight[slot] = (idx, probs, bgs, batch, dm, h_dm, h_rc, ev)
             timeline.append(("launch", slot, t_ - tstart, time.perf_counter() - tstart))
-    for slot in range(nslots):
-        finish((c + 1 + slot) % nslots)
+    for slot in range(nslots):  # finish() is a no-op for an empty slot
+        finish(slot)
     if return_info == "timeline":
         info["timeline"] = timeline
     if return_info:

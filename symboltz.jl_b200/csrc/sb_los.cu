@@ -207,6 +207,42 @@ int sbl_cl(int nl, int nk, int k0, int k1, const double* dck, const double* dThe
     return 0;
 }
 
+// FP64 roofline denominator, measured in the run that reports it (bench.py): independent DFMA chains on every SM.
+// Returns the best of `reps` timed launches in TFLOP/s through *tflops (events on `stream`); dscratch: blocks*256 doubles.
+__global__ void sbl_dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+int sbl_dfma_peak(int iters, int reps, double* tflops, void* stream) {
+    int dev, nsm;
+    SBL_CUDA_CHECK(cudaGetDevice(&dev));
+    SBL_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = nsm * 8, threads = 256;
+    double* d = nullptr;
+    SBL_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    SBL_CUDA_CHECK(cudaEventCreate(&e0)); SBL_CUDA_CHECK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int r = 0; r <= reps; r++) { // launch 0 is the warm-up
+        cudaEventRecord(e0, (cudaStream_t)stream);
+        sbl_dfma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, (cudaStream_t)stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    SBL_CUDA_CHECK(cudaGetLastError());
+    *tflops = best;
+    return 0;
+}
+
 int sbl_kinterp(int nk, int nc, const double* dBw, const double* dSc, int n2t, double* dSf, void* stream) {
     if (nk <= 0) return 0;
     sbl_kinterp_kernel<<<nk, 256, 0, (cudaStream_t)stream>>>(nk, nc, dBw, dSc, n2t, dSf);
@@ -242,6 +278,12 @@ extern "C" int sbl_cmb_host(int nk, const double* ks, int nc, const double* Bw, 
     const double step = xmax / (n - 1);
     int nxp = n + 1;
     if (xcut < xmax) nxp = std::min(nxp, (int)ceil(xcut / step) + 2);
+    { // the reference asserts jl.x[end] >= kmax·τmax (src/observables/angular.jl:110-116); the kernel would clamp silently
+        double kmax = 0, chimax = 0;
+        for (int i = 0; i < nk; i++) kmax = std::max(kmax, ks[i]);
+        for (int i = 0; i < nt; i++) chimax = std::max(chimax, chi[i]);
+        if ((nxp - 2) * step < kmax * chimax) return -4;
+    }
     SblDevBuf B;
     double *dks, *dBw = nullptr, *dSc, *dchi, *dwt, *djy, *djdy, *dck, *dTh, *dCl;
     int *dls, *dmA, *dmB;
