@@ -74,7 +74,7 @@ int sbm_solvept_sched(const double* dP, int nb, const double* dt, const double* 
                       const double* dtab, int nk, const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems,
                       const int* dibeg, int nlists, double* dcont, int* dflags, void* stream);
-/* One background cosmology as the integrator sees it (device pointers; 112 bytes, natural C layout). */
+/* One background cosmology as the integrator sees it (device pointers; 128 bytes, natural C layout). */
 typedef struct {
     const double* P;              /* [npar] parameters incl. tau0, kappa0 */
     int nb;                       /* spline knots */
@@ -86,7 +86,17 @@ typedef struct {
     const double* tab;            /* [(nb-1)*msub + 1][2][NBETA], from sbm_build_table */
     double tend;                  /* end of the integration (tau0) */
     const double* saveat;         /* [nsave] or NULL */
+    const double* srcbg;          /* [nsave][sbm_srcbg_stride()] from sbm_srcbg at `saveat` (fused sources, sbm_solvept_batch_src), or NULL */
+    double taurec;                /* time of maximal visibility (only the lensing source Spsi uses it) */
 } sbm_cosmo_t;
+
+/* Request for the fused evaluation of the CMB source functions inside the perturbation solve (host struct, passed by pointer). */
+typedef struct {
+    const double* dsrcbg;         /* device [nsave][sbm_srcbg_stride()] from sbm_srcbg (single-cosmology calls; batched: sbm_cosmo_t.srcbg) */
+    double* dS;                   /* device output [nk][nS][nsave] */
+    int nS, scale_k;              /* nS = 2 (ST, SE) or 3 (+ Spsi); scale_k != 0 returns (k ST, k^2 SE), src/observables/angular.jl:293 */
+    double taurec;                /* single-cosmology calls */
+} sbm_src_t;
 
 /* Perturbation solve of a BATCH of cosmologies in one launch: mode i belongs to cosmology dcosmo_of[i] (replaces the serial outer
  * loop `for theta: spectrum_matter(probgen(theta), ks)` of docs/src/forecasting.md:56-59 / SURVEY 8b "batched variants with leading
@@ -96,6 +106,25 @@ typedef struct {
 int sbm_solvept_batch(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg,
                       int nlists, double* dcont, int* dflags, void* stream);
+/* The same three solves with the source functions S(tau, k) formed INSIDE the integrator at the save times, from the dense output,
+ * and written with coalesced stores (replaces the output_func of solvept in source_grid, src/observables/fourier.jl:267-281, which
+ * evaluates getsym(prob.pt, Ss) per save time and keeps only S).  dusave may be NULL: the saved states then never reach HBM.
+ * src == NULL: identical to the plain entry points. */
+int sbm_solvept_src(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                    const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                    double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas,
+                    void* stream, const sbm_src_t* src);
+int sbm_solvept_sched_src(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                          const double* dtab, int nk, const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol,
+                          double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems,
+                          const int* dibeg, int nlists, double* dcont, int* dflags, void* stream, const sbm_src_t* src);
+int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
+                          double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg,
+                          int nlists, double* dcont, int* dflags, void* stream, const sbm_src_t* src);
+/* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
+ * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
+ * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */
+int sbm_srcbg(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, void* stream);
 int sbm_cosmo_bytes(void);
 int sbm_cont_stride(void);
 int sbm_resident_warps(void);
@@ -106,7 +135,8 @@ int sbm_warps_per_cta(void);
  * inside spectrum_matter(sol, k), src/observables/fourier.jl:39-52, 90-97). */
 int sbm_delta_m(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, double tau, int nk, const double* dks, const double* du, double* dout, void* stream);
 
-/* CMB source functions at every saved (k, τ) (replaces getsym(prob.pt, Ss) in source_grid's output_func,
+/* CMB source functions at every saved (k, τ) from states kept in HBM -- the stand-alone form of what sbm_solvept_src fuses into the
+ * solve; same arithmetic, same bits (replaces getsym(prob.pt, Ss) in source_grid's output_func,
  * src/observables/fourier.jl:267-281, with ST and SE of src/models/cosmologies.jl:99-104).
  * dsrcbg: scratch of nt * sbm_srcbg_stride() doubles.  dS[nk][nS][nt], nS = 2 (ST, SE) or 3 (+ the lensing source Sψ of
  * src/models/cosmologies.jl:105, which needs taurec); scale_k != 0 returns (k·ST, k²·SE) as fed to the line-of-sight integrator
@@ -119,8 +149,8 @@ int sbm_smem_bytes(void);
 /* One-call HOST-buffer variant of the perturbation solve (for hosts without a device allocator: Julia without CUDA.jl, C):
  * every pointer is a host pointer; the library allocates device memory, uploads the nb background knots, builds the β-table
  * and interval look-up (msub = 16, 4096 entries), orders the work queue by descending k, runs sbm_solvept and -- when the
- * outputs are non-NULL -- sbm_delta_m at tend (delta_m[nk]) and sbm_sources on the saved states (S[nk][nS][nsave], needs
- * nsave > 0), and downloads.  usave[nk][nsave][N], uend[nk][N], retcode[nk], stats[nk][4], delta_m, S may each be NULL.
+ * outputs are non-NULL -- sbm_delta_m at tend (delta_m[nk]) and the fused source evaluation at the save times (S[nk][nS][nsave],
+ * needs nsave > 0; the states are kept in device memory only when usave is asked for), and downloads.  usave[nk][nsave][N], uend[nk][N], retcode[nk], stats[nk][4], delta_m, S may each be NULL.
  * Blocking.  (replaces solvept(ptprob, bgsol, ks, ptivini; saveat, output_func), src/solve.jl:543-569, as called from
  * solve(prob, ks), src/solve.jl:398, spectrum_matter, src/observables/fourier.jl:90-97, and source_grid, fourier.jl:279) */
 int sbm_solvept_host(const double* P, int nb, const double* t, const double* y, const double* dy, int nk, const double* ks, const double* tini, double tend, int nsave,

@@ -341,6 +341,7 @@ class PerturbationSolution:
     def __init__(self, prob, bgsol, ks, tini, saveat, uend, usave, retcode, stats, dks):
         self.prob, self.bg, self.ks, self.tini, self.saveat = prob, bgsol, ks, tini, saveat
         self.d_uend, self.d_usave, self.d_retcode, self.d_stats, self.d_ks = uend, usave, retcode, stats, dks
+        self.d_S = None  # fused source functions [nk][nS][nsave] (solvept(..., sources=...))
         self._rc = None
 
     @property
@@ -435,11 +436,36 @@ def resident_warps(prob, batch=False):
     return int(prob.lib.sbm_resident_warps_batch() if batch else prob.lib.sbm_resident_warps())
 
 
-def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None):
+class SbmSrc(C.Structure):
+    """sbm_src_t (include/symboltz_b200.h): request for the fused source evaluation of the *_src solves."""
+    _fields_ = [("dsrcbg", C.c_void_p), ("dS", C.c_void_p), ("nS", C.c_int), ("scale_k", C.c_int), ("taurec", C.c_double)]
+
+
+def _src_request(sources, taurec_default=0.0):
+    nS = int(sources.get("nS", 2))
+    if nS not in (2, 3):
+        raise ValueError("sources: nS must be 2 (ST, SE) or 3 (+ Sψ)")
+    return nS, 1 if sources.get("scale_k", True) else 0, float(sources.get("taurec", taurec_default))
+
+
+def source_background(prob, d, nb, dsave):
+    """Per-save-time background table of the source evaluation (`sbm_srcbg`): κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, β_m and their flow derivatives."""
+    out = torch.empty((len(dsave), int(prob.lib.sbm_srcbg_stride())), dtype=torch.float64, device=dsave.device)
+    rc = prob.lib.sbm_srcbg(_cptr(d["P"]), C.c_int(nb), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(len(dsave)), _cptr(dsave), _cptr(out), _stream())
+    if rc != 0:
+        raise RuntimeError(f"sbm_srcbg failed with code {rc}")
+    return out
+
+
+def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None, sources=None,
+            keep_states=True):
     """Perturbation solve over independent k-modes on the GPU (reference solvept, src/solve.jl:543-569).
     ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527).
     cost: optional per-mode estimate of attempted steps (array or vectorised callable ks -> cost, e.g. a ModeCostModel): run under the static preemptive
-    schedule of `build_schedule` instead of the atomic queue (same results, better balance for few modes per warp)."""
+    schedule of `build_schedule` instead of the atomic queue (same results, better balance for few modes per warp).
+    sources: dict(nS = 2 | 3, scale_k = True, taurec = bgsol.taurec) -- evaluate the CMB source functions at the `saveat` times INSIDE the
+    integrator (the reference's output_func, src/observables/fourier.jl:272-278) into sol.d_S[nk][nS][nsave]; with keep_states = False the saved
+    states never leave the SM (sol.d_usave is None)."""
     _require_cuda()
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
     nk = len(ks)
@@ -458,13 +484,20 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     retcode = torch.empty(nk, dtype=torch.int32, device=dev)
     stats = torch.empty((nk, 4), dtype=torch.int64, device=dev)
     queue = torch.zeros(1, dtype=torch.int32, device=dev)
+    src, dS, keep = None, None, None
     if saveat is not None:
         saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         dsave = torch.from_numpy(saveat).to(dev)
-        usave = torch.empty((nk, len(saveat), N), dtype=torch.float64, device=dev)
         ns = len(saveat)
+        if sources is not None and ns > 0:
+            nS, sk, trec = _src_request(sources, bgsol.taurec)
+            keep = source_background(prob, d, len(bgsol.t), dsave)
+            dS = torch.empty((nk, nS, ns), dtype=torch.float64, device=dev)
+            src = SbmSrc(keep.data_ptr(), dS.data_ptr(), nS, sk, trec)
+        usave = torch.empty((nk, ns, N), dtype=torch.float64, device=dev) if (keep_states or src is None) else None
     else:
         dsave, usave, ns = None, None, 0
+    srcp = C.byref(src) if src is not None else None
     dtrace = torch.zeros((trace, 3), dtype=torch.float64, device=dev) if trace else None  # debug: (t, dt, EEst) of mode 0
     if cost is not None and nk > 0:
         cvec = np.asarray(cost(ks) if callable(cost) else cost, dtype=np.float64) * np.ones(nk)
@@ -474,9 +507,13 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         ditems, dibeg = torch.from_numpy(items).to(dev), torch.from_numpy(ibeg).to(dev)
         dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
         dflags = torch.zeros(nk, dtype=torch.int32, device=dev)
-        rc = prob.lib.sbm_solvept_sched(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
-                                        C.c_int(nk), _cptr(dks), _cptr(dtini), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
-                                        _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream())
+        rc = prob.lib.sbm_solvept_sched_src(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+                                            C.c_int(nk), _cptr(dks), _cptr(dtini), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                            _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream(), srcp)
+    elif src is not None:
+        rc = prob.lib.sbm_solvept_src(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+                                      C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                      _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), C.c_int(nctas), _stream(), srcp)
     else:
         rc = prob.lib.sbm_solvept(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
                                   C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
@@ -484,6 +521,7 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     if rc < 0:
         raise RuntimeError(f"sbm_solvept failed with code {rc}")
     sol = PerturbationSolution(prob, bgsol, ks, tini, saveat, uend, usave, retcode, stats, dks)
+    sol.d_S, sol._keep = dS, keep
     sol.grid = rc
     sol.trace = dtrace.cpu().numpy() if trace else None
     if sync and warn:
@@ -492,10 +530,10 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     return sol
 
 
-# sbm_cosmo_t (include/symboltz_b200.h): natural C layout, 112 bytes
-COSMO_DTYPE = np.dtype({"names": ["P", "nb", "t", "y", "dy", "tb_nb", "msub", "nlut", "s0", "inv_dsl", "tb_t", "lut", "tab", "tend", "saveat"],
-                        "formats": ["u8", "i4", "u8", "u8", "u8", "i4", "i4", "i4", "f8", "f8", "u8", "u8", "u8", "f8", "u8"],
-                        "offsets": [0, 8, 16, 24, 32, 40, 44, 48, 56, 64, 72, 80, 88, 96, 104], "itemsize": 112})
+# sbm_cosmo_t (include/symboltz_b200.h): natural C layout, 128 bytes
+COSMO_DTYPE = np.dtype({"names": ["P", "nb", "t", "y", "dy", "tb_nb", "msub", "nlut", "s0", "inv_dsl", "tb_t", "lut", "tab", "tend", "saveat", "srcbg", "taurec"],
+                        "formats": ["u8", "i4", "u8", "u8", "u8", "i4", "i4", "i4", "f8", "f8", "u8", "u8", "u8", "f8", "u8", "u8", "f8"],
+                        "offsets": [0, 8, 16, 24, 32, 40, 44, 48, 56, 64, 72, 80, 88, 96, 104, 112, 120], "itemsize": 128})
 
 
 def cosmo_record(bgsol, msub=16, dsave=None):
@@ -507,6 +545,7 @@ def cosmo_record(bgsol, msub=16, dsave=None):
     r["tb_nb"], r["msub"], r["nlut"], r["s0"], r["inv_dsl"] = nb, d["msub"], d["nlut"], d["s0"], 1.0 / d["dsl"]
     r["tb_t"], r["lut"], r["tab"], r["tend"] = d["t"].data_ptr(), d["lut"].data_ptr(), d["tab"].data_ptr(), bgsol.tau0
     r["saveat"] = 0 if dsave is None else dsave.data_ptr()
+    r["srcbg"], r["taurec"] = 0, bgsol.taurec
     return r
 
 
@@ -559,6 +598,7 @@ class CosmoArena:
             r["P"], r["nb"], r["t"], r["y"], r["dy"] = dP.data_ptr(), nb, dt.data_ptr(), dy.data_ptr(), ddy.data_ptr()
             r["tb_nb"], r["msub"], r["nlut"], r["s0"], r["inv_dsl"] = nb, msub, self.NLUT, s0, 1.0 / dsl
             r["tb_t"], r["lut"], r["tab"], r["tend"] = dt.data_ptr(), lut.data_ptr(), tab.data_ptr(), b.tau0
+            r["srcbg"], r["taurec"] = 0, b.taurec
         self.d_f[:fo[-1]].copy_(self.h_f[:fo[-1]], non_blocking=True)
         self.d_i[:nc * self.NLUT].copy_(self.h_i[:nc * self.NLUT], non_blocking=True)
         for v in self.views:
@@ -585,14 +625,16 @@ class BatchSolution:
         return bool((self.d_retcode == 0).all().item())
 
 
-def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, cost=None, arena=None, max_lists=None):
+def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, cost=None, arena=None, max_lists=None, sources=None,
+                  keep_states=True):
     """Perturbation solve of several cosmologies (same model structure) in ONE integrator launch over all (cosmology, mode)
     pairs, ordered by descending k across cosmologies (SURVEY §8b batched variant; the reference runs one `solvept` per
     cosmology, docs/src/forecasting.md:56-59).  bgsols: BackgroundSolutions; ks: one array for all, or one array per cosmology;
     saveat: None, or one array of save times per cosmology (equal lengths).  Per-mode results are bit-identical to `solvept` on that
     cosmology.  cost: optional vectorised callable ks -> estimated attempts, switches to the static preemptive schedule; every list of
     a static schedule must be resident from the start of the launch, so callers that keep several scheduled launches in flight
-    (the sweep's stream slots) pass max_lists = resident warps / launches in flight."""
+    (the sweep's stream slots) pass max_lists = resident warps / launches in flight.
+    sources / keep_states: as in `solvept` (fused source evaluation at each cosmology's own save times; taurec of each cosmology)."""
     _require_cuda()
     nc = len(bgsols)
     prob = bgsols[0].prob
@@ -621,6 +663,18 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
         dsaves = [dsv[i] for i in range(nc)]
     arena = arena if arena is not None else CosmoArena()
     recs = arena.load(bgsols, msub)  # uploads knots, builds the β-tables (same kernel and node layout as BackgroundSolution.device)
+    src, dS, dsb = None, None, None
+    if sources is not None and ns > 0:
+        nS, sk, _ = _src_request(sources)
+        stride = int(prob.lib.sbm_srcbg_stride())
+        dsb = torch.empty((nc, ns, stride), dtype=torch.float64, device=dev)
+        for i, v in enumerate(arena.views):
+            rc = prob.lib.sbm_srcbg(_cptr(v["P"]), C.c_int(v["nb"]), _cptr(v["t"]), _cptr(v["y"]), _cptr(v["dy"]), C.c_int(ns), _cptr(dsaves[i]), _cptr(dsb[i]), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_srcbg failed with code {rc}")
+            recs[i]["srcbg"] = dsb[i].data_ptr()
+        dS = torch.empty((int(offsets[-1]), nS, ns), dtype=torch.float64, device=dev)
+        src = SbmSrc(None, dS.data_ptr(), nS, sk, 0.0)
     for i in range(nc):
         recs[i]["saveat"] = 0 if dsaves[i] is None else dsaves[i].data_ptr()
     dcos = _h2d(np.frombuffer(recs.tobytes(), dtype=np.uint8).reshape(nc, COSMO_DTYPE.itemsize).copy(), dev)
@@ -629,7 +683,7 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
     dcof, dorder = _h2d(cosmo_of, dev), _h2d(order, dev)
     N = prob.N
     uend = torch.empty((nk, N), dtype=torch.float64, device=dev)
-    usave = torch.empty((nk, ns, N), dtype=torch.float64, device=dev) if ns else None
+    usave = torch.empty((nk, ns, N), dtype=torch.float64, device=dev) if (ns and (keep_states or src is None)) else None
     retcode = torch.empty(nk, dtype=torch.int32, device=dev)
     stats = torch.empty((nk, 4), dtype=torch.int64, device=dev)
     queue = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -643,15 +697,17 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
         ditems, dibeg = _h2d(items, dev), _h2d(ibeg, dev)
         dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
         dflags = torch.zeros(nk, dtype=torch.int32, device=dev)
-    rc = prob.lib.sbm_solvept_batch(C.c_int(nc), _cptr(dcos), C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dcof), _cptr(dorder), C.c_int(ns), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
-                                    _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream())
+    rc = prob.lib.sbm_solvept_batch_src(C.c_int(nc), _cptr(dcos), C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dcof), _cptr(dorder), C.c_int(ns), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                        _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream(),
+                                        C.byref(src) if src is not None else None)
     if rc < 0:
         raise RuntimeError(f"sbm_solvept_batch failed with code {rc}")
     sols = []
     for i, b in enumerate(bgsols):
         a, e = int(offsets[i]), int(offsets[i + 1])
         sols.append(PerturbationSolution(b.prob, b, ks_list[i], tini[a:e], None if saveat is None else saveat[i], uend[a:e], None if usave is None else usave[a:e], retcode[a:e], stats[a:e], dks[a:e]))
-    return BatchSolution(sols, offsets, uend, usave, retcode, stats, keep=(arena, dcos, dkt, dcof, dorder, queue, ditems, dibeg, dcont, dflags, dsaves))
+        sols[-1].d_S = None if dS is None else dS[a:e]
+    return BatchSolution(sols, offsets, uend, usave, retcode, stats, keep=(arena, dcos, dkt, dcof, dorder, queue, ditems, dibeg, dcont, dflags, dsaves, dsb, dS))
 
 
 class CosmologySolution:
@@ -836,12 +892,18 @@ class SourceGrid:
         return np.ascontiguousarray(self.dS.cpu().numpy().transpose(2, 0, 1))
 
 
-def source_grid(prob, taus, ks, bgsol, scale_k=True, lensing=False, **ptopts):
-    """Solve the modes `ks` saving at `taus` and evaluate the CMB sources (k·ST, k²·SE[, Sψ if lensing]) there
-    (reference source_grid(prob, Ss, τs, ks, bgsol), src/observables/fourier.jl:267-281 with Ss of angular.jl:293)."""
+def source_grid(prob, taus, ks, bgsol, scale_k=True, lensing=False, fused=True, keep_states=False, **ptopts):
+    """Solve the modes `ks` and evaluate the CMB sources (k·ST, k²·SE[, Sψ if lensing]) at `taus`
+    (reference source_grid(prob, Ss, τs, ks, bgsol), src/observables/fourier.jl:267-281 with Ss of angular.jl:293).
+    fused (default): the sources are formed inside the integrator from the dense output, as the reference's output_func does, and only
+    S[nk][nS][nτ] reaches HBM (keep_states = True additionally returns the states in .sol.d_usave).  fused = False: the states
+    usave[nk][nτ][N] are written and a second kernel (`sbm_sources`) evaluates the sources from them -- same bits, 40× the traffic."""
     taus = np.ascontiguousarray(taus, dtype=np.float64)
     if taus.min() < bgsol.t[0] or taus.max() > bgsol.t[-1]:
         raise ValueError("input τs and computed background solution have different timespans")
+    if fused:
+        sol = solvept(prob, bgsol, ks, saveat=taus, sources=dict(nS=3 if lensing else 2, scale_k=scale_k, taurec=bgsol.taurec), keep_states=keep_states, **ptopts)
+        return SourceGrid(sol.d_S, sol.ks, taus, sol)
     sol = solvept(prob, bgsol, ks, saveat=taus, **ptopts)
     d = bgsol.device()
     dev = sol.d_uend.device
@@ -1112,9 +1174,9 @@ class CMBPlan:
     the knots; `upload()` must run once before the first `run()`.  Every launch goes to torch's current stream."""
 
     def __init__(self, prob, bg, jl, modes=("TT", "EE", "TE"), direct=True, kinterp=None, dkt0=math.pi, ntau=300, taucut=1e-2,
-                 reltol=1e-5, abstol=1e-5, maxiters=100000, msub=16, normalization="Cl"):
+                 reltol=1e-5, abstol=1e-5, maxiters=100000, msub=16, normalization="Cl", fused=True):
         _require_cuda()
-        self.prob, self.jl, self.modes, self.direct = prob, jl, list(modes), direct
+        self.prob, self.jl, self.modes, self.direct, self.fused = prob, jl, list(modes), direct, bool(fused)
         self.reltol, self.abstol, self.maxiters, self.msub, self.normalization = reltol, abstol, maxiters, msub, normalization
         self.kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
         dev = torch.device("cuda")
@@ -1144,7 +1206,7 @@ class CMBPlan:
         order = np.argsort(-self.ks_solve, kind="stable").astype(np.int32)  # ascending grids of fixed length: the order does not depend on the cosmology
         f64 = dict(dtype=torch.float64, device=dev)
         self.d_order = torch.from_numpy(order).to(dev)
-        self.d_usave = torch.empty((nk, nt, N), **f64)
+        self.d_usave = None if self.fused else torch.empty((nk, nt, N), **f64)  # fused: the saved states never reach HBM
         self.d_uend = torch.empty((nk, N), **f64)
         self.d_ret = torch.empty(nk, dtype=torch.int32, device=dev)
         self.d_stats = torch.empty((nk, 4), dtype=torch.int64, device=dev)
@@ -1160,8 +1222,10 @@ class CMBPlan:
         self.d_tab = torch.empty((nnode, 2, prob.NBETA), **f64)
         self.h2d_bytes = self.h_in.numel() * 8 + self.h_lut.numel() * 4
         self.d2h_bytes = self.h_Cl.numel() * 8
-        self.fused, self.src_flops = False, 0
-        self.launches_resident, self.launches_e2e = 5, 6
+        # algorithmic flops of one source evaluation (SURVEY §8d F_S): u̇ = J u (2 flop per stored Jacobian entry and factor), hub terms, Ψ̇, Π̈ rows, closing algebra
+        self.src_flops = 3 * prob.info["nnz_full"] + 120
+        self._src = SbmSrc(self.d_srcbg.data_ptr(), self.d_S.data_ptr(), 2, 1, 0.0)
+        self.launches_resident, self.launches_e2e = (3, 5) if self.fused else (5, 6)
         self.cost_model, self.d_items = None, None
 
     def learn_schedule(self, model=None):
@@ -1222,6 +1286,10 @@ class CMBPlan:
         rc = self.prob.lib.sbm_build_table(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), _cptr(self.d_tab), _stream())
         if rc != 0:
             raise RuntimeError(f"sbm_build_table failed with code {rc}")
+        if self.fused:  # per-save-time background of the source evaluation (the unfused path builds it inside sbm_sources)
+            rc = self.prob.lib.sbm_srcbg(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.nt), _cptr(self.d_taus), _cptr(self.d_srcbg), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_srcbg failed with code {rc}")
 
     def solve(self):
         """Perturbation solve of all modes up to the sources S(τ,k) on the device."""
@@ -1232,19 +1300,20 @@ class CMBPlan:
     def _integrate(self):
         P, t, y, dy = self._views()
         lib = self.prob.lib
+        srcp = C.byref(self._src) if self.fused else None
         if self.d_items is not None:
-            rc = lib.sbm_solvept_sched(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
-                                       C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
-                                       C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), _cptr(self.d_items), _cptr(self.d_ibeg),
-                                       C.c_int(self.nlists), _cptr(self.d_cont), _cptr(self.d_flags), _stream())
+            rc = lib.sbm_solvept_sched_src(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
+                                           C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
+                                           C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), _cptr(self.d_items), _cptr(self.d_ibeg),
+                                           C.c_int(self.nlists), _cptr(self.d_cont), _cptr(self.d_flags), _stream(), srcp)
             if rc < 0:
-                raise RuntimeError(f"sbm_solvept_sched failed with code {rc}")
+                raise RuntimeError(f"sbm_solvept_sched_src failed with code {rc}")
             return
-        rc = lib.sbm_solvept(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
-                             C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), _cptr(self.d_order), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
-                             C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), C.c_int(0), _stream(), None, C.c_int(0))
+        rc = lib.sbm_solvept_src(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
+                                 C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), _cptr(self.d_order), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
+                                 C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), C.c_int(0), _stream(), srcp)
         if rc < 0:
-            raise RuntimeError(f"sbm_solvept failed with code {rc}")
+            raise RuntimeError(f"sbm_solvept_src failed with code {rc}")
 
     def sources(self):
         P, t, y, dy = self._views()
@@ -1458,21 +1527,14 @@ def spectrum_cmb_batch(modes, probs, jl, normalization="Cl", kinterp=None, direc
     grids = [cmb_grids(bgsols[i], kinterp.minimum(), kinterp.maximum(), dkt0, ntau, taucut) for i in good]
     ks_list = [g[0] if direct else kinterp.xs for g in grids]
     arena = CosmoArena()
-    batch = solvept_batch([bgsols[i] for i in good], ks_list, saveat=[g[1] for g in grids], arena=arena, **dict(ptopts or {}))
-    dev = batch.d_uend.device
+    # the sources are formed inside the integrator (each cosmology with its own save times and background table): only S reaches HBM, so
+    # direct = True batches are bounded by nk·2·nτ·8 bytes per cosmology (9.7 MB), not by the saved states (397 MB)
+    batch = solvept_batch([bgsols[i] for i in good], ks_list, saveat=[g[1] for g in grids], arena=arena, sources=dict(nS=2, scale_k=True), keep_states=False, **dict(ptopts or {}))
     cls = []
     for j, i in enumerate(good):
-        prob, bg, sol, v = probs[i], bgsols[i], batch.sols[j], arena.views[j]
+        prob, sol = probs[i], batch.sols[j]
         ks_fine, taus = grids[j]
-        nk, nt = len(sol.ks), len(taus)
-        dS = torch.empty((nk, 2, nt), dtype=torch.float64, device=dev)
-        scratch = torch.empty(nt * prob.lib.sbm_srcbg_stride(), dtype=torch.float64, device=dev)
-        dtaus = _h2d(taus, dev)
-        rc = prob.lib.sbm_sources(_cptr(v["P"]), C.c_int(v["nb"]), _cptr(v["t"]), _cptr(v["y"]), _cptr(v["dy"]), C.c_int(nt), _cptr(dtaus), _cptr(scratch), C.c_int(nk), _cptr(sol.d_ks),
-                                  _cptr(sol.d_usave), _cptr(dS), C.c_int(1), C.c_int(2), C.c_double(bg.taurec), _stream())
-        if rc != 0:
-            raise RuntimeError(f"sbm_sources failed with code {rc}")
-        theta = los_integrate(SourceGrid(dS, sol.ks, taus, sol), jl, ks_fine=ks_fine, kinterp=None if direct else kinterp)
+        theta = los_integrate(SourceGrid(sol.d_S, sol.ks, taus, sol), jl, ks_fine=ks_fine, kinterp=None if direct else kinterp)
         cls.append(spectrum_cmb_from_theta(theta, modes, spectrum_primordial(ks_fine, prob), jl.l, ks_fine, normalization))
     allcl = torch.stack(cls).cpu().numpy()  # [ngood, nmodes, nl]
     for j, i in enumerate(good):

@@ -314,9 +314,18 @@ struct SbCosmo {
     SbTable tb;
     double tend;
     const double* saveat; // [nsave] save times (may be null when nsave = 0)
+    const double* srcbg;  // [nsave][SB_SRCBG_STRIDE] per-save-time background of the fused source evaluation (sbm_srcbg), or null
+    double taurec;        // time of maximal visibility (lensing source Sψ)
 };
-static_assert(sizeof(SbCosmo) == 112, "SbCosmo must match sbm_cosmo_t");
-#define SB_COSMO_DOUBLES 14
+static_assert(sizeof(SbCosmo) == 128, "SbCosmo must match sbm_cosmo_t");
+// Fused source evaluation request (= sbm_src_t of include/symboltz_b200.h): host struct passed by pointer to the *_src entry points.
+struct sbm_src_t {
+    const double* dsrcbg; // device [nsave][sbm_srcbg_stride()] from sbm_srcbg (single-cosmology calls; batched calls take it from sbm_cosmo_t)
+    double* dS;           // device [nk][nS][nsave]
+    int nS, scale_k;      // nS = 2 (ST, SE) or 3 (+ Sψ); scale_k != 0: (k·ST, k²·SE)
+    double taurec;        // single-cosmology calls
+};
+#define SB_COSMO_DOUBLES 16
 
 struct SbSolveArgs {
     SbCosmo c0;            // the cosmology of a single-cosmology launch
@@ -339,6 +348,9 @@ struct SbSolveArgs {
     const int* ibeg;
     double* cont;     // [nk][SB_CONT] continuation records
     int* flags;       // [nk]: 0 not yet parked, 1 parked (record valid), 2 finished inside the first piece
+    // fused source evaluation (sbm_solvept_src & co.): S[nk][nS][nsave] formed from the dense output at every save time
+    double* S;
+    int nS, scale_k;
 };
 #define SB_CONT (SB_N + 12)
 
@@ -358,7 +370,9 @@ struct SbSolveArgs {
 #define SB_SM_BD (SB_SM_BS + 6 * SB_NB)
 #define SB_SM_KP (SB_SM_BD + SB_NB)
 #define SB_SM_COSMO (SB_SM_KP + 8 + 48)  // batched launches: the current mode's SbCosmo
-#define SB_SM_DOUBLES (SB_SM_COSMO + 16)
+#define SB_SM_SBUF (SB_SM_COSMO + 16)    // fused sources: [3][SB_SWIN] values of the current window of save times
+#define SB_SWIN 16
+#define SB_SM_DOUBLES (SB_SM_SBUF + 3 * SB_SWIN)
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
 #ifndef SB_MINBLOCKS
@@ -935,6 +949,94 @@ __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, co
     s1 = warp_sum(a); s2 = warp_sum(c);
 }
 
+// ------------------------------------------------------------------------------------------------ CMB source functions
+// ST, SE (reference src/models/cosmologies.jl:99-104) and the lensing source Sψ (:105) from ONE saved state u (natural order).
+// Derivatives of unknowns are expanded through the ODE itself (u̇ = J u, ü = J̇ u + J u̇), as MTK does symbolically.  The pieces
+// below are shared by the fused evaluation inside the integrator (sb_source_point: the reference evaluates S in solvept's
+// output_func, src/observables/fourier.jl:272-278) and by the stand-alone kernel over saved states (sb_source_kernel), so that
+// both produce the same bits from the same state.
+// Per-τ background row srcbg[it][0..5] = κ̇, κ̈, κ⃛, exp(−κ), τ0 − τ, spare;  then β_m (NBETA) and flow-derivative dβ_m/dτ (NBETA).
+#define SB_SRCBG_STRIDE (8 + 2 * SB_NBETA)
+__device__ __forceinline__ double sb_row_dot(int i, const double* b, const double* u) { // (J_local u)_i
+    double acc = 0;
+    for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * b[sb_bidx[e]] * u[sb_col[e]];
+    return acc;
+}
+__device__ __forceinline__ double sb_row_ddot(int i, const double* b, const double* bd, const double* u, const double* ud) { // (J̇_local u + J_local u̇)_i
+    double acc = 0;
+    for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * (bd[sb_bidx[e]] * u[sb_col[e]] + b[sb_bidx[e]] * ud[sb_col[e]]);
+    return acc;
+}
+__device__ __forceinline__ double sb_hub_seq(int v, const double* b, const double* u) { // hub functional v (2: Φ̇ = φᵀu, 3: Ψ = ψᵀu)
+    double acc = 0;
+    for (int t = sb_hptr[v]; t < sb_hptr[v + 1]; t++) acc += sb_hcoef[t] * b[sb_hb[t]] * u[sb_hidx[t]];
+    return acc;
+}
+// the scalar tail, run by ONE thread: hub columns into u̇, Ψ̇, Π and its derivatives, the sources.  ud holds J_local u on entry.
+__device__ __forceinline__ void sb_source_tail(const double* sb, double k, double tau, double taurec, int scale_k, int nS, const double* b, const double* bd, const double* u, double* ud,
+                                               double Phd, double Psi, double* out, int ostride) {
+    for (int t = sb_hptr[0]; t < sb_hptr[1]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Phd;
+    for (int t = sb_hptr[1]; t < sb_hptr[2]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Psi;
+    double Psid = 0;
+    for (int t = sb_hptr[3]; t < sb_hptr[4]; t++) Psid += sb_hcoef[t] * (bd[sb_hb[t]] * u[sb_hidx[t]] + b[sb_hb[t]] * ud[sb_hidx[t]]);
+    // second derivatives of F2, G0, G2 (rows without hub terms): ü_i = J_i(ḃ) u + J_i(b) u̇
+    const int rows3[3] = {SB_I_F2, SB_I_G0, SB_I_G2};
+    double Pig = 0, Pigd = 0, Pigdd = 0;
+    for (int r = 0; r < 3; r++) {
+        const int i = rows3[r];
+        const double acc = sb_row_ddot(i, b, bd, u, ud);
+        Pig += u[i]; Pigd += ud[i]; Pigdd += acc;
+    }
+    const double kd = sb[0], kdd = sb[1], kddd = sb[2], ek = sb[3], chi = sb[4];
+    const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
+    const double thb = u[SB_I_TB], thbd = ud[SB_I_TB];
+    double ST = v * (u[SB_I_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
+    double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
+    if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
+    out[0] = ST;
+    out[ostride] = SE;
+    if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
+}
+// Warp-cooperative evaluation at one save time inside the integrator.  Not inlined: it is called ≈300 times per mode against
+// ≈2000 Rosenbrock attempts, and keeping it out of line keeps its registers out of the step loop.  un: saved state in natural
+// order, ud/b/bd: scratch (all in the warp's shared memory); out[s * ostride] receives source s (written by lane 0).
+__device__ __noinline__ void sb_source_point(const double* __restrict__ sb, const double* kp, double k, double tau, double taurec, int scale_k, int nS, const double* un, double* ud, double* b,
+                                             double* bd, double* out, int ostride, int lane) {
+    for (int m = lane; m < SB_NB; m += SB_WARP) {
+        const double kk = kp[sb_basis_kpow[m] + 3];
+        b[m] = kk * __ldg(sb + 8 + sb_basis_beta[m]);
+        bd[m] = kk * __ldg(sb + 8 + SB_NBETA + sb_basis_beta[m]);
+    }
+    __syncwarp();
+    double Phd = 0, Psi = 0;
+    if (lane == 0) Phd = sb_hub_seq(2, b, un);
+    if (lane == 1) Psi = sb_hub_seq(3, b, un);
+    Phd = __shfl_sync(SB_FULL, Phd, 0); Psi = __shfl_sync(SB_FULL, Psi, 1);
+    for (int i = lane; i < SB_N; i += SB_WARP) ud[i] = sb_row_dot(i, b, un);
+    __syncwarp();
+    if (lane == 0) {
+        double sbl[5];
+        for (int j = 0; j < 5; j++) sbl[j] = __ldg(sb + j);
+        sb_source_tail(sbl, k, tau, taurec, scale_k, nS, b, bd, un, ud, Phd, Psi, out, ostride);
+    }
+    __syncwarp();
+}
+// Coalesced store of the window of source values: lane 0 has put the sources of save index `it` into sbuf[s][it % SB_SWIN]; when the
+// window is full (or the mode's last save time is reached) the lanes write it as contiguous runs of S[s][w0 .. w0+cnt).  wstart: first
+// valid slot of the window (non-zero only right after a parked mode was resumed in the middle of a window).
+__device__ __forceinline__ void sb_source_flush(const double* sbuf, double* Sout, int nS, int nsave, int it, int& wstart, bool force, int lane) {
+    __syncwarp();
+    if ((it & (SB_SWIN - 1)) == SB_SWIN - 1 || it == nsave - 1 || force) {
+        const int w0 = it & ~(SB_SWIN - 1), cnt = (it & (SB_SWIN - 1)) + 1;
+        for (int q = lane; q < nS * SB_SWIN; q += SB_WARP) {
+            const int s = q / SB_SWIN, j = q - s * SB_SWIN;
+            if (j >= wstart && j < cnt) Sout[(size_t)s * nsave + w0 + j] = sbuf[q];
+        }
+        wstart = 0;
+        __syncwarp();
+    }
+}
+
 // Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
 // queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
 // BATCH: every mode carries its own cosmology (A.cosmos[A.cosmo_of[mode]], staged in shared memory per mode) -- one launch over
@@ -955,7 +1057,9 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
 #endif
     double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
            *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
+    double* const sbuf = sm + SB_SM_SBUF;
     const double reltol = A.reltol, abstol = A.abstol;
+    const bool SRC = A.S != nullptr; // fused source evaluation at the save times (scratch: di = state in natural order, up = its derivative, bs = basis)
     SbLane S;
     S.load(lane);
     const SbCosmo& CC = *(BATCH ? reinterpret_cast<const SbCosmo*>(sm + SB_SM_COSMO) : &A.c0);
@@ -992,10 +1096,13 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
         long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
         int rc = SB_RC_SUCCESS, isave = 0;
         double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
+        double* Sout = SRC ? A.S + (size_t)mode * A.nS * A.nsave : nullptr;
+        int wstart = 0; // first valid slot of the current window of source values (see sb_source_flush)
 
         if (!(k > 0) || !isfinite(k)) { // reference: solve fails for k = 0 / NaN (test "Success checking", runtests.jl:358-361)
             for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = NAN;
             if (usave) for (int i = lane; i < A.nsave * SB_N; i += SB_WARP) usave[i] = NAN;
+            if (SRC) for (int i = lane; i < A.nsave * A.nS; i += SB_WARP) Sout[i] = NAN;
             if (lane == 0) { A.retcode[mode] = SB_RC_UNSTABLE; for (int j = 0; j < 4; j++) A.stats[4 * mode + j] = 0; }
             continue;
         }
@@ -1027,6 +1134,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
             for (int i = lane; i < SB_N; i += SB_WARP) u[i] = __ldcg(c + i);
             t = __ldcg(c + SB_N); dt = __ldcg(c + SB_N + 1); ctl.qold = __ldcg(c + SB_N + 2); ctl.q11 = __ldcg(c + SB_N + 3);
             isave = (int)__ldcg(c + SB_N + 4); jt = (int)__ldcg(c + SB_N + 5); it0 = (int)__ldcg(c + SB_N + 6);
+            wstart = isave & (SB_SWIN - 1); // the parking warp has stored the slots before isave of this window
             naccept = (long long)__ldcg(c + SB_N + 7); nreject = (long long)__ldcg(c + SB_N + 8); nf = (long long)__ldcg(c + SB_N + 9); nsolve = (long long)__ldcg(c + SB_N + 10);
             __syncwarp();
         } else {
@@ -1035,7 +1143,17 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
         for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
         __syncwarp();
         while (isave < A.nsave && CC.saveat[isave] <= t) { // save points at (or before) the start
-            for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = (CC.saveat[isave] == t) ? u[i] : NAN;
+            const bool at = CC.saveat[isave] == t;
+            if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = at ? u[i] : NAN;
+            if (SRC) {
+                double* so = sbuf + (isave & (SB_SWIN - 1));
+                if (at) {
+                    for (int i = lane; i < SB_N; i += SB_WARP) di[sb_nat[i]] = u[i];
+                    __syncwarp();
+                    sb_source_point(CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, t, CC.taurec, A.scale_k, A.nS, di, up, bs, bs + SB_NB, so, SB_SWIN, lane);
+                } else if (lane < A.nS) so[lane * SB_SWIN] = NAN;
+                sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
+            }
             isave++;
         }
         }
@@ -1077,6 +1195,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                         c[SB_N] = t; c[SB_N + 1] = dt; c[SB_N + 2] = ctl.qold; c[SB_N + 3] = ctl.q11; c[SB_N + 4] = isave; c[SB_N + 5] = jt; c[SB_N + 6] = it;
                         c[SB_N + 7] = (double)naccept; c[SB_N + 8] = (double)nreject; c[SB_N + 9] = (double)nf; c[SB_N + 10] = (double)nsolve;
                     }
+                    if (SRC && (isave & (SB_SWIN - 1)) != 0) sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave - 1, wstart, true, lane); // partial window of source values
                     parked = true;
                     break;
                 }
@@ -1216,11 +1335,18 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                         dT[i] = a1; f0[i] = a2; Zp[i] = a3;
                     }
                     while (isave < A.nsave && CC.saveat[isave] <= tn) {
-                        double ts = CC.saveat[isave];
-                        if (ts == tn) { for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = U[i] + K[7 * SB_N + i]; }
-                        else {
-                            double th = (ts - t) / dt, t1 = 1 - th;
-                            for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; usave[(size_t)isave * SB_N + sb_nat[i]] = t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i]))); }
+                        const double ts = CC.saveat[isave];
+                        const double th = (ts - t) / dt, t1 = 1 - th;
+                        for (int i = lane; i < SB_N; i += SB_WARP) {
+                            const double un = U[i] + K[7 * SB_N + i];
+                            const double v = (ts == tn) ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
+                            if (usave) usave[(size_t)isave * SB_N + sb_nat[i]] = v;
+                            if (SRC) di[sb_nat[i]] = v;
+                        }
+                        if (SRC) { // the sources at this save time, from the state just formed (reference: output_func of solvept, fourier.jl:272-278)
+                            __syncwarp();
+                            sb_source_point(CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, ts, CC.taurec, A.scale_k, A.nS, di, up, bs, bs + SB_NB, sbuf + (isave & (SB_SWIN - 1)), SB_SWIN, lane);
+                            sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
                         }
                         isave++;
                     }
@@ -1243,7 +1369,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
             continue;
         }
         for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
-        if (usave) for (; isave < A.nsave; isave++) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
+        for (; isave < A.nsave; isave++) { // save times the mode never reached (failed solve)
+            if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
+            if (SRC) { if (lane < A.nS) sbuf[lane * SB_SWIN + (isave & (SB_SWIN - 1))] = NAN; sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane); }
+        }
         if (lane == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
         if (quota > 0 && lane == 0) atomicExch(A.flags + mode, 2);
         __syncwarp();
@@ -1258,9 +1387,7 @@ __global__ void sb_deltam_kernel(const double* __restrict__ P, SbSpline spl, dou
     out[i] = sb_delta_m(tau, ks[i], y, P, u + (size_t)i * SB_N);
 }
 
-// Per-τ background quantities for the CMB sources: one thread per saved time.
-// srcbg[it][0..5] = κ̇, κ̈, κ⃛, exp(−κ), τ0 − τ, spare;  then β_m (NBETA) and flow-derivative dβ_m/dτ (NBETA)
-#define SB_SRCBG_STRIDE (8 + 2 * SB_NBETA)
+// Per-τ background quantities for the CMB sources: one thread per saved time (row layout: see SB_SRCBG_STRIDE above).
 __global__ void sb_srcbg_kernel(const double* __restrict__ P, SbSpline spl, int nt, const double* __restrict__ taus, double* __restrict__ srcbg) {
     int it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= nt) return;
@@ -1272,9 +1399,9 @@ __global__ void sb_srcbg_kernel(const double* __restrict__ P, SbSpline spl, int 
     sb_beta(tau, y, g, P, o + 8, o + 8 + SB_NBETA); // time derivatives along the background flow: dy/dτ = g(y)
 }
 
-// CMB source functions ST, SE (reference src/models/cosmologies.jl:99-104) at every saved (k, τ): one thread per point.
-// Derivatives of unknowns are expanded through the ODE itself (u̇ = J u, ü = J̇ u + J u̇), as MTK does symbolically.
-// out layout: S[ik][iS][it], iS = 0: ST, 1: SE, (nS == 3) 2: Sψ = −(Ψ+Φ)(τ−τrec)/(τ0−τrec)/(τ0−τ) for τ ≥ τrec (lensing source, cosmologies.jl:105)
+// CMB source functions at every saved (k, τ) from states kept in HBM: one thread per point (the fused path inside the integrator,
+// sb_source_point, is what the C_l pipeline uses; this kernel serves callers that asked for the states themselves).
+// out layout: S[ik][iS][it], iS = 0: ST, 1: SE, (nS == 3) 2: Sψ
 __global__ void sb_source_kernel(int nt, const double* __restrict__ taus, const double* __restrict__ srcbg, int nk, const double* __restrict__ ks,
                                  const double* __restrict__ usave, double* __restrict__ S, int scale_k, int nS, double taurec) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1287,37 +1414,10 @@ __global__ void sb_source_kernel(int nt, const double* __restrict__ taus, const 
     for (int e = 0; e < 7; e++) kpw[e] = pow(k, (double)(e - 3));
     double b[SB_NB], bd[SB_NB];
     for (int m = 0; m < SB_NB; m++) { double kk = kpw[sb_basis_kpow[m] + 3]; b[m] = kk * sb[8 + sb_basis_beta[m]]; bd[m] = kk * sb[8 + SB_NBETA + sb_basis_beta[m]]; }
-    // hubs and their time derivatives
-    double Phd = 0, Psi = 0;
-    for (int t = sb_hptr[2]; t < sb_hptr[3]; t++) Phd += sb_hcoef[t] * b[sb_hb[t]] * u[sb_hidx[t]];
-    for (int t = sb_hptr[3]; t < sb_hptr[4]; t++) Psi += sb_hcoef[t] * b[sb_hb[t]] * u[sb_hidx[t]];
+    const double Phd = sb_hub_seq(2, b, u), Psi = sb_hub_seq(3, b, u);
     double ud[SB_N];
-    for (int i = 0; i < SB_N; i++) { double acc = 0; for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * b[sb_bidx[e]] * u[sb_col[e]]; ud[i] = acc; }
-    for (int t = sb_hptr[0]; t < sb_hptr[1]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Phd;
-    for (int t = sb_hptr[1]; t < sb_hptr[2]; t++) ud[sb_hidx[t]] += sb_hcoef[t] * b[sb_hb[t]] * Psi;
-    double Psid = 0;
-    for (int t = sb_hptr[3]; t < sb_hptr[4]; t++) Psid += sb_hcoef[t] * (bd[sb_hb[t]] * u[sb_hidx[t]] + b[sb_hb[t]] * ud[sb_hidx[t]]);
-    // second derivatives of F2, G0, G2 (rows without hub terms): ü_i = J_i(ḃ) u + J_i(b) u̇
-    const int rows3[3] = {SB_I_F2, SB_I_G0, SB_I_G2};
-    double Pig = 0, Pigd = 0, Pigdd = 0;
-    for (int r = 0; r < 3; r++) {
-        int i = rows3[r];
-        double acc = 0;
-        for (int e = sb_rowptr[i]; e < sb_rowptr[i + 1]; e++) acc += sb_coef[e] * (bd[sb_bidx[e]] * u[sb_col[e]] + b[sb_bidx[e]] * ud[sb_col[e]]);
-        Pig += u[i]; Pigd += ud[i]; Pigdd += acc;
-    }
-    const double kd = sb[0], kdd = sb[1], kddd = sb[2], ek = sb[3], chi = sb[4];
-    const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
-    const double thb = u[SB_I_TB], thbd = ud[SB_I_TB];
-    double ST = v * (u[SB_I_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
-    double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
-    if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
-    S[((size_t)ik * nS + 0) * nt + it] = ST;
-    S[((size_t)ik * nS + 1) * nt + it] = SE;
-    if (nS > 2) {
-        const double tau = taus[it];
-        S[((size_t)ik * nS + 2) * nt + it] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
-    }
+    for (int i = 0; i < SB_N; i++) ud[i] = sb_row_dot(i, b, u);
+    sb_source_tail(sb, k, taus[it], taurec, scale_k, nS, b, bd, u, ud, Phd, Psi, S + (size_t)ik * nS * nt + it, nt);
 }
 
 // ================================================================================================ C ABI (device pointers)
@@ -1357,13 +1457,17 @@ int sbm_build_table(const double* dP, int nb, const double* dt, const double* dy
 static int sb_solvept_impl(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
                            const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
                            int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, double* dtrace, int ntrace,
-                           const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags, const SbCosmo* dcosmos = nullptr, const int* dcosmo_of = nullptr) {
+                           const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags, const SbCosmo* dcosmos = nullptr, const int* dcosmo_of = nullptr,
+                           const sbm_src_t* src = nullptr) {
     if (nk <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SbSolveArgs A;
-    A.c0 = SbCosmo{dP, SbSpline{nb, dt, dy, ddy}, SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab}, tend, dsaveat};
+    const bool fused = src && src->dS && nsave > 0;
+    if (fused && (src->nS < 2 || src->nS > 3 || (!dcosmos && !src->dsrcbg))) return -1;
+    A.c0 = SbCosmo{dP, SbSpline{nb, dt, dy, ddy}, SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab}, tend, dsaveat, fused ? src->dsrcbg : nullptr, fused ? src->taurec : 0.0};
     A.cosmos = dcosmos; A.cosmo_of = dcosmo_of;
-    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = dusave ? nsave : 0;
+    A.S = fused ? src->dS : nullptr; A.nS = fused ? src->nS : 0; A.scale_k = fused ? src->scale_k : 0;
+    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = (dusave || fused) ? nsave : 0;
     A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue; A.trace = dtrace; A.ntrace = ntrace;
     A.items = ditems; A.ibeg = dibeg; A.cont = dcont; A.flags = dflags;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
@@ -1421,6 +1525,40 @@ int sbm_solvept_batch(int ncosmo, const void* dcosmos, int nk, const double* dks
     if (ditems && (!dibeg || !dcont || !dflags)) return -1;
     return sb_solvept_impl(nullptr, 0, nullptr, nullptr, nullptr, 1, 1, 0.0, 1.0, nullptr, nullptr, nk, dks, dtini, dorder, 0.0, nsave, nullptr, reltol, abstol, maxiters, dusave, duend, dretcode, dstats,
                            dqueue, 0, stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags, (const SbCosmo*)dcosmos, dcosmo_of);
+}
+// The three solves with the CMB source functions formed INSIDE the integrator at the save times (reference: the output_func of
+// solvept evaluates getsym(prob.pt, Ss) on the dense output and keeps only S, src/observables/fourier.jl:267-281): `src` (host struct)
+// names the output dS[nk][nS][nsave] and, for the single-cosmology calls, the per-save-time background table from sbm_srcbg and
+// taurec (the batched call reads both from each sbm_cosmo_t).  dusave may be NULL: the states then never leave the SM
+// (the round-1 path wrote usave[nk][nsave][N] = 397 MB per cosmology at the bench size and re-read it in a second kernel).
+int sbm_solvept_src(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                    const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                    int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, int nctas, void* stream, const sbm_src_t* src) {
+    return sb_solvept_impl(dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, nctas,
+                           stream, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, src);
+}
+int sbm_solvept_sched_src(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                          const double* dks, const double* dtini, double tend, int nsave, const double* dsaveat, double reltol, double abstol, int maxiters, double* dusave, double* duend,
+                          int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags, void* stream, const sbm_src_t* src) {
+    if (!ditems || !dibeg || !dcont || !dflags) return -1;
+    return sb_solvept_impl(dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, nullptr, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, 0,
+                           stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags, nullptr, nullptr, src);
+}
+int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol, double abstol,
+                          int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg, int nlists, double* dcont, int* dflags,
+                          void* stream, const sbm_src_t* src) {
+    if (ncosmo <= 0 || !dcosmos || !dcosmo_of) return -1;
+    if (ditems && (!dibeg || !dcont || !dflags)) return -1;
+    return sb_solvept_impl(nullptr, 0, nullptr, nullptr, nullptr, 1, 1, 0.0, 1.0, nullptr, nullptr, nk, dks, dtini, dorder, 0.0, nsave, nullptr, reltol, abstol, maxiters, dusave, duend, dretcode, dstats,
+                           dqueue, 0, stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags, (const SbCosmo*)dcosmos, dcosmo_of, src);
+}
+// Per-save-time background table of the source evaluation: dsrcbg[nt][sbm_srcbg_stride()] (κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, the β_m and their
+// flow derivatives at dtaus[nt]); input of sbm_solvept_src / sbm_cosmo_t.srcbg and of sbm_sources.
+int sbm_srcbg(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int nt, const double* dtaus, double* dsrcbg, void* stream) {
+    if (nt <= 0) return 0;
+    sb_srcbg_kernel<<<(nt + 63) / 64, 64, 0, (cudaStream_t)stream>>>(dP, SbSpline{nb, dt, dy, ddy}, nt, dtaus, dsrcbg);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 int sbm_cosmo_bytes(void) { return (int)sizeof(SbCosmo); }
 int sbm_cont_stride(void) { return SB_CONT; }
@@ -1504,7 +1642,8 @@ int sbm_solvept_host(const double* P, int nb, const double* t, const double* y, 
     double *dP, *dt, *dy_, *ddy, *dtab, *dks, *dtini, *dsave, *dus = nullptr, *due, *ddm = nullptr, *dsb = nullptr, *dS = nullptr;
     int *dlut, *dorder, *dret, *dq;
     long long* dst;
-    const bool keep = (usave || S) && nsave > 0;
+    const bool keep = usave && nsave > 0;      // the states are kept only if the caller wants them
+    const bool fuse = S && nsave > 0;          // the sources are formed inside the integrator
     SB_CUDA_CHECK(B.get(&dP, SB_NPAR, P)); SB_CUDA_CHECK(B.get(&dt, nb, t)); SB_CUDA_CHECK(B.get(&dy_, (size_t)nb * 5, y)); SB_CUDA_CHECK(B.get(&ddy, (size_t)nb * 5, dy));
     SB_CUDA_CHECK(B.get(&dtab, ((size_t)(nb - 1) * msub + 1) * 2 * SB_NBETA)); SB_CUDA_CHECK(B.get(&dks, nk, ks)); SB_CUDA_CHECK(B.get(&dtini, nk, tini));
     SB_CUDA_CHECK(B.get(&dsave, nsave, saveat)); SB_CUDA_CHECK(B.get(&dlut, nlut, lut.data())); SB_CUDA_CHECK(B.get(&dorder, nk, order.data()));
@@ -1512,17 +1651,19 @@ int sbm_solvept_host(const double* P, int nb, const double* t, const double* y, 
     if (keep) SB_CUDA_CHECK(B.get(&dus, (size_t)nk * nsave * SB_N));
     int rc = sbm_build_table(dP, nb, dt, dy_, ddy, msub, dtab, nullptr);
     if (rc < 0) return rc;
-    rc = sbm_solvept(dP, nb, dt, dy_, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, keep ? nsave : 0, dsave, reltol, abstol, maxiters, dus, due, dret, dst, dq, 0,
-                     nullptr, nullptr, 0);
+    sbm_src_t src{nullptr, nullptr, nS, scale_k, taurec};
+    if (fuse) {
+        SB_CUDA_CHECK(B.get(&dsb, (size_t)nsave * SB_SRCBG_STRIDE)); SB_CUDA_CHECK(B.get(&dS, (size_t)nk * nS * nsave));
+        rc = sbm_srcbg(dP, nb, dt, dy_, ddy, nsave, dsave, dsb, nullptr);
+        if (rc < 0) return rc;
+        src.dsrcbg = dsb; src.dS = dS;
+    }
+    rc = sbm_solvept_src(dP, nb, dt, dy_, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, (keep || fuse) ? nsave : 0, dsave, reltol, abstol, maxiters, dus, due, dret, dst, dq, 0,
+                         nullptr, fuse ? &src : nullptr);
     if (rc < 0) return rc;
     if (delta_m) {
         SB_CUDA_CHECK(B.get(&ddm, nk));
         rc = sbm_delta_m(dP, nb, dt, dy_, ddy, tend, nk, dks, due, ddm, nullptr);
-        if (rc < 0) return rc;
-    }
-    if (S) {
-        SB_CUDA_CHECK(B.get(&dsb, (size_t)nsave * SB_SRCBG_STRIDE)); SB_CUDA_CHECK(B.get(&dS, (size_t)nk * nS * nsave));
-        rc = sbm_sources(dP, nb, dt, dy_, ddy, nsave, dsave, dsb, nk, dks, dus, dS, scale_k, nS, taurec, nullptr);
         if (rc < 0) return rc;
     }
     SB_CUDA_CHECK(cudaDeviceSynchronize());

@@ -79,7 +79,7 @@ def test_source_functions_match_oracle_given_same_states(sb, oracle, prob5, bg5,
     SAME saved states: 1e-9 relative to the column maximum."""
     ks = sb.ChebyshevInterpolator(1e-2, 2e3, 60).xs[::5].copy()
     _, taus = sb.cmb_grids(bg5)
-    S = sb.source_grid(prob5, taus, ks, bg5, scale_k=False)
+    S = sb.source_grid(prob5, taus, ks, bg5, scale_k=False, keep_states=True)  # sources formed inside the integrator + the states they were formed from
     assert S.sol.success and not np.isnan(S.sol.usave).any()
     oS = oracle.sources(obg_same, ks, taus, S.sol.usave)
     Sg = S.dS.cpu().numpy()
@@ -320,7 +320,7 @@ def test_host_buffer_abi_matches_device_pointer_path(sb, prob5, bg5, jl129):
     rc = prob5.lib.sbm_solvept_host(cp(bg5.P), C.c_int(len(bg5.t)), cp(bg5.t), cp(bg5.y), cp(bg5.dy), C.c_int(nk), cp(ks), cp(tini), C.c_double(bg5.t[-1]), C.c_int(nt), cp(taus),
                                     C.c_double(1e-5), C.c_double(1e-5), C.c_int(100000), cp(usave), cp(uend), cp(ret), cp(stats), cp(dm), C.c_int(2), C.c_double(bg5.taurec), C.c_int(1), cp(S))
     assert rc == 0 and (ret == 0).all()
-    grid = sb.source_grid(prob5, taus, ks, bg5)
+    grid = sb.source_grid(prob5, taus, ks, bg5, keep_states=True)
     sol = grid.sol
     assert np.array_equal(uend, sol.uend) and np.array_equal(usave, sol.d_usave.cpu().numpy().reshape(nk, nt, N))
     assert np.array_equal(stats, sol.stats) and np.array_equal(S, grid.dS.cpu().numpy())
@@ -501,3 +501,40 @@ def test_device_background_batch_matches_host_solver(sb, oracle):
     Pd, id_ = sb.spectrum_matter_sweep(prob, names, th[:6], ks, chunk=6, return_info=True, background="device")
     assert ih["mode_failures"] == 0 and id_["mode_failures"] == 0 and id_["background_failures"] == 0
     assert np.abs(Pd / Ph - 1).max() < 1e-5
+
+
+def test_fused_sources_bit_identical_to_state_path(sb, prob5, bg5):
+    """S(τ,k) formed inside the integrator from the dense output (sbm_solvept_src & co.; reference: output_func of solvept,
+    src/observables/fourier.jl:272-278) equals, bit for bit, the sources evaluated by the stand-alone kernel from states written to
+    HBM (sbm_sources) -- for the queue, for the static schedule (modes parked in the middle of a 16-slot store window), for 2 and 3
+    sources, for save counts that are not multiples of the window, for a save time at the very start of the integration and for a
+    failed mode (k = 0: NaN rows)."""
+    import warnings
+    ks = np.concatenate([[0.0], np.linspace(0.5, 400.0, 150)])
+    for nt, lens in ((37, False), (48, True), (5, True)):
+        taus = np.geomspace(bg5.t[0] if nt == 37 else 1e-3, bg5.tau0, nt)  # nt = 37: the first save time IS the start of the integration
+        taus[0], taus[-1] = max(taus[0], bg5.t[0]), bg5.t[-1]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = sb.source_grid(prob5, taus, ks, bg5, lensing=lens, fused=False)
+            a = sb.source_grid(prob5, taus, ks, bg5, lensing=lens)
+            att = ref.sol.stats[:, 0] + ref.sol.stats[:, 1]
+            b = sb.source_grid(prob5, taus, ks, bg5, lensing=lens, cost=np.maximum(att, 1) * 0.7)
+        R = ref.dS.cpu().numpy()
+        assert R.shape == (len(ks), 3 if lens else 2, nt) and np.isnan(R[0]).all() and np.isfinite(R[1:, 0, :-1]).all()
+        assert a.sol.d_usave is None and np.array_equal(a.dS.cpu().numpy(), R, equal_nan=True)
+        assert np.array_equal(b.dS.cpu().numpy(), R, equal_nan=True)
+        assert np.array_equal(a.sol.stats, ref.sol.stats) and np.array_equal(a.sol.uend, ref.sol.uend, equal_nan=True)
+    # batched launch: every cosmology with its own save times and background table
+    M = sb.ΛCDM(lmax=5)
+    pars = sb.parameters_Planck18(M)
+    pars["Omega_c"] *= 1.07
+    b2 = sb.solvebg(sb.CosmologyProblem(M, pars))
+    kk = [np.geomspace(0.3, 300, 21), np.array([5.0, 50.0, 500.0])]
+    sv = [np.geomspace(1e-3, bg5.tau0, 19), np.geomspace(2e-3, b2.tau0, 19)]
+    for t in sv:
+        t[-1] = min(t[-1], bg5.t[-1], b2.t[-1])
+    batch = sb.solvept_batch([bg5, b2], kk, saveat=sv, sources=dict(nS=2, scale_k=True), keep_states=False)
+    for bg, k, t, sol in zip([bg5, b2], kk, sv, batch.sols):
+        one = sb.source_grid(bg.prob, t, k, bg, fused=False)
+        assert sol.d_usave is None and np.array_equal(sol.d_S.cpu().numpy(), one.dS.cpu().numpy(), equal_nan=True)
