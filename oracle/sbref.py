@@ -405,16 +405,20 @@ def cmb_grids(bg, kmin=1e-2, kmax=2e3, dkt0=np.pi, ntau=300, taucut=1e-2):
 
 
 def spectrum_cmb(modes, bg, jl, normalization="Cl", kmin=1e-2, kmax=2e3, order=60, dkt0=np.pi, ntau=300, taucut=1e-2,
-                 direct=False, reltol=1e-5, abstol=1e-5, nthreads=0, return_all=False, ks=None):
+                 direct=False, reltol=1e-5, abstol=1e-5, nthreads=0, return_all=False, ks=None, taus=None):
     """Mirror of spectrum_cmb(modes, prob, jl) for T/E modes (src/observables/angular.jl:260-341).
     direct=True solves every fine k instead of interpolating from the Chebyshev nodes.
     ks: solve exactly these (ascending) wavenumbers directly and use them as the k-quadrature grid (bounded samples of the
-    direct workload for the CPU baseline timing in bench.py)."""
+    direct workload for the CPU baseline timing in bench.py).  taus: use these line-of-sight times instead of the default grid."""
     ls = np.asarray(jl.l)
     tau0 = bg.tau0
-    ks_fine, taus = cmb_grids(bg, kmin, kmax, dkt0, ntau, taucut)
+    ks_fine, taus_default = cmb_grids(bg, kmin, kmax, dkt0, ntau, taucut)
+    if taus is None:
+        taus = taus_default
     if ks is not None:
         ks_fine, direct = np.ascontiguousarray(ks, dtype=float), True
+    if taus is not None:  # line-of-sight times given by the caller (the default grid is anchored on a background SOLVER STEP, angular.jl:280-286)
+        taus = np.ascontiguousarray(taus, dtype=float)
     ks_coarse = ks_fine if direct else chebpoints(order, kmin, kmax)
     sol = solvept(bg, ks_coarse, ptivini=-np.inf, saveat=taus, reltol=reltol, abstol=abstol, nthreads=nthreads)
     S = sources(bg, ks_coarse, taus, sol["usave"])  # [nk, nτ, 6]

@@ -897,7 +897,8 @@ def source_grid(prob, taus, ks, bgsol, scale_k=True, lensing=False, fused=True, 
     (reference source_grid(prob, Ss, τs, ks, bgsol), src/observables/fourier.jl:267-281 with Ss of angular.jl:293).
     fused (default): the sources are formed inside the integrator from the dense output, as the reference's output_func does, and only
     S[nk][nS][nτ] reaches HBM (keep_states = True additionally returns the states in .sol.d_usave).  fused = False: the states
-    usave[nk][nτ][N] are written and a second kernel (`sbm_sources`) evaluates the sources from them -- same bits, 40× the traffic."""
+    usave[nk][nτ][N] are written and a second kernel (`sbm_sources`) evaluates the sources from them -- the same algebra (results
+    agree to rounding), 40× the traffic."""
     taus = np.ascontiguousarray(taus, dtype=np.float64)
     if taus.min() < bgsol.t[0] or taus.max() > bgsol.t[-1]:
         raise ValueError("input τs and computed background solution have different timespans")
@@ -1228,10 +1229,13 @@ class CMBPlan:
         self.launches_resident, self.launches_e2e = (3, 5) if self.fused else (5, 6)
         self.cost_model, self.d_items = None, None
 
-    def learn_schedule(self, model=None):
+    def learn_schedule(self, model=None, save_cost=None):
         """Switch the perturbation launch from the atomic queue to the static preemptive schedule (`build_schedule`), with the
         per-mode cost taken from `model` (a ModeCostModel) or learnt from the step counters of this plan's last solve
-        (blocking read of 64 KB).  Returns the model so that other plans / later cosmologies can reuse it."""
+        (blocking read of 64 KB).  Returns the model so that other plans / later cosmologies can reuse it.
+        save_cost: cost of one save point (dense output + fused source evaluation) in units of a Rosenbrock attempt; the same for every
+        mode, so it matters for lists that hold many short modes."""
+        save_cost = (0.12 if self.fused else 0.03) if save_cost is None else save_cost
         lib = self.prob.lib
         if model is None:
             st = self.d_stats.cpu().numpy()
@@ -1239,7 +1243,7 @@ class CMBPlan:
         self.cost_model = model
         wpc = int(lib.sbm_warps_per_cta())
         self.nlists = max(wpc, min(int(lib.sbm_resident_warps()), self.nk) // wpc * wpc)
-        items, ibeg, self.sched_T = build_schedule(model(self.ks_solve), self.nlists)
+        items, ibeg, self.sched_T = build_schedule(model(self.ks_solve) + save_cost * self.nt, self.nlists)
         self.d_items, self.d_ibeg = torch.from_numpy(items).to(self.dev), torch.from_numpy(ibeg).to(self.dev)
         self.d_cont = torch.empty(self.nk * int(lib.sbm_cont_stride()), dtype=torch.float64, device=self.dev)
         self.d_flags = torch.zeros(self.nk, dtype=torch.int32, device=self.dev)

@@ -610,6 +610,8 @@ def generate(m: Model):
     W(f"#define SB_EOFF(r) ({_sel(eoff)})  // first ELL slot of round r")
     W(_arr("short", "sb_nat", nat))
     W(_arr("short", "sb_newidx", inv))
+    for nm in ["Phi", "tb", "F0", "F2", "G0", "G2"]:  # the same unknowns in the integrator's (path-contiguous) order: fused source evaluation
+        W(f"#define SB_J_{nm.upper()} {inv[m.unames.index(nm)]}")
     W(_arr("double", "sb_ell_coef", ell_coef, "{!r}"))
     W(_arr("unsigned int", "sb_ell_idx", ell_idx, "{}u"))
     W(_arr("double", "sb_pq_coef", pq_coef, "{!r}"))

@@ -560,7 +560,8 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
 // out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU.
 // FUSE: out = J(b)·U + radd[r] + hd·dT  (the stage right-hand side is assembled in the same pass: one store per row)
 template <bool FUSE>
-__device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane, const double* radd = nullptr, double hd = 0.0, const double* dT = nullptr) {
+__device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane, const double* radd = nullptr, double hd = 0.0, const double* dT = nullptr,
+                                          double* hubs = nullptr /* out: Φ̇ = φᵀU, Ψ = ψᵀU */) {
     double sphi = 0, spsi = 0;
 #pragma unroll
     for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[SB_HI16(S.phi[t])] * U[SB_LO16(S.phi[t])];
@@ -589,6 +590,7 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
         if (FUSE) { if (i < SB_N) a_ += radd[r] + hd * dT[i]; }
         if (i < SB_N) out[i] = a_;
     }
+    if (hubs) { hubs[0] = sphi; hubs[1] = spsi; }
     __syncwarp();
 }
 // ∂f/∂τ = J'u with J' = J_local(ḃ) + ṗ φᵀ + p φ̇ᵀ + q̇ ψᵀ + q ψ̇ᵀ
@@ -997,30 +999,6 @@ __device__ __forceinline__ void sb_source_tail(const double* sb, double k, doubl
     out[ostride] = SE;
     if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
 }
-// Warp-cooperative evaluation at one save time inside the integrator.  Not inlined: it is called ≈300 times per mode against
-// ≈2000 Rosenbrock attempts, and keeping it out of line keeps its registers out of the step loop.  un: saved state in natural
-// order, ud/b/bd: scratch (all in the warp's shared memory); out[s * ostride] receives source s (written by lane 0).
-__device__ __noinline__ void sb_source_point(const double* __restrict__ sb, const double* kp, double k, double tau, double taurec, int scale_k, int nS, const double* un, double* ud, double* b,
-                                             double* bd, double* out, int ostride, int lane) {
-    for (int m = lane; m < SB_NB; m += SB_WARP) {
-        const double kk = kp[sb_basis_kpow[m] + 3];
-        b[m] = kk * __ldg(sb + 8 + sb_basis_beta[m]);
-        bd[m] = kk * __ldg(sb + 8 + SB_NBETA + sb_basis_beta[m]);
-    }
-    __syncwarp();
-    double Phd = 0, Psi = 0;
-    if (lane == 0) Phd = sb_hub_seq(2, b, un);
-    if (lane == 1) Psi = sb_hub_seq(3, b, un);
-    Phd = __shfl_sync(SB_FULL, Phd, 0); Psi = __shfl_sync(SB_FULL, Psi, 1);
-    for (int i = lane; i < SB_N; i += SB_WARP) ud[i] = sb_row_dot(i, b, un);
-    __syncwarp();
-    if (lane == 0) {
-        double sbl[5];
-        for (int j = 0; j < 5; j++) sbl[j] = __ldg(sb + j);
-        sb_source_tail(sbl, k, tau, taurec, scale_k, nS, b, bd, un, ud, Phd, Psi, out, ostride);
-    }
-    __syncwarp();
-}
 // Coalesced store of the window of source values: lane 0 has put the sources of save index `it` into sbuf[s][it % SB_SWIN]; when the
 // window is full (or the mode's last save time is reached) the lanes write it as contiguous runs of S[s][w0 .. w0+cnt).  wstart: first
 // valid slot of the window (non-zero only right after a parked mode was resumed in the middle of a window).
@@ -1035,6 +1013,57 @@ __device__ __forceinline__ void sb_source_flush(const double* sbuf, double* Sout
         wstart = 0;
         __syncwarp();
     }
+}
+
+// Warp-cooperative evaluation at one save time inside the integrator, on the integrator's own register-resident schedule (the
+// generated CSR tables of the stand-alone kernel live in global memory: walking them from here costs an L2 round trip per entry,
+// which made a source point as expensive as half a Rosenbrock attempt).  u: the saved state in the integrator's order, ud/b/bd:
+// scratch (all in the warp's shared memory); out[s * ostride] receives source s (written by lane 0).  Same algebra as
+// sb_source_tail; the sums run in a different order (lanes + butterfly), so results agree with it to rounding, not bit for bit.
+__device__ __forceinline__ void sb_source_point(const SbLane& S, const double* __restrict__ sb, const double* kp, double k, double tau, double taurec, int scale_k, int nS, const double* u,
+                                                double* ud, double* b, double* bd, double* out, int ostride, int lane) {
+#pragma unroll
+    for (int r = 0; r < SB_NBR; r++) {
+        const int m = r * 32 + lane;
+        if (m < SB_NB) {
+            const int be = SB_LO16(S.bp[r]);
+            const double kk = kp[SB_HI16(S.bp[r])];
+            b[m] = kk * __ldg(sb + 8 + be);
+            bd[m] = kk * __ldg(sb + 8 + SB_NBETA + be);
+        }
+    }
+    __syncwarp();
+    double hub[2];
+    sb_eval_f<false>(S, b, u, ud, lane, nullptr, 0.0, nullptr, hub); // u̇ = J u (hub columns included), Φ̇, Ψ
+    const double Phd = hub[0], Psi = hub[1];
+    // Ψ̇ = ψ̇ᵀu + ψᵀu̇ and Π̈ = Σ_{F2,G0,G2} (J̇_i u + J_i u̇) (rows without hub terms), reduced together
+    double a = 0, pdd = 0;
+#pragma unroll
+    for (int t = 0; t < SB_TPS; t++) a += S.psc[t] * (bd[SB_HI16(S.psi[t])] * u[SB_LO16(S.psi[t])] + b[SB_HI16(S.psi[t])] * ud[SB_LO16(S.psi[t])]);
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) {
+        const int i = r * 32 + lane;
+        if (i == SB_J_F2 || i == SB_J_G0 || i == SB_J_G2) {
+#pragma unroll
+            for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; pdd += S.ec[e] * (bd[SB_E_B(S.ei[e])] * u[SB_E_COL(S.ei[e])] + b[SB_E_B(S.ei[e])] * ud[SB_E_COL(S.ei[e])]); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(SB_FULL, a, o); pdd += __shfl_xor_sync(SB_FULL, pdd, o); }
+    if (lane == 0) {
+        const double Psid = a, Pigdd = pdd;
+        const double Pig = u[SB_J_F2] + u[SB_J_G0] + u[SB_J_G2], Pigd = ud[SB_J_F2] + ud[SB_J_G0] + ud[SB_J_G2];
+        const double kd = __ldg(sb), kdd = __ldg(sb + 1), kddd = __ldg(sb + 2), ek = __ldg(sb + 3), chi = __ldg(sb + 4);
+        const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
+        const double thb = u[SB_J_TB], thbd = ud[SB_J_TB];
+        double ST = v * (u[SB_J_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
+        double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
+        if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
+        out[0] = ST;
+        out[ostride] = SE;
+        if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_J_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
+    }
+    __syncwarp();
 }
 
 // Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
@@ -1148,9 +1177,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
             if (SRC) {
                 double* so = sbuf + (isave & (SB_SWIN - 1));
                 if (at) {
-                    for (int i = lane; i < SB_N; i += SB_WARP) di[sb_nat[i]] = u[i];
-                    __syncwarp();
-                    sb_source_point(CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, t, CC.taurec, A.scale_k, A.nS, di, up, bs, bs + SB_NB, so, SB_SWIN, lane);
+                    sb_source_point(S, CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, t, CC.taurec, A.scale_k, A.nS, u, up, bs, bs + SB_NB, so, SB_SWIN, lane);
                 } else if (lane < A.nS) so[lane * SB_SWIN] = NAN;
                 sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
             }
@@ -1341,11 +1368,11 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                             const double un = U[i] + K[7 * SB_N + i];
                             const double v = (ts == tn) ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
                             if (usave) usave[(size_t)isave * SB_N + sb_nat[i]] = v;
-                            if (SRC) di[sb_nat[i]] = v;
+                            if (SRC) di[i] = v;
                         }
                         if (SRC) { // the sources at this save time, from the state just formed (reference: output_func of solvept, fourier.jl:272-278)
                             __syncwarp();
-                            sb_source_point(CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, ts, CC.taurec, A.scale_k, A.nS, di, up, bs, bs + SB_NB, sbuf + (isave & (SB_SWIN - 1)), SB_SWIN, lane);
+                            sb_source_point(S, CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, ts, CC.taurec, A.scale_k, A.nS, di, up, bs, bs + SB_NB, sbuf + (isave & (SB_SWIN - 1)), SB_SWIN, lane);
                             sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
                         }
                         isave++;

@@ -503,12 +503,13 @@ def test_device_background_batch_matches_host_solver(sb, oracle):
     assert np.abs(Pd / Ph - 1).max() < 1e-5
 
 
-def test_fused_sources_bit_identical_to_state_path(sb, prob5, bg5):
+def test_fused_sources_match_state_path(sb, prob5, bg5):
     """S(τ,k) formed inside the integrator from the dense output (sbm_solvept_src & co.; reference: output_func of solvept,
-    src/observables/fourier.jl:272-278) equals, bit for bit, the sources evaluated by the stand-alone kernel from states written to
-    HBM (sbm_sources) -- for the queue, for the static schedule (modes parked in the middle of a 16-slot store window), for 2 and 3
-    sources, for save counts that are not multiples of the window, for a save time at the very start of the integration and for a
-    failed mode (k = 0: NaN rows)."""
+    src/observables/fourier.jl:272-278) against the sources evaluated by the stand-alone kernel from states written to HBM
+    (sbm_sources): the same algebra with sums in a different order -> 1e-11 of each row's maximum; identical NaN pattern (failed
+    k = 0 mode); identical step counters and final states.  The fused result itself must not depend on the work distribution:
+    queue, static schedule (modes parked in the middle of a 16-slot store window) and batched launch agree BIT FOR BIT, for 2 and 3
+    sources, save counts that are not multiples of the window and a save time at the very start of the integration."""
     import warnings
     ks = np.concatenate([[0.0], np.linspace(0.5, 400.0, 150)])
     for nt, lens in ((37, False), (48, True), (5, True)):
@@ -520,10 +521,13 @@ def test_fused_sources_bit_identical_to_state_path(sb, prob5, bg5):
             a = sb.source_grid(prob5, taus, ks, bg5, lensing=lens)
             att = ref.sol.stats[:, 0] + ref.sol.stats[:, 1]
             b = sb.source_grid(prob5, taus, ks, bg5, lensing=lens, cost=np.maximum(att, 1) * 0.7)
-        R = ref.dS.cpu().numpy()
+        R, Af = ref.dS.cpu().numpy(), a.dS.cpu().numpy()
         assert R.shape == (len(ks), 3 if lens else 2, nt) and np.isnan(R[0]).all() and np.isfinite(R[1:, 0, :-1]).all()
-        assert a.sol.d_usave is None and np.array_equal(a.dS.cpu().numpy(), R, equal_nan=True)
-        assert np.array_equal(b.dS.cpu().numpy(), R, equal_nan=True)
+        assert a.sol.d_usave is None and np.array_equal(np.isnan(Af), np.isnan(R))
+        fin = np.isfinite(R)
+        scale = np.nanmax(np.where(fin, np.abs(R), 0.0), axis=2, keepdims=True)
+        assert (np.abs(np.where(fin, Af - R, 0.0)) <= 1e-11 * scale).all()
+        assert np.array_equal(b.dS.cpu().numpy(), Af, equal_nan=True)
         assert np.array_equal(a.sol.stats, ref.sol.stats) and np.array_equal(a.sol.uend, ref.sol.uend, equal_nan=True)
     # batched launch: every cosmology with its own save times and background table
     M = sb.ΛCDM(lmax=5)
@@ -536,5 +540,5 @@ def test_fused_sources_bit_identical_to_state_path(sb, prob5, bg5):
         t[-1] = min(t[-1], bg5.t[-1], b2.t[-1])
     batch = sb.solvept_batch([bg5, b2], kk, saveat=sv, sources=dict(nS=2, scale_k=True), keep_states=False)
     for bg, k, t, sol in zip([bg5, b2], kk, sv, batch.sols):
-        one = sb.source_grid(bg.prob, t, k, bg, fused=False)
+        one = sb.source_grid(bg.prob, t, k, bg)
         assert sol.d_usave is None and np.array_equal(sol.d_S.cpu().numpy(), one.dS.cpu().numpy(), equal_nan=True)
