@@ -33,9 +33,17 @@ const char* sbm_key(void);
 
 /* Background + thermodynamics solve on the host (replaces solvebg, src/solve.jl:427-435, with the "today" callback of
  * src/solve.jl:158-202 and the spline construction of src/utils.jl:118-127).  Writes the nb Hermite-spline knots
- * t[nb], y[nb][5] = (a, _κ, XH+, XHe+, ΔT), dy[nb][5]; info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
+ * t[nb], y[nb][5] = (a, _κ, XH+, XHe+, ΔT), dy[nb][5]; info[0..7] = tau0, kappa0, taurec, retcode, naccept, nreject, length of the
+ * solver step in which a crossed 1, 0.
  * Returns nb, or -1 if cap is too small. */
 int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info);
+
+/* The same solve in LOCKSTEP with a finished one (parameter lanes of the sensitivity path, BASELINE config 5): takes the knots
+ * tfix[nfix] of the primal solve and the length dtlast of its event step (the primal's info[6]) instead of choosing steps, without
+ * error control, so that the result is a smooth function of the parameters -- the frozen-step discrete map is what the reference's
+ * ForwardDiff duals differentiate (parameters as Duals through solvebg, src/solve.jl:278-284, test/runtests.jl:363-422).
+ * info as sbm_solvebg, info[6] = length of the event step, info[7] = 1 if the knot count differs from nfix (lockstep lost). */
+int sbm_solvebg_lock(const double* P, double tini, double tmax, int nfix, const double* tfix, double dtlast, int cap, double* t, double* y, double* dy, double* info);
 
 /* The same background solve for n cosmologies in one kernel launch, one thread per cosmology (parameter sweeps: the reference
  * calls solvebg once per θ on the host, docs/src/forecasting.md:56-59 -> src/solve.jl:427-435).
@@ -121,6 +129,18 @@ int sbm_solvept_sched_src(const double* dP, int nb, const double* dt, const doub
 int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
                           double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const int* ditems, const int* dibeg,
                           int nlists, double* dcont, int* dflags, void* stream, const sbm_src_t* src);
+/* Parameter lanes in lockstep ("dual-number lanes in the batched solve", BASELINE config 5; replaces ForwardDiff.Dual parameters pushed
+ * through solvept, test/runtests.jl:363-422): G = ncosmo <= 8 neighbouring cosmologies -- lane 0 the primal, lane j >= 1 with one parameter
+ * moved by delta_j -- are integrated for the same nk wavenumbers by CTAs of G warps sharing ONE step controller, whose error norm covers
+ * the primal and the partials (u^j - u^0) * invdelta[j] (OrdinaryDiffEq's norm of Dual numbers).  With shared, frozen steps
+ * (u^j - u^0) / delta_j is the derivative of the discrete solution map, as forward-mode AD gives it, up to O(delta), at the cost of G
+ * solves running side by side.  Layout [mode][lane]: dks, dtini, dcosmo_of have nk*G entries (dks[m*G+j] = k_m, dcosmo_of[m*G+j] = j),
+ * outputs likewise (duend[nk*G][N], dretcode[nk*G], dstats[nk*G][4], src->dS[nk*G][nS][nsave], dusave optional).  dorder: optional
+ * order of the nk groups; invdelta: HOST array of G doubles ([0] unused).  Save decisions and the end of the integration follow the
+ * primal's save times / end time; each lane interpolates at its own.  Returns the grid size or a negative error. */
+int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
+                      double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, void* stream,
+                      const sbm_src_t* src);
 /* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
  * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
  * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */

@@ -21,3 +21,15 @@ jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * bg.tau0)
 print(sb.spectrum_cmb(["TT", "EE"], prob, jl, bgsol=bg)[:, 0])
 d = sb.solvebg_batch([prob, prob])
 print("device bg tau0", d[0].tau0, bg.tau0)
+# round 2: fused sources (queue, static schedule with parking, batched) and the lockstep parameter lanes
+taus = np.geomspace(1e-3, bg.tau0, 21); taus[-1] = bg.t[-1]
+a = sb.source_grid(prob, taus, ks, bg)
+b = sb.source_grid(prob, taus, ks, bg, cost=np.array([300.0, 500.0, 1200.0, 2500.0]))
+c = sb.solvept_batch([bg, bg], ks, saveat=[taus, taus], sources=dict(nS=3, scale_k=True), keep_states=False)
+torch.cuda.synchronize()
+print("fused: sched == queue", np.array_equal(a.dS.cpu().numpy(), b.dS.cpu().numpy(), equal_nan=True), "finite", bool(np.isfinite(c.sols[1].d_S.cpu().numpy()[:, :, :-1]).all()))
+J = sb.sensitivity_matter(prob, ["Omega_c", "Omega_b", "ns"], ks[:3])
+ls2 = np.array([30, 300])
+Jc = sb.sensitivity_cmb("TT", prob, ["Omega_c", "h"], sb.SphericalBesselCache(ls2, xmax=2.1e3 * bg.tau0), kinterp=sb.ChebyshevInterpolator(1e-2, 400.0, 12))
+torch.cuda.synchronize()
+print("lanes dlnP/dlnθ", J[0], "dlnD_l/dlnθ", Jc[0])

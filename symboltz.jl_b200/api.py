@@ -240,6 +240,7 @@ class BackgroundSolution:
         self.prob, self.t, self.y, self.dy = prob, t, y, dy
         self.tau0, self.kappa0, self.taurec = float(info[0]), float(info[1]), float(info[2])
         self.retcode, self.naccept, self.nreject = int(info[3]), int(info[4]), int(info[5])
+        self.dtevent = float(info[6]) if len(info) > 6 else 0.0  # length of the solver step in which a crossed 1 (lockstep lanes re-take it)
         self.P = prob.P.copy()
         self.P[prob.iP_kappa0], self.P[prob.iP_tau0] = self.kappa0, self.tau0  # callback semantics, src/solve.jl:183-189
         self._dev = None
@@ -287,6 +288,22 @@ def solvebg(prob, reltol=1e-7, abstol=1e-7):
     if not sol.success:
         warnings.warn(f"Background solution failed with return code {RETCODES.get(sol.retcode)}.\nCheck the parameters and precision settings!")
     return sol
+
+
+def solvebg_lock(prob, primal):
+    """Background of `prob` in LOCKSTEP with the finished solve `primal` of a neighbouring cosmology (`sbm_solvebg_lock`): the same
+    step sequence (knots) and event step, no error control -- the result is then a smooth function of the parameters, which is what the
+    parameter lanes of `sensitivity_matter` / `sensitivity_cmb` difference (the reference pushes ForwardDiff duals through the same
+    Rodas5P steps, src/solve.jl:278-284)."""
+    nfix = len(primal.t)
+    cap = nfix + 64
+    t, y, dy, info = np.zeros(cap), np.zeros((cap, 5)), np.zeros((cap, 5)), np.zeros(8)
+    prob.lib.sbm_solvebg_lock.restype = C.c_int
+    nb = prob.lib.sbm_solvebg_lock(_cptr(prob.P), C.c_double(prob.ivspan[0]), C.c_double(prob.ivspan[1]), C.c_int(nfix), _cptr(np.ascontiguousarray(primal.t)), C.c_double(primal.dtevent),
+                                   C.c_int(cap), _cptr(t), _cptr(y), _cptr(dy), _cptr(info))
+    if nb != nfix or info[7] != 0 or info[3] != 0:
+        raise RuntimeError(f"lockstep background lost the primal's step sequence ({nb} knots for {nfix}, retcode {RETCODES.get(int(info[3]))}): the parameter step is too large")
+    return BackgroundSolution(prob, t[:nb].copy(), y[:nb].copy(), dy[:nb].copy(), info)
 
 
 def solvebg_batch(probs, reltol=1e-7, abstol=1e-7, cap=4096, warn=True):
@@ -708,6 +725,79 @@ def solvept_batch(bgsols, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, savea
         sols.append(PerturbationSolution(b.prob, b, ks_list[i], tini[a:e], None if saveat is None else saveat[i], uend[a:e], None if usave is None else usave[a:e], retcode[a:e], stats[a:e], dks[a:e]))
         sols[-1].d_S = None if dS is None else dS[a:e]
     return BatchSolution(sols, offsets, uend, usave, retcode, stats, keep=(arena, dcos, dkt, dcof, dorder, queue, ditems, dibeg, dcont, dflags, dsaves, dsb, dS))
+
+
+def solvept_lanes(bgsols, ks, invdelta, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, sources=None, keep_states=False):
+    """Perturbation solve of G = len(bgsols) ≤ 8 neighbouring cosmologies (lane 0: the primal; lane j: one parameter moved by δ_j =
+    1/invdelta[j]) for the SAME wavenumbers `ks` in lockstep: one CTA of G warps per mode, ONE step controller whose error norm covers
+    the primal and the partials (u^j − u^0)/δ_j (`sbm_solvept_lanes`; BASELINE config 5 "dual-number lanes in the batched solve";
+    reference: Dual parameters through solvept, test/runtests.jl:363-422).  saveat: one array of save times per lane (equal lengths;
+    save decisions follow the primal's).  Returns one PerturbationSolution per lane (contiguous per-lane arrays)."""
+    _require_cuda()
+    G = len(bgsols)
+    prob = bgsols[0].prob
+    if not 2 <= G <= 8:
+        raise ValueError("solvept_lanes: 2 to 8 lanes")
+    if any(b.prob.N != prob.N or b.prob.lib._name != prob.lib._name for b in bgsols):
+        raise ValueError("solvept_lanes: all lanes must share one model structure")
+    ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
+    nk = len(ks)
+    f = ptivini if callable(ptivini) else (lambda k: ptivini)
+    b0 = bgsols[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tini = np.array([min(max(f(k), b0.t[0]), b0.t[-1]) if k == k else b0.t[0] for k in ks], dtype=np.float64)
+    dev = torch.device("cuda")
+    ns, dsaves = 0, [None] * G
+    if saveat is not None:
+        saveat = [np.ascontiguousarray(sv, dtype=np.float64) for sv in saveat]
+        ns = len(saveat[0])
+        if len(saveat) != G or any(len(sv) != ns for sv in saveat):
+            raise ValueError("solvept_lanes: need one saveat array per lane, all of the same length")
+        dsv = _h2d(np.stack(saveat), dev)
+        dsaves = [dsv[i] for i in range(G)]
+    arena = CosmoArena()
+    recs = arena.load(bgsols, msub)
+    src, dS, dsb = None, None, None
+    if sources is not None and ns > 0:
+        nS, sk, _ = _src_request(sources)
+        dsb = torch.empty((G, ns, int(prob.lib.sbm_srcbg_stride())), dtype=torch.float64, device=dev)
+        for i, v in enumerate(arena.views):
+            rc = prob.lib.sbm_srcbg(_cptr(v["P"]), C.c_int(v["nb"]), _cptr(v["t"]), _cptr(v["y"]), _cptr(v["dy"]), C.c_int(ns), _cptr(dsaves[i]), _cptr(dsb[i]), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_srcbg failed with code {rc}")
+            recs[i]["srcbg"] = dsb[i].data_ptr()
+        dS = torch.empty((nk * G, nS, ns), dtype=torch.float64, device=dev)
+        src = SbmSrc(None, dS.data_ptr(), nS, sk, 0.0)
+    for i in range(G):
+        recs[i]["saveat"] = 0 if dsaves[i] is None else dsaves[i].data_ptr()
+    dcos = _h2d(np.frombuffer(recs.tobytes(), dtype=np.uint8).reshape(G, COSMO_DTYPE.itemsize).copy(), dev)
+    dkt = _h2d(np.concatenate([np.repeat(ks, G), np.repeat(tini, G)]), dev)
+    dks, dtini = dkt[:nk * G], dkt[nk * G:]
+    dcof = _h2d(np.tile(np.arange(G, dtype=np.int32), nk), dev)
+    dorder = _h2d(np.argsort(-np.nan_to_num(ks, nan=0.0), kind="stable").astype(np.int32), dev)
+    N = prob.N
+    uend = torch.empty((nk * G, N), dtype=torch.float64, device=dev)
+    usave = torch.empty((nk * G, ns, N), dtype=torch.float64, device=dev) if (ns and (keep_states or src is None)) else None
+    retcode = torch.empty(nk * G, dtype=torch.int32, device=dev)
+    stats = torch.empty((nk * G, 4), dtype=torch.int64, device=dev)
+    queue = torch.zeros(1, dtype=torch.int32, device=dev)
+    invd = np.ascontiguousarray(np.concatenate([[0.0], np.asarray(invdelta, dtype=np.float64)[1:G]]) if len(invdelta) == G else np.concatenate([[0.0], np.asarray(invdelta, dtype=np.float64)]))
+    if len(invd) != G:
+        raise ValueError("solvept_lanes: invdelta needs one entry per lane (the primal's is ignored) or one per non-primal lane")
+    prob.lib.sbm_solvept_lanes.restype = C.c_int
+    rc = prob.lib.sbm_solvept_lanes(C.c_int(G), _cptr(dcos), C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dcof), _cptr(dorder), C.c_int(ns), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                    _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(invd), _stream(), C.byref(src) if src is not None else None)
+    if rc < 0:
+        raise RuntimeError(f"sbm_solvept_lanes failed with code {rc}")
+    sols = []
+    for j, b in enumerate(bgsols):  # [mode][lane] -> contiguous per-lane arrays
+        sol = PerturbationSolution(b.prob, b, ks, tini, None if saveat is None else saveat[j], uend.view(nk, G, N)[:, j].contiguous(),
+                                   None if usave is None else usave.view(nk, G, ns, N)[:, j].contiguous(), retcode.view(nk, G)[:, j].contiguous(), stats.view(nk, G, 4)[:, j].contiguous(),
+                                   dks.view(nk, G)[:, j].contiguous())
+        sol.d_S = None if dS is None else dS.view(nk, G, dS.shape[1], ns)[:, j].contiguous()
+        sols.append(sol)
+    sols[0]._keep = (arena, dcos, dkt, dcof, dorder, queue, dsaves, dsb)
+    return sols
 
 
 class CosmologySolution:
@@ -1235,7 +1325,7 @@ class CMBPlan:
         (blocking read of 64 KB).  Returns the model so that other plans / later cosmologies can reuse it.
         save_cost: cost of one save point (dense output + fused source evaluation) in units of a Rosenbrock attempt; the same for every
         mode, so it matters for lists that hold many short modes."""
-        save_cost = (0.12 if self.fused else 0.03) if save_cost is None else save_cost
+        save_cost = (0.2 if self.fused else 0.05) if save_cost is None else save_cost  # measured: scripts/ab_fused.py (profiles/integrate_r2.md)
         lib = self.prob.lib
         if model is None:
             st = self.d_stats.cpu().numpy()
@@ -1564,23 +1654,124 @@ def _central_log_points(theta0, relstep):
     return np.array(pts), h
 
 
-def sensitivity_matter(prob, names, ks, relstep=1e-3, **kw):
-    """∂ln P(k)/∂ln θ_j by central differences over a batched launch of the 2p perturbed cosmologies (BASELINE config 5's
-    quantity; the reference obtains it with ForwardDiff duals through the whole solve and tests it against exactly this
-    finite difference, runtests.jl:363-376).  Returns [nk, p]."""
-    th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
-    pts, h = _central_log_points(th0, relstep)
-    P = spectrum_matter_sweep(prob, names, pts, ks, chunk=len(pts), **kw)
-    L = np.log(P)
-    return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
+_PRIMORDIAL = ("ln_As1e10", "ns")  # enter only through P0(k): their columns are closed-form, no lane needed
 
 
-def sensitivity_cmb(mode, prob, names, jl, relstep=1e-3, normalization="Dl", **kw):
-    """∂ln C_l^{mode}/∂ln θ_j by central differences, all 2p cosmologies in one batched launch (BASELINE config 5; reference
-    ForwardDiff.jacobian of log D_l vs FiniteDiff, runtests.jl:391-406).  Returns [nl, p]."""
-    th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
-    pts, h = _central_log_points(th0, relstep)
-    upd = parameter_updater(prob, names)
-    Cl = spectrum_cmb_batch([mode], [upd(t) for t in pts], jl, normalization=normalization, **kw)[:, :, 0]
-    L = np.log(np.abs(Cl))
-    return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
+def _lane_problems(prob, names, delta):
+    """The lane cosmologies of a sensitivity: lane 0 = `prob`, lane j = parameter j moved by δ in ln|θ_j| (sign kept); parameters
+    that enter only through the primordial spectrum need no lane."""
+    lane_names = [n for n in names if n not in _PRIMORDIAL]
+    if len(lane_names) > 7:
+        raise ValueError("at most 7 non-primordial parameters per call (8 lanes per CTA)")
+    upd = parameter_updater(prob, lane_names)
+    th0 = np.array([prob.pars[n] for n in lane_names], dtype=np.float64)
+    probs = [prob]
+    for j in range(len(lane_names)):
+        th = th0.copy()
+        th[j] *= math.exp(delta)
+        probs.append(upd(th))
+    return lane_names, probs
+
+
+def _lane_backgrounds(probs, bgsol=None):
+    bg0 = bgsol if bgsol is not None else solvebg(probs[0])
+    if not bg0.success:
+        raise RuntimeError("sensitivity: the primal background solve failed")
+    return [bg0] + [solvebg_lock(p, bg0) for p in probs[1:]]
+
+
+def sensitivity_matter(prob, names, ks, method="lanes", delta=1e-5, relstep=1e-3, kτini=1e-2, τinimax=1e-4, bgsol=None, return_info=False, **kw):
+    """∂ln P(k)/∂ln θ_j, [nk, p] (BASELINE config 5's quantity; the reference obtains it with ForwardDiff duals through the whole solve
+    and tests it against a central finite difference, runtests.jl:363-376).
+    method = "lanes" (default): the primal and one cosmology per non-primordial parameter (moved by `delta` in ln θ) are solved IN
+    LOCKSTEP -- backgrounds on the primal's step sequence (`solvebg_lock`), perturbations by CTAs of 1 + p warps sharing one step
+    controller with the partials in its error norm (`solvept_lanes`) -- so that the difference quotient is the derivative of the discrete
+    solution map, as forward-mode AD gives it, at the cost of (1 + p) solves running side by side; ln_As1e10 and ns columns are closed-form.
+    method = "fd": round-1 path, 2p independent solves, central difference with relative step `relstep` (noisy: adaptive step
+    sequences differ between the two sides)."""
+    ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
+    if method == "fd":
+        th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
+        pts, h = _central_log_points(th0, relstep)
+        P = spectrum_matter_sweep(prob, names, pts, ks, chunk=len(pts), kτini=kτini, τinimax=τinimax, **kw)
+        L = np.log(P)
+        return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
+    if method != "lanes":
+        raise ValueError("method must be 'lanes' or 'fd'")
+    lane_names, probs = _lane_problems(prob, names, delta)
+    J = np.zeros((len(ks), len(names)))
+    info = dict(lanes=len(probs))
+    if len(probs) > 1:
+        bgs = _lane_backgrounds(probs, bgsol)
+        sols = solvept_lanes(bgs, ks, [0.0] + [1.0 / delta] * (len(probs) - 1), ptivini=lambda k: min(kτini / k, τinimax) if k > 0 else τinimax, **kw)
+        lnP = []
+        for p, b, sol in zip(probs, bgs, sols):
+            d = b.device()
+            dm = torch.empty(len(ks), dtype=torch.float64, device=sol.d_uend.device)
+            rc = p.lib.sbm_delta_m(_cptr(d["P"]), C.c_int(len(b.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_double(b.tau0), C.c_int(len(ks)), _cptr(sol.d_ks), _cptr(sol.d_uend), _cptr(dm), _stream())
+            if rc != 0:
+                raise RuntimeError(f"sbm_delta_m failed with code {rc}")
+            lnP.append(np.log(spectrum_primordial(ks, p) * dm.cpu().numpy() ** 2))
+        info.update(success=all(s_.success for s_ in sols), attempts=int((sols[0].stats[:, 0] + sols[0].stats[:, 1]).sum()))
+        for j, n in enumerate(lane_names):
+            J[:, names.index(n)] = (lnP[j + 1] - lnP[0]) / delta
+    for n in names:
+        if n == "ln_As1e10":
+            J[:, names.index(n)] = prob.pars["ln_As1e10"]                                   # P ∝ exp(x): ∂ln P/∂ln x = x
+        elif n == "ns":
+            J[:, names.index(n)] = prob.pars["ns"] * np.log(ks / prob.derived["kpivot"])    # P ∝ (k/kp)^(ns−1)
+    return (J, info) if return_info else J
+
+
+def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1e-3, normalization="Dl", kinterp=None, dkt0=math.pi, ntau=300, taucut=1e-2, bgsol=None,
+                    return_info=False, **kw):
+    """∂ln C_l^{mode}/∂ln θ_j, [nl, p] (BASELINE config 5; reference ForwardDiff.jacobian of log D_l, runtests.jl:391-406).
+    method = "lanes": as in `sensitivity_matter`; every lane runs sources -> line of sight -> C_l with its OWN τ0 (χ = τ0 − τ, save times)
+    on the primal's k-quadrature grid and Chebyshev nodes (grids are index sets, not functions of θ -- as with duals, where the grids
+    are built from values); ln_As1e10 and ns columns come from the primal's Θ_l(k) with the weights ∂P0/∂θ.  method = "fd": round-1 path."""
+    if method == "fd":
+        th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
+        pts, h = _central_log_points(th0, relstep)
+        upd = parameter_updater(prob, names)
+        Cl = spectrum_cmb_batch([mode], [upd(t) for t in pts], jl, normalization=normalization, **kw)[:, :, 0]
+        L = np.log(np.abs(Cl))
+        return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
+    if method != "lanes":
+        raise ValueError("method must be 'lanes' or 'fd'")
+    if len(mode) != 2 or mode[0] not in "TE" or mode[1] not in "TE":
+        raise ValueError("sensitivity_cmb handles the T and E modes")
+    lane_names, probs = _lane_problems(prob, names, delta)
+    bgs = _lane_backgrounds(probs, bgsol)
+    kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
+    ks_fine, taus0 = cmb_grids(bgs[0], kinterp.minimum(), kinterp.maximum(), dkt0, ntau, taucut)
+    i0 = int(np.searchsorted(bgs[0].t, taucut, side="left"))  # first knot ≥ τcut: the same knot in every lane (lockstep backgrounds)
+    cg = cosgrid(0.0, 1.0, length=ntau)
+    saves = []
+    for b in bgs:
+        tj = b.t[i0] + (b.t[-1] - b.t[i0]) * cg
+        tj[-1] = b.t[-1]
+        saves.append(tj)
+    assert np.array_equal(saves[0], taus0)
+    if len(bgs) > 1:
+        sols = solvept_lanes(bgs, kinterp.xs, [0.0] + [1.0 / delta] * (len(bgs) - 1), saveat=saves, sources=dict(nS=2, scale_k=True), **kw)
+    else:
+        sols = [solvept(prob, bgs[0], kinterp.xs, saveat=saves[0], sources=dict(nS=2, scale_k=True), keep_states=False, **kw)]
+    lnC, theta0, Cl0 = [], None, None
+    for p, b, sol, tj in zip(probs, bgs, sols, saves):
+        theta = los_integrate(SourceGrid(sol.d_S, kinterp.xs, tj, sol), jl, ks_fine=ks_fine, kinterp=kinterp)
+        Cl = spectrum_cmb_from_theta(theta, [mode], spectrum_primordial(ks_fine, p), jl.l, ks_fine, normalization).cpu().numpy()[0]
+        if theta0 is None:
+            theta0, Cl0 = theta, Cl
+        lnC.append(np.log(np.abs(Cl)))
+    J = np.zeros((len(jl.l), len(names)))
+    for j, n in enumerate(lane_names):
+        J[:, names.index(n)] = (lnC[j + 1] - lnC[0]) / delta
+    P0 = spectrum_primordial(ks_fine, prob)
+    for n in names:
+        if n == "ln_As1e10":
+            J[:, names.index(n)] = prob.pars["ln_As1e10"]
+        elif n == "ns":  # ∂C_l/∂ns = Σ_k c_k ln(k/kp) Θ^A Θ^B
+            dC = spectrum_cmb_from_theta(theta0, [mode], P0 * np.log(ks_fine / prob.derived["kpivot"]), jl.l, ks_fine, normalization).cpu().numpy()[0]
+            J[:, names.index(n)] = prob.pars["ns"] * dC / Cl0  # d ln|C| = dC / C
+    info = dict(lanes=len(probs), success=all(s_.success for s_ in sols))
+    return (J, info) if return_info else J

@@ -159,7 +159,12 @@ namespace bgsolve {
 // The background solve proper.  Knots (t, y, y') are written straight into the caller's arrays (capacity cap); returns the number
 // of knots, or -1 if cap is too small / the solve failed before its first accepted step.
 // info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
-SB_HD static inline int solve(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* T, double* Y, double* DY, double* info) {
+// tfix/nfix/dtlast (optional): LOCKSTEP mode for parameter lanes (sbm_solvebg_lock) -- take exactly the steps of another solve
+// (its knots tfix[0..nfix-1]; the event step, in which a crosses 1, with length dtlast) without error control, so that the result
+// is a smooth function of the parameters (the discrete map with frozen steps is what forward-mode AD differentiates as well).
+// info[6] = length of the event step, info[7] = 1 if the knot count differs from nfix (lockstep lost).
+SB_HD static inline int solve(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* T, double* Y, double* DY, double* info,
+                              const double* tfix = nullptr, int nfix = 0, double dtlast = 0.0) {
     // a(τini) from ℋ = 1/τ (reference src/models/cosmologies.jl:76), Newton on ȧ τ / a − 1
     double a = sqrt(P[3] + P[4]) * tini;
     for (int it = 0; it < 100; it++) {
@@ -193,16 +198,17 @@ SB_HD static inline int solve(const double* P, double tini, double tmax, double 
         dt = fmin(fmin(100 * dt0, dt1), tmax - tini);
     }
     double tt = tini; int rc = SB_RC_SUCCESS; long nacc = 0, nrej = 0; bool first = true;
-    double tau0 = 0, kappa0 = 0;
+    double tau0 = 0, kappa0 = 0, dtevent = 0;
     for (long it = 0;; it++) {
         if (it >= 100000) { rc = SB_RC_MAXITERS; break; }
         if (over) break;
+        if (tfix) dt = (nacc + 1 <= nfix - 2) ? tfix[nacc + 1] - tt : dtlast; // prescribed steps; from the event step on: its length
         if (tt + dt > tmax) dt = tmax - tt;
         if (!S.run(P, u, dt)) { rc = SB_RC_UNSTABLE; break; }
         double EEst = errnorm(S.ks[7], u, S.unew, abstol, reltol);
-        if (!isfinite(EEst)) { nrej++; dt /= 5; if (dt < 1e-14 * tt) { rc = SB_RC_UNSTABLE; break; } continue; }
+        if (!isfinite(EEst)) { if (tfix) { rc = SB_RC_UNSTABLE; break; } nrej++; dt /= 5; if (dt < 1e-14 * tt) { rc = SB_RC_UNSTABLE; break; } continue; }
         double q = ctl.q_of(EEst);
-        if (EEst > 1) { nrej++; dt = ctl.reject(dt); if (dt < 1e-14 * tt) { rc = SB_RC_DTMIN; break; } continue; }
+        if (EEst > 1 && !tfix) { nrej++; dt = ctl.reject(dt); if (dt < 1e-14 * tt) { rc = SB_RC_DTMIN; break; } continue; }
         nacc++;
         double dtnew = ctl.accept(dt, q, EEst), d[5];
         if (first) { S.dinterp(u, S.unew, 0.0, dt, d); SB_BG_PUSH_D(d); first = false; }
@@ -214,11 +220,11 @@ SB_HD static inline int solve(const double* P, double tini, double tmax, double 
             // dense-output vectors of the shortened step (what OrdinaryDiffEq recomputes after moving t); S is not needed any more
             if (S.run(P, u, dtr)) S.dinterp(u, uend, 1.0, dtr, dend); else sb_bg_rhs(uend, P, dend);
             SB_BG_PUSH_TY(tr, uend); SB_BG_PUSH_D(dend);
-            tau0 = tr; kappa0 = uend[1];
+            tau0 = tr; kappa0 = uend[1]; dtevent = dt;
             break;
         }
         S.dinterp(u, S.unew, 1.0, dt, d);
-        tt += dt;
+        tt = (tfix && nacc <= nfix - 2) ? tfix[nacc] : tt + dt; // lockstep: land on the prescribed knot bit for bit
         for (int i = 0; i < 5; i++) u[i] = S.unew[i];
         SB_BG_PUSH_TY(tt, u); SB_BG_PUSH_D(d);
         if (tt >= tmax) { tau0 = tt; kappa0 = u[1]; break; }
@@ -231,6 +237,7 @@ SB_HD static inline int solve(const double* P, double tini, double tmax, double 
     double vmax = -1, taurec = tau0;
     for (int i = 0; i < nb; i++) { double g[5]; sb_bg_rhs(&Y[5 * i], P, g); double v = -g[1] * exp(-(Y[5 * i + 1] - kappa0)); if (v > vmax) { vmax = v; taurec = T[i]; } }
     info[0] = tau0; info[1] = kappa0; info[2] = taurec; info[3] = rc; info[4] = (double)nacc; info[5] = (double)nrej;
+    info[6] = dtevent; info[7] = (tfix && nb != nfix) ? 1.0 : 0.0;
     if (over || nD != nb) return -1;
     return nb;
 }
@@ -247,9 +254,15 @@ int sbm_info(int* out) {
 const char* sbm_key(void) { return SB_MODEL_KEY; }
 
 // Background solve on the host.  Returns the number of spline knots, or -1 if cap is too small.
-// info[0..5] = tau0, kappa0, taurec, retcode, naccept, nreject.
+// info[0..7] = tau0, kappa0, taurec, retcode, naccept, nreject, length of the event step, 0.
 int sbm_solvebg(const double* P, double tini, double tmax, double reltol, double abstol, int cap, double* t, double* y, double* dy, double* info) {
     return bgsolve::solve(P, tini, tmax, reltol, abstol, cap, t, y, dy, info);
+}
+// The same solve in LOCKSTEP with another one (parameter lanes of the sensitivity path): takes the prescribed knots tfix[nfix] of the
+// primal solve and its event-step length dtlast = info[6] instead of choosing steps.  info[7] = 1 if the knot count came out different.
+int sbm_solvebg_lock(const double* P, double tini, double tmax, int nfix, const double* tfix, double dtlast, int cap, double* t, double* y, double* dy, double* info) {
+    if (nfix < 3 || !tfix || !(dtlast > 0)) return -1;
+    return bgsolve::solve(P, tini, tmax, 1.0, 1.0, cap, t, y, dy, info, tfix, nfix, dtlast);
 }
 
 } // extern "C"
@@ -265,11 +278,10 @@ __global__ void __launch_bounds__(32) sb_solvebg_kernel(int n, double* __restric
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     double* Pc = P + (size_t)c * SB_NPAR;
-    double inf[6];
+    double inf[8];
     const int r = bgsolve::solve(Pc, tini, tmax, reltol, abstol, cap, t + (size_t)c * cap, y + (size_t)c * cap * 5, dy + (size_t)c * cap * 5, inf);
     nb[c] = r;
-    for (int j = 0; j < 6; j++) info[(size_t)c * 8 + j] = inf[j];
-    info[(size_t)c * 8 + 6] = 0; info[(size_t)c * 8 + 7] = 0;
+    for (int j = 0; j < 8; j++) info[(size_t)c * 8 + j] = inf[j];
     Pc[SB_P_KAPPA0] = inf[1]; Pc[SB_P_TAU0] = inf[0];
 }
 
@@ -351,7 +363,12 @@ struct SbSolveArgs {
     // fused source evaluation (sbm_solvept_src & co.): S[nk][nS][nsave] formed from the dense output at every save time
     double* S;
     int nS, scale_k;
+    // parameter lanes in lockstep (sbm_solvept_lanes): G warps of one CTA integrate the same mode for G cosmologies with ONE step controller
+    int G;
+    double invdelta[8]; // 1/δ_j of lane j (δ_j = parameter step of the lane in the units of the wanted derivative); [0] unused
 };
+#define SB_GROUP_MAX 8
+#define SB_XCH_HDR 8 // doubles at the head of the CTA's exchange area: [0] work index, [1] initial step
 #define SB_CONT (SB_N + 12)
 
 // shared-memory layout per warp (doubles)
@@ -997,7 +1014,7 @@ __device__ __forceinline__ void sb_source_tail(const double* sb, double k, doubl
     if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
     out[0] = ST;
     out[ostride] = SE;
-    if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
+    if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_I_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0 * Psi; // (0·Ψ: a failed mode stays NaN) // τ0 = χ + τ
 }
 // Coalesced store of the window of source values: lane 0 has put the sources of save index `it` into sbuf[s][it % SB_SWIN]; when the
 // window is full (or the mode's last save time is reached) the lanes write it as contiguous runs of S[s][w0 .. w0+cnt).  wstart: first
@@ -1061,7 +1078,7 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
         if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
         out[0] = ST;
         out[ostride] = SE;
-        if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_J_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0; // τ0 = χ + τ
+        if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_J_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0 * Psi; // τ0 = χ + τ
     }
     __syncwarp();
 }
@@ -1070,20 +1087,28 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
 // queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
 // BATCH: every mode carries its own cosmology (A.cosmos[A.cosmo_of[mode]], staged in shared memory per mode) -- one launch over
 // the (cosmology, mode) pairs of a parameter sweep; otherwise the single cosmology A.c0 is read from the kernel parameters.
-template <bool BATCH>
+// GROUP (sbm_solvept_lanes; BASELINE config 5, "dual-number lanes in the batched solve"): the CTA has A.G warps; warp j integrates
+// the SAME mode for cosmology j (lane 0: the primal, lanes j >= 1: one parameter moved by δ_j) and all of them share one step
+// controller: every attempt ends with one CTA barrier at which the lanes exchange (u_n, u_{n+1}, k_8); each warp then forms the same
+// error norm over the primal AND the partials (u^j − u^0)/δ_j (OrdinaryDiffEq's norm of Dual numbers), so accept/reject
+// and the next step are identical in all lanes.  With frozen, shared steps the lanes' results are smooth in the parameters and
+// (u^j − u^0)/δ_j is the derivative of the discrete solution map -- what ForwardDiff computes -- up to O(δ).
+template <bool BATCH, bool GROUP = false>
 #ifdef SB_NOLB
 __global__ void sb_integrate_kernel
 #else
-__global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCKS_BATCH : SB_MINBLOCKS) sb_integrate_kernel
+__global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_WARPS_PER_CTA, GROUP ? 1 : (BATCH ? SB_MINBLOCKS_BATCH : SB_MINBLOCKS)) sb_integrate_kernel
 #endif
     (const __grid_constant__ SbSolveArgs A) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
 #if SB_WARPS_PER_CTA == 1
-    double* const sm = sm_all; // constant base: shared-memory accesses become [index.X8 + immediate], no address arithmetic
+    double* const sm = GROUP ? sm_all + warp * SB_SM_DOUBLES : sm_all; // constant base: shared-memory accesses become [index.X8 + immediate], no address arithmetic
 #else
-    double* sm = sm_all + (threadIdx.x >> 5) * SB_SM_DOUBLES;
+    double* sm = sm_all + warp * SB_SM_DOUBLES;
 #endif
+    double* const xch = sm_all + (GROUP ? A.G : 0) * SB_SM_DOUBLES; // GROUP: header + [2 parities][G lanes][3][N] exchange of (u_n, u_{n+1}, k_8)
     double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
            *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
     double* const sbuf = sm + SB_SM_SBUF;
@@ -1106,6 +1131,13 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
             if (item >= item_end) break;
             mode = A.items[3 * item]; quota = A.items[3 * item + 1]; resume = A.items[3 * item + 2];
             item++;
+        } else if (GROUP) {
+            __syncthreads(); // every lane is done with the previous mode (and with the exchange area)
+            if (threadIdx.x == 0) reinterpret_cast<int*>(xch)[0] = atomicAdd(A.queue, 1);
+            __syncthreads();
+            const int qi = reinterpret_cast<const int*>(xch)[0];
+            if (qi >= A.nk / A.G) break;
+            mode = (A.order ? A.order[qi] : qi) * A.G + warp; // modes are laid out [group][lane]
         } else {
             int qi = 0;
             if (lane == 0) qi = atomicAdd(A.queue, 1);
@@ -1122,6 +1154,11 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
         const double k = A.ks[mode];
         double t = A.tini[mode];
         const double tend = CC.tend;
+        // GROUP: every decision that steers the step sequence is taken on the PRIMAL lane's end time and save times (each lane still
+        // integrates to its own end time and interpolates at its own save times: they differ by O(δ))
+        const SbCosmo* const C0 = GROUP ? A.cosmos + A.cosmo_of[mode - warp] : nullptr;
+        const double tend0 = GROUP ? C0->tend : tend;
+        const double* const saveat0 = GROUP ? C0->saveat : CC.saveat;
         long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
         int rc = SB_RC_SUCCESS, isave = 0;
         double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
@@ -1171,8 +1208,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
         __syncwarp();
         for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
         __syncwarp();
-        while (isave < A.nsave && CC.saveat[isave] <= t) { // save points at (or before) the start
-            const bool at = CC.saveat[isave] == t;
+        while (isave < A.nsave && saveat0[isave] <= t) { // save points at (or before) the start
+            const bool at = saveat0[isave] == t;
             if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = at ? u[i] : NAN;
             if (SRC) {
                 double* so = sbuf + (isave & (SB_SWIN - 1));
@@ -1184,7 +1221,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
             isave++;
         }
         }
-        if (tend > t) {
+        if (tend0 > t) {
             if (!resume) {
             jt = sb_interval(CC.tb, t); // knot interval of the current time
             jt = sb_basis_at(S, CC.tb, t, jt, kp, bs, bdv, lane);
@@ -1210,6 +1247,11 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
                 __syncwarp();
             }
+            if (GROUP) { // one initial step for all lanes: the primal's
+                if (threadIdx.x == 0) xch[1] = dt;
+                __syncthreads();
+                dt = xch[1];
+            }
             }
             int jend = jt;       // interval of t + dt after the step (becomes jt on accept)
             bool moved = resume; // t advanced since f0, dT and the slot-0 basis were evaluated
@@ -1227,7 +1269,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                     break;
                 }
                 bool last = false;
-                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
+                double dtc = dt; // the step as the (shared) controller sees it; dt is what this lane integrates over (differs only on the last step of a GROUP lane)
+                if (t + dt >= tend0 - 100 * 2.2e-16 * fabs(tend0)) { dtc = tend0 - t; dt = tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
                 __syncwarp();
@@ -1346,27 +1389,51 @@ __global__ void __launch_bounds__(SB_WARP* SB_WARPS_PER_CTA, BATCH ? SB_MINBLOCK
                 __syncwarp();
                 // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
                 double es = 0; bool bad = false;
+                if (GROUP) {
+                    // publish (u_n, u_{n+1}, k_8) of this lane, then every warp forms the SAME norm over primal and partials:
+                    // r_i = Dual(k8_i) / (abstol + reltol·max(‖u_n,i‖, ‖u_{n+1},i‖)), ‖x‖² = x² + Σ_j (∂_j x)², EEst² = Σ_i ‖r_i‖² / N
+                    const int G = A.G;
+                    double* X = xch + SB_XCH_HDR + (size_t)(((it & 1) * G + warp) * 3) * SB_N;
+                    for (int i = lane; i < SB_N; i += SB_WARP) { const double k8 = K[7 * SB_N + i]; X[i] = u[i]; X[SB_N + i] = U[i] + k8; X[2 * SB_N + i] = k8; }
+                    __syncthreads();
+                    const double* X0 = xch + SB_XCH_HDR + (size_t)((it & 1) * G * 3) * SB_N;
+                    for (int i = lane; i < SB_N; i += SB_WARP) {
+                        const double u0 = X0[i], u1 = X0[SB_N + i], k8 = X0[2 * SB_N + i];
+                        double s0 = u0 * u0, s1 = u1 * u1, sk = k8 * k8;
+                        for (int j = 1; j < G; j++) {
+                            const double* Xj = X0 + (size_t)j * 3 * SB_N;
+                            const double d = A.invdelta[j];
+                            const double a0 = (Xj[i] - u0) * d, a1 = (Xj[SB_N + i] - u1) * d, ak = (Xj[2 * SB_N + i] - k8) * d;
+                            s0 += a0 * a0; s1 += a1 * a1; sk += ak * ak;
+                        }
+                        const double sc = abstol + reltol * fmax(sqrt(s0), sqrt(s1));
+                        const double r = sqrt(sk) / sc; // with vanishing partials this is |k8| / (abstol + reltol·max(|u_n|, |u_{n+1}|)): the plain norm, bit for bit
+                        es += r * r;
+                    }
+                } else
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
                 double EEst = sqrt(warp_sum(es) / SB_N);
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
-                if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
+                if (!isfinite(EEst)) { nreject++; dt = dtc / 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
                 double q = ctl.q_of(EEst);
-                if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                if (EEst > 1) { nreject++; dt = ctl.reject(dtc); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
-                const double dtnew = ctl.accept(dt, q, EEst);
+                const double dtnew = ctl.accept(dtc, q, EEst);
                 const double tn = last ? tend : t + dt;
-                if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order), vectors stored over dT, f0, Zp
+                const double tn0 = GROUP ? (last ? tend0 : t + dtc) : tn;
+                if (isave < A.nsave && saveat0[isave] <= tn0) { // dense output (4th order), vectors stored over dT, f0, Zp
                     for (int i = lane; i < SB_N; i += SB_WARP) {
                         double a1 = 0, a2 = 0, a3 = 0;
                         for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
                         dT[i] = a1; f0[i] = a2; Zp[i] = a3;
                     }
-                    while (isave < A.nsave && CC.saveat[isave] <= tn) {
+                    while (isave < A.nsave && saveat0[isave] <= tn0) {
                         const double ts = CC.saveat[isave];
                         const double th = (ts - t) / dt, t1 = 1 - th;
+                        const bool atend = GROUP ? (saveat0[isave] == tn0) : (ts == tn); // a save time that IS the step end takes the step result
                         for (int i = lane; i < SB_N; i += SB_WARP) {
                             const double un = U[i] + K[7 * SB_N + i];
-                            const double v = (ts == tn) ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
+                            const double v = atend ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
                             if (usave) usave[(size_t)isave * SB_N + sb_nat[i]] = v;
                             if (SRC) di[i] = v;
                         }
@@ -1578,6 +1645,42 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
     if (ditems && (!dibeg || !dcont || !dflags)) return -1;
     return sb_solvept_impl(nullptr, 0, nullptr, nullptr, nullptr, 1, 1, 0.0, 1.0, nullptr, nullptr, nk, dks, dtini, dorder, 0.0, nsave, nullptr, reltol, abstol, maxiters, dusave, duend, dretcode, dstats,
                            dqueue, 0, stream, nullptr, 0, ditems, dibeg, nlists, dcont, dflags, (const SbCosmo*)dcosmos, dcosmo_of, src);
+}
+// Parameter lanes in lockstep (BASELINE config 5: "ForwardDiff gradient ... via dual-number lanes in the batched solve"; reference:
+// ForwardDiff.Dual parameters pushed through solvept, test/runtests.jl:363-422).  G = ncosmo cosmologies -- lane 0 the primal, lane
+// j >= 1 with one parameter moved by δ_j -- are integrated for the same nk wavenumbers by CTAs of G warps that share ONE step
+// controller whose error norm covers the primal and the partials (u^j − u^0)·invdelta[j] (see sb_integrate_kernel<.., GROUP>).
+// Arrays are laid out [mode][lane]: dks/dtini/dcosmo_of have nk·G entries with dks[m·G + j] = k_m and dcosmo_of[m·G + j] = j;
+// outputs likewise (duend[nk·G][N], dretcode[nk·G], dstats[nk·G][4], src->dS[nk·G][nS][nsave]).  dorder: optional order of the
+// nk groups.  invdelta: host array of G doubles ([0] unused).  Cost: G solves running side by side, i.e. (1 + p)× one solve.
+int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol, double abstol,
+                      int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, void* stream, const sbm_src_t* src) {
+    const int G = ncosmo;
+    if (G < 2 || G > SB_GROUP_MAX || !dcosmos || !dcosmo_of || !invdelta) return -1;
+    if (nk <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SbSolveArgs A;
+    memset(&A, 0, sizeof(A));
+    const bool fused = src && src->dS && nsave > 0;
+    if (fused && (src->nS < 2 || src->nS > 3)) return -1;
+    A.c0 = SbCosmo{nullptr, SbSpline{0, nullptr, nullptr, nullptr}, SbTable{0, 1, 1, 0.0, 1.0, nullptr, nullptr, nullptr}, 0.0, nullptr, nullptr, 0.0};
+    A.cosmos = (const SbCosmo*)dcosmos; A.cosmo_of = dcosmo_of;
+    A.S = fused ? src->dS : nullptr; A.nS = fused ? src->nS : 0; A.scale_k = fused ? src->scale_k : 0;
+    A.nk = nk * G; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = (dusave || fused) ? nsave : 0;
+    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
+    A.G = G;
+    for (int j = 0; j < SB_GROUP_MAX; j++) A.invdelta[j] = j < G ? invdelta[j] : 0.0;
+    SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
+    const size_t smem = ((size_t)G * SB_SM_DOUBLES + SB_XCH_HDR + (size_t)2 * G * 3 * SB_N) * sizeof(double);
+    int dev, nsm, occ = 0;
+    SB_CUDA_CHECK(cudaGetDevice(&dev));
+    SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_integrate_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_kernel<true, true>, SB_WARP * G, smem));
+    const int grid = std::min(nk, nsm * std::max(1, occ));
+    sb_integrate_kernel<true, true><<<grid, SB_WARP * G, smem, st>>>(A);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return grid;
 }
 // Per-save-time background table of the source evaluation: dsrcbg[nt][sbm_srcbg_stride()] (κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, the β_m and their
 // flow derivatives at dtaus[nt]); input of sbm_solvept_src / sbm_cosmo_t.srcbg and of sbm_sources.

@@ -318,3 +318,25 @@ def test_build_cli_and_freshness_stamps(sb, prob5, tmp_path):
     assert sb.build._newer(str(tgt), [str(src)])
     src.write_text("two")
     assert not sb.build._newer(str(tgt), [str(src)])
+
+
+def test_lockstep_background_is_smooth_in_the_parameters(sb, prob5, bg5):
+    """`solvebg_lock` (host; parameter lanes of BASELINE config 5): re-taking the primal's steps reproduces the primal to rounding, and
+    the difference quotient of a moved parameter is linear in the step (no step-selection noise): δ = 1e-6 and 2e-6 give the same
+    partials of all five background unknowns and of τ0 to 1e-4 of their size -- independent adaptive solves at reltol = 1e-7 could not
+    resolve a 1e-6 step at all."""
+    import math
+    again = sb.solvebg_lock(prob5, bg5)
+    assert len(again.t) == len(bg5.t) and abs(again.tau0 / bg5.tau0 - 1) < 1e-13
+    assert np.abs(again.y - bg5.y).max() <= 1e-13 * np.abs(bg5.y).max()
+    upd = sb.parameter_updater(prob5, ["Omega_c"])
+    part = {}
+    for d in (1e-6, 2e-6):
+        lane = sb.solvebg_lock(upd([prob5.pars["Omega_c"] * math.exp(d)]), bg5)
+        assert len(lane.t) == len(bg5.t) and np.array_equal(lane.t[:-1], bg5.t[:-1])  # same knots; only the event time moves
+        part[d] = ((lane.y - bg5.y) / d, (lane.tau0 - bg5.tau0) / d)
+    sc = np.abs(part[1e-6][0]).max(axis=0)
+    assert (np.abs(part[1e-6][0] - part[2e-6][0]).max(axis=0) <= 1e-4 * sc).all()
+    assert abs(part[1e-6][1] / part[2e-6][1] - 1) < 1e-5 and part[1e-6][1] < 0  # more matter -> earlier today
+    with pytest.raises(RuntimeError):
+        sb.solvebg_lock(upd([prob5.pars["Omega_c"] * 1.5]), bg5)  # a step that changes the number of solver steps is refused
