@@ -1,9 +1,10 @@
 /* symboltz_b200.h -- C ABI of the B200-native SymBoltz hot path.
  *
- * Two shared libraries export these symbols:
+ * Three shared libraries export these symbols:
  *   libsbm_<model>.so  (one per model structure lmax/nx/w0wa; built at problem-build time by symboltz.jl_b200/build.py,
  *                       sources: symboltz.jl_b200/csrc/sb_engine.cu + sb_debug.cpp + generated sb_model_gen.h)   -> sbm_*
  *   libsbl.so          (model independent; symboltz.jl_b200/csrc/sb_los.cu)                                       -> sbl_*
+ *   libsbc.so          (model independent, links NCCL; symboltz.jl_b200/csrc/sb_comm.cu)                          -> sbc_*
  *
  * Conventions: plain pointers and sizes only; doubles are IEEE binary64; τ in 1/H0, k in H0/c (reference
  * docs/src/conventions.md:14-18).  Pointers named d* are DEVICE pointers (cudaMalloc / torch / CUDA.jl memory), all others
@@ -223,6 +224,28 @@ int sbl_dfma_peak(int iters, int reps, double* tflops, void* stream);
  * (replaces the body of spectrum_cmb(modes, prob, jl, ls), src/observables/angular.jl:293-340, after source_grid) */
 int sbl_cmb_host(int nk, const double* ks, int nc, const double* Bw, const double* Sc, int nS, int nt, const double* chi, const double* wt, int nl, const int* ls, double dx,
                  double xmax, double xcut, const double* ck, int nmodes, const int* modeA, const int* modeB, int l_limber, double* Cl, double* Theta);
+
+/* ------------------------------------------------------------------ exchange library (libsbc.so; symboltz.jl_b200/csrc/sb_comm.cu) */
+
+/* Multi-GPU exchange steps of the hot path with the NCCL communicator owned by the library (one process or host thread per GPU).
+ * (replaces the fan-out over `Threads.@spawn` tasks of src/solve.jl:566 and the serial sweep loop of docs/src/forecasting.md:56-59 across
+ * the GPUs of one box: modes / cosmologies are strided over the ranks, results are combined by sum all-reduces over disjoint supports.)
+ * Rank 0 obtains the id (sbc_unique_id_bytes() = 128 bytes) and passes it to the other ranks on the host side; sbc_comm_init is
+ * collective and binds the communicator to the calling thread's current CUDA device. */
+int sbc_unique_id_bytes(void);
+int sbc_unique_id(char* out);
+int sbc_comm_init(const char* id_bytes, int rank, int world, void** comm);
+int sbc_comm_destroy(void* comm);
+/* In-place sum over all ranks of the device array dbuf[n], asynchronous on `stream`: (1) gather of the sources S[nk][nS][nt] solved by
+ * different ranks (zero-initialised, disjoint supports), (2) the partial C_l sums [nmodes][nl] of the ranks' fine-k slices
+ * (sbl_los / sbl_cl with k0, k1), (3) gather of P[ncosmo][nk] in a sharded parameter sweep. */
+int sbc_allreduce_sum(void* comm, double* dbuf, long long n, void* stream);
+/* The ownership rules of the sharded paths: rank r owns the modes / cosmologies r, r + world, ... (sbc_owned_count of them; the j-th is
+ * sbc_owned_index(j, ...)) and the contiguous slice [sbc_slice_begin, sbc_slice_end) of the n fine wavenumbers. */
+int sbc_owned_count(int n, int rank, int world);
+int sbc_owned_index(int j, int rank, int world);
+int sbc_slice_begin(int n, int rank, int world);
+int sbc_slice_end(int n, int rank, int world);
 
 #ifdef __cplusplus
 }

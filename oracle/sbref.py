@@ -226,8 +226,19 @@ def loggrid(a, b, **kw):
     return x
 
 
+def cospi(x):
+    """cos(πx), argument reduced before multiplying by π (Julia's cospi, used by the reference's cosgrid, src/utils.jl:285): exact zeros at
+    the half-integers."""
+    x = np.abs(np.asarray(x, dtype=float))
+    r = x - 2.0 * np.floor(x / 2.0)
+    r = np.where(r > 1.0, 2.0 - r, r)
+    sgn = np.where(r > 0.5, -1.0, 1.0)
+    r = np.where(r > 0.5, 1.0 - r, r)
+    return sgn * np.where(r <= 0.25, np.cos(np.pi * r), np.sin(np.pi * (0.5 - r)))
+
+
 def cosgrid(a, b, length):
-    return a + (b - a) * (1 - np.cos(np.pi * lingrid(0.0, 0.5, length=length)))
+    return a + (b - a) * (1 - cospi(lingrid(0.0, 0.5, length=length)))
 
 
 def chebpoints(order, a, b):

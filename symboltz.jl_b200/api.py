@@ -52,8 +52,20 @@ def loggrid(a, b, **kw):
     return x
 
 
+def cospi(x):
+    """cos(πx) with the argument reduced BEFORE the multiplication by π, as Julia's `cospi` (the reference's cosgrid uses it,
+    src/utils.jl:285): exact at the half-integers, so the grid ends land on a and b bit for bit.  Quadrant reduction to |r| ≤ 1/4, then
+    cos/sin of π·r."""
+    x = np.abs(np.asarray(x, dtype=np.float64))
+    r = x - 2.0 * np.floor(x / 2.0)                       # [0, 2), exact
+    r = np.where(r > 1.0, 2.0 - r, r)                     # cos is even about 1: [0, 1]
+    sign = np.where(r > 0.5, -1.0, 1.0)
+    r = np.where(r > 0.5, 1.0 - r, r)                     # cos(π(1 − r)) = −cos(πr): [0, 1/2]
+    return sign * np.where(r <= 0.25, np.cos(np.pi * r), np.sin(np.pi * (0.5 - r)))
+
+
 def cosgrid(a, b, step=None, length=None):
-    return a + (b - a) * (1 - np.cos(np.pi * lingrid(0.0, 0.5, step=None if step is None else step / math.pi, length=length)))
+    return a + (b - a) * (1 - cospi(lingrid(0.0, 0.5, step=None if step is None else step / math.pi, length=length)))
 
 
 def chebpoints(order, a, b):
@@ -170,6 +182,65 @@ def _load(path):
 def los_lib():
     lib = _load(_build.build_los())
     return lib
+
+
+def comm_lib():
+    return _load(_build.build_comm())
+
+
+class Communicator:
+    """NCCL communicator owned by the library (libsbc.so, `sbc_*`): what a host without torch.distributed (Julia over ccall) uses for the
+    exchange steps of the sharded paths.  Rank 0 creates `Communicator.unique_id()` and hands the 128 bytes to the other
+    ranks by any host-side means; every rank then constructs `Communicator(rank, world, id)` with its GPU current.  Accepted wherever the
+    host API takes `group=` (spectrum_cmb, spectrum_matter_sweep)."""
+
+    def __init__(self, rank, world, unique_id):
+        _require_cuda()
+        self.rank, self.world = int(rank), int(world)
+        self._h = C.c_void_p()
+        rc = comm_lib().sbc_comm_init(C.c_char_p(bytes(unique_id)), C.c_int(self.rank), C.c_int(self.world), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"sbc_comm_init failed with code {rc}")
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(int(comm_lib().sbc_unique_id_bytes()))
+        rc = comm_lib().sbc_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"sbc_unique_id failed with code {rc}")
+        return buf.raw
+
+    def allreduce_sum(self, t):
+        """In-place sum over ranks of a contiguous float64 device tensor (asynchronous on torch's current stream)."""
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise ValueError("allreduce_sum: contiguous float64 device tensor expected")
+        rc = comm_lib().sbc_allreduce_sum(self._h, _cptr(t), C.c_longlong(t.numel()), _stream())
+        if rc != 0:
+            raise RuntimeError(f"sbc_allreduce_sum failed with code {rc}")
+        return t
+
+    def close(self):
+        if self._h:
+            comm_lib().sbc_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def _ranks(group):
+    """(world, rank) of `group`: a library Communicator, a torch.distributed group, or the default group if one is initialised."""
+    if isinstance(group, Communicator):
+        return group.world, group.rank
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _allreduce(t, group):
+    if isinstance(group, Communicator):
+        return group.allreduce_sum(t)
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t
 
 
 class CosmologyProblem:
@@ -1215,13 +1286,13 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
     (reference spectrum_cmb(modes, prob, jl[, ls]), src/observables/angular.jl:260-359).  With a lensing mode (ψ, alias P) the default
     k-grid is the tanh-stretched order-130 Chebyshev grid to k = 1e4 and the ψ line-of-sight integral uses Limber for l ≥ l_limber.
     direct=True solves every fine k instead of interpolating from the Chebyshev nodes.
-    With torch.distributed initialised (group or default) the modes are sharded over ranks and the partial C_l are all-reduced."""
+    With torch.distributed initialised (group or default), or with `group` a library `Communicator` (NCCL behind the C ABI), the modes are
+    sharded over ranks (strided), the sources all-gathered, the line of sight run on contiguous fine-k slices and the partial C_l all-reduced."""
     modes = [modes] if isinstance(modes, str) else list(modes)
     for m in modes:
         if len(m) != 2 or m[0] not in _MODE_IDX or m[1] not in _MODE_IDX:
             raise ValueError(f"Unknown CMB power spectrum mode {m}")
-    import torch.distributed as dist
-    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if (dist.is_available() and dist.is_initialized()) else (1, 0)
+    world, rank = _ranks(group)
     bg = bgsol if bgsol is not None else solvebg(prob)
     lensing = any(c in ("ψ", "P") for m in modes for c in m)
     if kinterp is None:  # angular.jl:267-273
@@ -1237,7 +1308,7 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
         full = torch.zeros((len(ks_solve), S.dS.shape[1], len(taus)), dtype=torch.float64, device=S.dS.device)
         S.dS[:, :, -1] = 0  # χ = 0 row (Inf/NaN in SE, Sψ) is dropped by the LOS kernel anyway; keep the reduction finite
         full[torch.from_numpy(mine).to(S.dS.device)] = S.dS
-        dist.all_reduce(full, group=group)  # gather of the sources: supports are disjoint, so a sum is an all-gather
+        _allreduce(full, group)  # gather of the sources: supports are disjoint, so a sum is an all-gather
         S = SourceGrid(full, ks_solve, taus, S.sol)
     lo, hi = (nkf * rank) // world, (nkf * (rank + 1)) // world  # contiguous fine-k slice for LOS + partial C_l
     theta = los_integrate(S, jl, ks_fine=ks_fine, kinterp=None if direct else kinterp, k_range=(lo, hi), l_limber=l_limber if lensing else None)
@@ -1246,7 +1317,7 @@ def spectrum_cmb(modes, prob, jl, ls=None, normalization="Cl", kinterp=None, dir
     P0s = spectrum_primordial(ks_fine, prob)
     Cl = spectrum_cmb_from_theta(theta, modes, P0s, jl.l, ks_fine, normalization, k_mask=None if world == 1 else mask)
     if world > 1:
-        dist.all_reduce(Cl, group=group)  # partial k-sums → full C_l (north star: NCCL all-reduce of the partial C_l sums)
+        _allreduce(Cl, group)  # partial k-sums → full C_l (north star: NCCL all-reduce of the partial C_l sums)
     out = Cl.cpu().numpy().T.copy()  # [nl, nmodes] like the reference's spectra[il, imode]
     if ls is not None:
         if (min(ls), max(ls)) != (jl.l[0], jl.l[-1]):
@@ -1459,9 +1530,9 @@ def gather_rows(local, mine, n, group=None):
     local = np.asarray(local, dtype=np.float64)
     full = torch.zeros((n,) + local.shape[1:], dtype=torch.float64)
     full[torch.from_numpy(np.asarray(mine, dtype=np.int64))] = torch.from_numpy(local)
-    if dist.get_backend(group) == "nccl":
+    if isinstance(group, Communicator) or dist.get_backend(group) == "nccl":
         full = full.cuda()
-    dist.all_reduce(full, group=group)
+    _allreduce(full, group)
     return full.cpu().numpy()
 
 
@@ -1487,8 +1558,8 @@ def spectrum_matter_sweep(prob, names, thetas, ks, chunk=32, nthreads=None, kτi
     thetas = np.asarray(thetas, dtype=np.float64)
     thetas = thetas.reshape(0, len(names)) if thetas.size == 0 else np.atleast_2d(thetas)
     ks = np.ascontiguousarray(ks, dtype=np.float64)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if _ranks(group)[0] > 1:
+        world, rank = _ranks(group)
         mine = shard_rows(len(thetas), rank, world)
         kw = dict(chunk=chunk, nthreads=nthreads or max(1, (os.cpu_count() or 1) // world), kτini=kτini, τinimax=τinimax, reltol=reltol, abstol=abstol, cost=cost, msub=msub,
                   nslots=nslots, background=background)
@@ -1657,20 +1728,38 @@ def _central_log_points(theta0, relstep):
 _PRIMORDIAL = ("ln_As1e10", "ns")  # enter only through P0(k): their columns are closed-form, no lane needed
 
 
-def _lane_problems(prob, names, delta):
-    """The lane cosmologies of a sensitivity: lane 0 = `prob`, lane j = parameter j moved by δ in ln|θ_j| (sign kept); parameters
-    that enter only through the primordial spectrum need no lane."""
+def _lane_problems(prob, names, delta, central=False):
+    """The lane cosmologies of a sensitivity: lane 0 = `prob`, then per non-primordial parameter one lane moved by +δ in ln|θ_j| (sign
+    kept) and, with `central`, one moved by −δ; parameters that enter only through the primordial spectrum need no lane.
+    Returns (lane parameter names, problems, signed steps per lane)."""
     lane_names = [n for n in names if n not in _PRIMORDIAL]
-    if len(lane_names) > 7:
-        raise ValueError("at most 7 non-primordial parameters per call (8 lanes per CTA)")
+    per = 2 if central else 1
+    if per * len(lane_names) > 7:
+        raise ValueError("at most 7 parameter lanes per call (8 warps per CTA): %d parameters × %d" % (len(lane_names), per))
     upd = parameter_updater(prob, lane_names)
     th0 = np.array([prob.pars[n] for n in lane_names], dtype=np.float64)
-    probs = [prob]
+    probs, steps = [prob], [0.0]
     for j in range(len(lane_names)):
-        th = th0.copy()
-        th[j] *= math.exp(delta)
-        probs.append(upd(th))
-    return lane_names, probs
+        for sgn in ((+1.0, -1.0) if central else (+1.0,)):
+            th = th0.copy()
+            th[j] *= math.exp(sgn * delta)
+            probs.append(upd(th))
+            steps.append(sgn * delta)
+    return lane_names, probs, steps
+
+
+def _lane_quotients(vals, steps, central):
+    """Difference quotients per parameter from per-lane values (lane order of `_lane_problems`)."""
+    out = []
+    j = 1
+    while j < len(vals):
+        if central:
+            out.append((vals[j] - vals[j + 1]) / (steps[j] - steps[j + 1]))
+            j += 2
+        else:
+            out.append((vals[j] - vals[0]) / steps[j])
+            j += 1
+    return out
 
 
 def _lane_backgrounds(probs, bgsol=None):
@@ -1680,13 +1769,17 @@ def _lane_backgrounds(probs, bgsol=None):
     return [bg0] + [solvebg_lock(p, bg0) for p in probs[1:]]
 
 
-def sensitivity_matter(prob, names, ks, method="lanes", delta=1e-5, relstep=1e-3, kτini=1e-2, τinimax=1e-4, bgsol=None, return_info=False, **kw):
+def sensitivity_matter(prob, names, ks, method="lanes", delta=None, central=False, norm_partials=True, relstep=1e-3, kτini=1e-2, τinimax=1e-4, bgsol=None, return_info=False, **kw):
     """∂ln P(k)/∂ln θ_j, [nk, p] (BASELINE config 5's quantity; the reference obtains it with ForwardDiff duals through the whole solve
     and tests it against a central finite difference, runtests.jl:363-376).
     method = "lanes" (default): the primal and one cosmology per non-primordial parameter (moved by `delta` in ln θ) are solved IN
     LOCKSTEP -- backgrounds on the primal's step sequence (`solvebg_lock`), perturbations by CTAs of 1 + p warps sharing one step
     controller with the partials in its error norm (`solvept_lanes`) -- so that the difference quotient is the derivative of the discrete
     solution map, as forward-mode AD gives it, at the cost of (1 + p) solves running side by side; ln_As1e10 and ns columns are closed-form.
+    delta: step in ln θ (default 1e-5 one-sided: truncation O(δ), rounding noise O(1e-11/δ) -- lockstep removes the step-selection noise
+    of independent solves, ≈1e-4 relative, not the rounding); central = True: ±δ lanes (1 + 2p warps per mode, default δ = 1e-3, truncation
+    O(δ²)); norm_partials: the shared controller's error norm covers the partials, as OrdinaryDiffEq's norm of Duals does (≈1.6× the
+    primal's steps); False: the lanes take exactly the primal's steps.
     method = "fd": round-1 path, 2p independent solves, central difference with relative step `relstep` (noisy: adaptive step
     sequences differ between the two sides)."""
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
@@ -1698,12 +1791,13 @@ def sensitivity_matter(prob, names, ks, method="lanes", delta=1e-5, relstep=1e-3
         return np.stack([(L[2 * j] - L[2 * j + 1]) / (2 * h[j]) for j in range(len(names))], axis=1)
     if method != "lanes":
         raise ValueError("method must be 'lanes' or 'fd'")
-    lane_names, probs = _lane_problems(prob, names, delta)
+    delta = (1e-3 if central else 1e-5) if delta is None else float(delta)
+    lane_names, probs, steps = _lane_problems(prob, names, delta, central)
     J = np.zeros((len(ks), len(names)))
-    info = dict(lanes=len(probs))
+    info = dict(lanes=len(probs), delta=delta, central=central)
     if len(probs) > 1:
         bgs = _lane_backgrounds(probs, bgsol)
-        sols = solvept_lanes(bgs, ks, [0.0] + [1.0 / delta] * (len(probs) - 1), ptivini=lambda k: min(kτini / k, τinimax) if k > 0 else τinimax, **kw)
+        sols = solvept_lanes(bgs, ks, [0.0] + [(1.0 / st if norm_partials else 0.0) for st in steps[1:]], ptivini=lambda k: min(kτini / k, τinimax) if k > 0 else τinimax, **kw)
         lnP = []
         for p, b, sol in zip(probs, bgs, sols):
             d = b.device()
@@ -1713,8 +1807,8 @@ def sensitivity_matter(prob, names, ks, method="lanes", delta=1e-5, relstep=1e-3
                 raise RuntimeError(f"sbm_delta_m failed with code {rc}")
             lnP.append(np.log(spectrum_primordial(ks, p) * dm.cpu().numpy() ** 2))
         info.update(success=all(s_.success for s_ in sols), attempts=int((sols[0].stats[:, 0] + sols[0].stats[:, 1]).sum()))
-        for j, n in enumerate(lane_names):
-            J[:, names.index(n)] = (lnP[j + 1] - lnP[0]) / delta
+        for n, q in zip(lane_names, _lane_quotients(lnP, steps, central)):
+            J[:, names.index(n)] = q
     for n in names:
         if n == "ln_As1e10":
             J[:, names.index(n)] = prob.pars["ln_As1e10"]                                   # P ∝ exp(x): ∂ln P/∂ln x = x
@@ -1723,12 +1817,14 @@ def sensitivity_matter(prob, names, ks, method="lanes", delta=1e-5, relstep=1e-3
     return (J, info) if return_info else J
 
 
-def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1e-3, normalization="Dl", kinterp=None, dkt0=math.pi, ntau=300, taucut=1e-2, bgsol=None,
-                    return_info=False, **kw):
+def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=None, central=False, norm_partials=True, relstep=1e-3, normalization="Dl", kinterp=None, dkt0=math.pi, ntau=300,
+                    taucut=1e-2, bgsol=None, return_info=False, **kw):
     """∂ln C_l^{mode}/∂ln θ_j, [nl, p] (BASELINE config 5; reference ForwardDiff.jacobian of log D_l, runtests.jl:391-406).
     method = "lanes": as in `sensitivity_matter`; every lane runs sources -> line of sight -> C_l with its OWN τ0 (χ = τ0 − τ, save times)
     on the primal's k-quadrature grid and Chebyshev nodes (grids are index sets, not functions of θ -- as with duals, where the grids
-    are built from values); ln_As1e10 and ns columns come from the primal's Θ_l(k) with the weights ∂P0/∂θ.  method = "fd": round-1 path."""
+    are built from values); ln_As1e10 and ns columns come from the primal's Θ_l(k) with the weights ∂P0/∂θ.  delta: default 1e-4 one-sided
+    (C_l sums ≈6e5 source values per multipole, its rounding noise is ≈1e-7 relative, so a smaller step only amplifies it), 1e-3 with
+    central = True.  method = "fd": round-1 path (independent solves: step-selection noise ≈1e-4 relative in C_l, i.e. ≈0.1 in the quotient)."""
     if method == "fd":
         th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
         pts, h = _central_log_points(th0, relstep)
@@ -1740,7 +1836,8 @@ def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1
         raise ValueError("method must be 'lanes' or 'fd'")
     if len(mode) != 2 or mode[0] not in "TE" or mode[1] not in "TE":
         raise ValueError("sensitivity_cmb handles the T and E modes")
-    lane_names, probs = _lane_problems(prob, names, delta)
+    delta = (1e-3 if central else 1e-4) if delta is None else float(delta)
+    lane_names, probs, steps = _lane_problems(prob, names, delta, central)
     bgs = _lane_backgrounds(probs, bgsol)
     kinterp = kinterp if kinterp is not None else ChebyshevInterpolator(1e-2, 2e3, 60)
     ks_fine, taus0 = cmb_grids(bgs[0], kinterp.minimum(), kinterp.maximum(), dkt0, ntau, taucut)
@@ -1753,7 +1850,7 @@ def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1
         saves.append(tj)
     assert np.array_equal(saves[0], taus0)
     if len(bgs) > 1:
-        sols = solvept_lanes(bgs, kinterp.xs, [0.0] + [1.0 / delta] * (len(bgs) - 1), saveat=saves, sources=dict(nS=2, scale_k=True), **kw)
+        sols = solvept_lanes(bgs, kinterp.xs, [0.0] + [(1.0 / st if norm_partials else 0.0) for st in steps[1:]], saveat=saves, sources=dict(nS=2, scale_k=True), **kw)
     else:
         sols = [solvept(prob, bgs[0], kinterp.xs, saveat=saves[0], sources=dict(nS=2, scale_k=True), keep_states=False, **kw)]
     lnC, theta0, Cl0 = [], None, None
@@ -1764,8 +1861,8 @@ def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1
             theta0, Cl0 = theta, Cl
         lnC.append(np.log(np.abs(Cl)))
     J = np.zeros((len(jl.l), len(names)))
-    for j, n in enumerate(lane_names):
-        J[:, names.index(n)] = (lnC[j + 1] - lnC[0]) / delta
+    for n, q in zip(lane_names, _lane_quotients(lnC, steps, central)):
+        J[:, names.index(n)] = q
     P0 = spectrum_primordial(ks_fine, prob)
     for n in names:
         if n == "ln_As1e10":
@@ -1773,5 +1870,5 @@ def sensitivity_cmb(mode, prob, names, jl, method="lanes", delta=1e-5, relstep=1
         elif n == "ns":  # ∂C_l/∂ns = Σ_k c_k ln(k/kp) Θ^A Θ^B
             dC = spectrum_cmb_from_theta(theta0, [mode], P0 * np.log(ks_fine / prob.derived["kpivot"]), jl.l, ks_fine, normalization).cpu().numpy()[0]
             J[:, names.index(n)] = prob.pars["ns"] * dC / Cl0  # d ln|C| = dC / C
-    info = dict(lanes=len(probs), success=all(s_.success for s_ in sols))
+    info = dict(lanes=len(probs), delta=delta, central=central, success=all(s_.success for s_ in sols), attempts=int((sols[0].stats[:, 0] + sols[0].stats[:, 1]).sum()))
     return (J, info) if return_info else J

@@ -102,14 +102,42 @@ def build_los(force=False, verbose=False):
     return so
 
 
-# BASELINE configs: 1/2 (ΛCDM lmax 10), the reference test fixture (lmax 5), 4 (w0waCDM), 3 (massive-ν momentum grids nx = 8), the reference's "High lmax" test (32)
-DEFAULT_MODELS = [dict(lmax=10, nx=4, w0wa=False), dict(lmax=5, nx=4, w0wa=False), dict(lmax=10, nx=4, w0wa=True), dict(lmax=10, nx=8, w0wa=False), dict(lmax=32, nx=4, w0wa=False)]
+def build_comm(force=False, verbose=False):
+    """libsbc.so: NCCL communicator + exchange steps behind the C ABI (csrc/sb_comm.cu).  Links the NCCL the process will see at run time
+    (soname libnccl.so.2: torch's bundled copy when torch is loaded first, the system copy for a plain C / Julia host)."""
+    so = os.path.join(BUILD_DIR, "libsbc.so")
+    src = os.path.join(CSRC, "sb_comm.cu")
+    if not force and _newer(so, [src]):
+        return so
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    inc, lib = "/usr/include", "/usr/lib/x86_64-linux-gnu"
+    try:
+        import nvidia.nccl as _n  # torch's bundled NCCL (same soname), preferred when present
+        base = list(_n.__path__)[0]
+        if os.path.exists(os.path.join(base, "include", "nccl.h")):
+            inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+    except Exception:
+        pass
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", inc, "-o", so, src, "-L", lib, "-l:libnccl.so.2", "-Xlinker", "-rpath," + lib]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    _stamp(so, [src])
+    return so
 
 
-def build_all(force=False, verbose=False):
-    out = [build_los(force=force, verbose=verbose)]
-    for m in DEFAULT_MODELS:
-        out.append(build_model(force=force, verbose=verbose, **m)[0])
+# BASELINE configs: 1/2 (ΛCDM lmax 10), the reference test fixture (lmax 5), 4 (w0waCDM), 3 (massive-ν momentum grids nx = 8 and 16), the reference's "High lmax" test (32)
+DEFAULT_MODELS = [dict(lmax=10, nx=4, w0wa=False), dict(lmax=5, nx=4, w0wa=False), dict(lmax=10, nx=4, w0wa=True), dict(lmax=10, nx=8, w0wa=False), dict(lmax=32, nx=4, w0wa=False),
+                  dict(lmax=10, nx=16, w0wa=False)]
+
+
+def build_all(force=False, verbose=False, jobs=None):
+    """Everything the tests and the bench load, the model engines in parallel (each is one nvcc process of 0.5-2 minutes)."""
+    import concurrent.futures as cf
+    out = [build_los(force=force, verbose=verbose), build_comm(force=force, verbose=verbose)]
+    jobs = jobs or min(len(DEFAULT_MODELS), os.cpu_count() or 1)
+    with cf.ThreadPoolExecutor(jobs) as pool:
+        out += [r[0] for r in pool.map(lambda m: build_model(force=force, verbose=verbose, **m), DEFAULT_MODELS)]
     return out
 
 

@@ -389,7 +389,18 @@ struct SbSolveArgs {
 #define SB_SM_COSMO (SB_SM_KP + 8 + 48)  // batched launches: the current mode's SbCosmo
 #define SB_SM_SBUF (SB_SM_COSMO + 16)    // fused sources: [3][SB_SWIN] values of the current window of save times
 #define SB_SWIN 16
-#define SB_SM_DOUBLES (SB_SM_SBUF + 3 * SB_SWIN)
+// SB_TMA (A/B switch, default off -- measured slower, profiles/integrate_r2.md): the 2 x 2 β-table rows of the six stage times of an
+// attempt are staged into shared memory by six bulk async copies (cp.async.bulk + mbarrier) instead of being read through L1 with __ldg
+#ifndef SB_TMA
+#define SB_TMA 0
+#endif
+#if SB_TMA
+#define SB_SM_TAB ((SB_SM_SBUF + 3 * SB_SWIN + 1) & ~1) // 16-byte aligned: [6 slots][4 rows][NBETA]
+#define SB_SM_MBAR (SB_SM_TAB + 6 * 4 * SB_NBETA)
+#define SB_SM_DOUBLES ((SB_SM_MBAR + 1 + 1) & ~1)
+#else
+#define SB_SM_DOUBLES ((SB_SM_SBUF + 3 * SB_SWIN + 1) & ~1)
+#endif
 #define SB_SM_BYTES_WARP (SB_SM_DOUBLES * 8)
 #define SB_WARPS_PER_CTA 1
 #ifndef SB_MINBLOCKS
@@ -447,6 +458,24 @@ struct SbSolveArgs {
 #define SB_NOKID 1023
 #define SB_NOPAR 4095
 #endif
+
+// SB_RCP (A/B switch): 1/x as MUFU.RCP64H seed + two Newton steps (not correctly rounded: results differ from the IEEE division in the last
+// bit, so it is off by default -- bit-identity with the queue/batch/lane variants does not depend on it, agreement with round 1 does)
+#ifndef SB_RCP
+#define SB_RCP 0
+#endif
+__device__ __forceinline__ double sb_rcp(double x) {
+#if SB_RCP
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+__device__ __forceinline__ unsigned sb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -530,8 +559,16 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 // Batched look-up of the basis at the stage times of one Rosenbrock attempt: slots 1..5 = t + c_s·dt (and, if with0, slot 0 = t
 // together with ḃ(t)).  Lanes 0..5 locate their slot's table node in parallel and publish (node, w, hs, τ) through shared memory;
 // then all lanes sweep the (slot, basis) items, so that every L2 access of the attempt is in flight at once.
-__device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x8*/, int lane) {
+__device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x8*/, int lane,
+                                              double* tabs = nullptr, unsigned* parity = nullptr) {
     int jend = jt;
+#if SB_TMA
+    const int s0t = with0 ? 0 : 1;
+    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
+    constexpr unsigned ROWB = 4 * SB_NBETA * 8; // two nodes x (β, dβ/dτ): contiguous in the table
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((6 - s0t) * ROWB) : "memory");
+#endif
     if (lane < 6) {
         const double tau = t + ((lane == 0) ? 0.0 : cc[lane]) * dt;
         int j = jt;
@@ -545,10 +582,35 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
         sp[1] = (1 + 2 * w) * w1 * w1; sp[2] = w * w1 * w1 * hs; sp[3] = w * w * (3 - 2 * w); sp[4] = w * w * w1 * hs;
         sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
         jend = j;
+#if SB_TMA
+        if (lane >= s0t) {
+            const double* src = tb.tab + ((size_t)j * tb.msub + sidx) * 2 * SB_NBETA;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
+        }
+#endif
     }
     jend = __shfl_sync(SB_FULL, jend, 5);
     __syncwarp();
     const int s0 = with0 ? 0 : 1;
+#if SB_TMA
+    {
+        const unsigned ph = *parity;
+        asm volatile("{\n .reg .pred p;\n SB_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra SB_WAIT_%=;\n}" ::"r"(mbar), "r"(ph) : "memory");
+        *parity = ph ^ 1u;
+    }
+    for (int q = s0 * SB_NB + lane; q < 6 * SB_NB; q += SB_WARP) {
+        const int s = q / SB_NB, m = q - s * SB_NB;
+        const double* sp = slotp + s * 8;
+        const unsigned pk = sb_basis_pack[m];
+        const int be = SB_LO16(pk);
+        const double* n0 = tabs + s * 4 * SB_NBETA;
+        const double v0 = n0[be], d0 = n0[SB_NBETA + be], v1 = n0[2 * SB_NBETA + be], d1 = n0[3 * SB_NBETA + be];
+        const double kk = kp[SB_HI16(pk)];
+        bs[q] = kk * (sp[1] * v0 + sp[2] * d0 + sp[3] * v1 + sp[4] * d1);
+        if (s == 0) bdv[m] = kk * (sp[5] * (v0 - v1) + sp[6] * d0 + sp[7] * d1);
+    }
+    return jend;
+#endif
     // pull the 2 x 2 table rows of every slot into L1 first (one round trip to L2 for the whole attempt instead of one per sweep iteration)
     {
         constexpr int LINES = (4 * SB_NBETA * 8 + 127) / 128 + 1;
@@ -669,7 +731,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
         if (len > 0) {
             double* dip = di + start; double* mmp = mm + start; double* upp = up + start;
-            double dinv = 1.0 / dip[0];
+            double dinv = sb_rcp(dip[0]);
             dip[0] = dinv;
 #pragma unroll
             for (int pos = 1; pos < SB_PL; pos++) {
@@ -677,7 +739,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
                     const double mr = mmp[pos - 1], u = upp[pos - 1] * dinv;
                     mmp[pos - 1] = mr * dinv;
                     upp[pos - 1] = u;
-                    dinv = 1.0 / fma(-mr, u, dip[pos]);
+                    dinv = sb_rcp(fma(-mr, u, dip[pos]));
                     dip[pos] = dinv;
                 }
             }
@@ -694,7 +756,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             double dj = dip[0];
 #pragma unroll
             for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.rk[rd], c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
-            double dinv = 1.0 / dj;
+            double dinv = sb_rcp(dj);
             dip[0] = dinv;
 #pragma unroll
             for (int pos = 1; pos < SB_TL; pos++) {
@@ -702,7 +764,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
                     const double mr = mmp[pos - 1], u = upp[pos - 1] * dinv;
                     mmp[pos - 1] = mr * dinv;
                     upp[pos - 1] = u;
-                    dinv = 1.0 / fma(-mr, u, dip[pos]);
+                    dinv = sb_rcp(fma(-mr, u, dip[pos]));
                     dip[pos] = dinv;
                 }
             }
@@ -721,7 +783,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             dj = di[S.tv];
 #pragma unroll
             for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
-            if (i >= nb) { di[S.tv] = 1.0 / dj; up[S.tv] = 0; }
+            if (i >= nb) { di[S.tv] = sb_rcp(dj); up[S.tv] = 0; }
         }
 #if SB_GJ_INPLACE
         // In-place Gauss-Jordan: the column of the pivot is overwritten by the corresponding column of the inverse, so only the
@@ -752,7 +814,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             if (isp) myrow = kx;
             perm |= (unsigned)who << (3 * kx);
             const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
-            const double inv = 1.0 / piv;
+            const double inv = sb_rcp(piv);
             const double l = isp ? 0.0 : Ar[kx];
 #pragma unroll
             for (int j = 0; j < SB_TOPMAX; j++) {
@@ -784,7 +846,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
             if (i == who) myrow = kx;
             const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
-            const double inv = 1.0 / piv;
+            const double inv = sb_rcp(piv);
             const double l = (i == who) ? 0.0 : Ar[kx];
 #pragma unroll
             for (int j = 0; j < SB_TOPMAX; j++) {
@@ -1100,7 +1162,7 @@ __global__ void sb_integrate_kernel
 __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_WARPS_PER_CTA, GROUP ? 1 : (BATCH ? SB_MINBLOCKS_BATCH : SB_MINBLOCKS)) sb_integrate_kernel
 #endif
     (const __grid_constant__ SbSolveArgs A) {
-    extern __shared__ double sm_all[];
+    extern __shared__ __align__(16) double sm_all[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 #if SB_WARPS_PER_CTA == 1
@@ -1112,6 +1174,13 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
     double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
            *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
     double* const sbuf = sm + SB_SM_SBUF;
+#if SB_TMA
+    double* const tabs = sm + SB_SM_TAB;
+    unsigned tpar = 0;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_u32(sm + SB_SM_MBAR)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+#endif
     const double reltol = A.reltol, abstol = A.abstol;
     const bool SRC = A.S != nullptr; // fused source evaluation at the save times (scratch: di = state in natural order, up = its derivative, bs = basis)
     SbLane S;
@@ -1272,7 +1341,11 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 double dtc = dt; // the step as the (shared) controller sees it; dt is what this lane integrates over (differs only on the last step of a GROUP lane)
                 if (t + dt >= tend0 - 100 * 2.2e-16 * fabs(tend0)) { dtc = tend0 - t; dt = tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
+#if SB_TMA
+                jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar);
+#else
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
+#endif
                 __syncwarp();
                 if (moved) { sb_eval_f<false>(S, bs, u, f0, lane); nf++; sb_eval_dT(S, bs, bdv, u, dT, lane); moved = false; }
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
@@ -1300,8 +1373,8 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 sb_hub_dots(S, bs, Zp, m11, m21, lane);
                 sb_hub_dots(S, bs, Zq, m12, m22, lane);
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
-                const double idet = 1.0 / (m11 * m22 - m12 * m21);
-                const double idt = 1.0 / dt;
+                const double idet = sb_rcp(m11 * m22 - m12 * m21);
+                const double idt = sb_rcp(dt);
                 // 8 stages.  Per stage: (A) lane-local: finish k_{s-1} with its pending Woodbury correction and accumulate U_s = u + Σ a_sj k_j,
                 // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve.  The hub dot products of the
                 // rank-2 correction k_s += Z c and the correction itself are applied lazily in (A) of the next stage: no extra pass, no extra barrier.

@@ -17,12 +17,15 @@ def _ptr(a):
 def test_abi_exports_every_declared_symbol(sb, prob5):
     """Every function declared in include/symboltz_b200.h is exported by the built libraries."""
     hdr = open(os.path.join(ROOT, "include", "symboltz_b200.h")).read()
-    names = re.findall(r"\b(sb[ml]_\w+)\s*\(", hdr)
-    assert len(names) > 15
-    los = C.CDLL(sb.build.build_los())
+    names = re.findall(r"\b(sb[mlc]_\w+)\s*\(", hdr)
+    assert len(names) > 30 and any(n.startswith("sbc_") for n in names)
+    los, comm = C.CDLL(sb.build.build_los()), C.CDLL(sb.build.build_comm())
     for n in set(names):
-        lib = prob5.lib if n.startswith("sbm_") else los
+        lib = prob5.lib if n.startswith("sbm_") else (comm if n.startswith("sbc_") else los)
         assert hasattr(lib, n), f"{n} not exported"
+    # ownership rules of the sharded paths (same in every host language): strided modes, contiguous fine-k slices
+    assert [comm.sbc_owned_count(10, r, 4) for r in range(4)] == [3, 3, 2, 2] and comm.sbc_owned_index(2, 1, 4) == 9
+    assert [(comm.sbc_slice_begin(2019, r, 8), comm.sbc_slice_end(2019, r, 8)) for r in (0, 7)] == [(0, 252), (1766, 2019)]
     inf = (C.c_int * 16)()
     prob5.lib.sbm_info(inf)
     assert inf[0] == 47 and inf[4] == 5 and inf[5] == 4  # N = 5 + (lmax+1)(3+nx), reference test fixture lmax = 5
@@ -148,7 +151,10 @@ def test_grids(sb):
     assert g[0] == 1e-4 and g[-1] == 1.0 and len(g) == 100 and (np.diff(g) > 0).all()
     assert len(sb.lingrid(0.0, 1.0, step=0.3)) == 5 and sb.lingrid(0.0, 1.0, step=0.3)[-1] == 1.0
     c = sb.cosgrid(0.0, 1.0, length=300)
-    assert c[0] == 0.0 and abs(c[-1] - 1.0) < 1e-15 and len(c) == 300
+    assert c[0] == 0.0 and c[-1] == 1.0 and len(c) == 300 and (np.diff(c) > 0).all()  # cospi: the end points are exact (src/utils.jl:285)
+    assert sb.cospi(0.5) == 0.0 and sb.cospi(1.0) == -1.0 and sb.cospi(1.5) == 0.0 and sb.cospi(2.0) == 1.0
+    xs = np.linspace(0, 0.5, 1001)
+    assert np.abs(sb.cospi(xs) - np.cos(np.pi * xs)).max() < 2e-16
     ch = sb.chebgrid(1.0, 3.0, order=4)
     assert np.allclose(ch, 2 + np.cos(np.pi * np.arange(4, -1, -1) / 4))
     with pytest.raises(ValueError):
