@@ -137,11 +137,13 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
  * (u^j - u^0) / delta_j is the derivative of the discrete solution map, as forward-mode AD gives it, up to O(delta), at the cost of G
  * solves running side by side.  Layout [mode][lane]: dks, dtini, dcosmo_of have nk*G entries (dks[m*G+j] = k_m, dcosmo_of[m*G+j] = j),
  * outputs likewise (duend[nk*G][N], dretcode[nk*G], dstats[nk*G][4], src->dS[nk*G][nS][nsave], dusave optional).  dorder: optional
- * order of the nk groups; invdelta: HOST array of G doubles ([0] unused).  Save decisions and the end of the integration follow the
- * primal's save times / end time; each lane interpolates at its own.  Returns the grid size or a negative error. */
+ * order of the nk groups; invdelta: HOST array of G doubles ([0] unused; 0 leaves a lane's partial out of the norm); tend_common: the
+ * smallest sbm_cosmo_t.tend of the lanes.  The lockstep phase runs to tend_common with save decisions on the primal's save times (each
+ * lane interpolates at its own); then every lane closes with one private step to its own end time ("today" of its cosmology).
+ * Returns the grid size or a negative error. */
 int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
-                      double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, void* stream,
-                      const sbm_src_t* src);
+                      double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, double tend_common,
+                      void* stream, const sbm_src_t* src);
 /* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
  * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
  * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */

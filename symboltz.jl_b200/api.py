@@ -857,7 +857,8 @@ def solvept_lanes(bgsols, ks, invdelta, ptivini=-math.inf, reltol=1e-5, abstol=1
         raise ValueError("solvept_lanes: invdelta needs one entry per lane (the primal's is ignored) or one per non-primal lane")
     prob.lib.sbm_solvept_lanes.restype = C.c_int
     rc = prob.lib.sbm_solvept_lanes(C.c_int(G), _cptr(dcos), C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dcof), _cptr(dorder), C.c_int(ns), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
-                                    _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(invd), _stream(), C.byref(src) if src is not None else None)
+                                    _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(invd), C.c_double(min(b.tau0 for b in bgsols)), _stream(),
+                                    C.byref(src) if src is not None else None)
     if rc < 0:
         raise RuntimeError(f"sbm_solvept_lanes failed with code {rc}")
     sols = []
@@ -872,8 +873,63 @@ def solvept_lanes(bgsols, ks, invdelta, ptivini=-math.inf, reltol=1e-5, abstol=1
 
 
 class CosmologySolution:
-    def __init__(self, prob, bg, ks, pts):
+    """Result of `solve(prob, ks)` (reference CosmologySolution, src/solve.jl:343-378).  Calling it, `sol(vars, τs, ks)`, evaluates perturbation
+    unknowns at arbitrary times and wavenumbers (reference src/solve.jl:720-776): dense output in time for the solved modes, linear
+    interpolation in ktransform(k) (default ln k) between the two neighbouring solved modes."""
+
+    def __init__(self, prob, bg, ks, pts, ptivini=-math.inf, ptopts=None):
         self.prob, self.bg, self.ks, self.pts = prob, bg, ks, pts
+        self._ptivini, self._ptopts, self._dense = ptivini, dict(ptopts or {}), {}
+
+    def _states_at(self, taus):
+        """Dense output of every solved mode at `taus`: one launch with saveat (the solve is deterministic, so this is the interpolant of
+        the step sequence `solve` took); cached per time grid."""
+        key = taus.tobytes()
+        if key not in self._dense:
+            opts = {k: v for k, v in self._ptopts.items() if k not in ("saveat", "sources", "keep_states")}
+            self._dense = {key: solvept(self.prob, self.bg, self.ks, self._ptivini, saveat=taus, warn=False, **opts).usave}
+        return self._dense[key]
+
+    def __call__(self, vars, taus, ks, ktransform=np.log):
+        if self.ks is None or len(self.ks) == 0:
+            raise RuntimeError("No perturbations solved for. Pass ks to solve().")
+        if (np.diff(self.ks) < 0).any():
+            raise RuntimeError("Solution wavenumbers are not sorted in ascending order")
+        scal = (isinstance(vars, str), np.ndim(taus) == 0, np.ndim(ks) == 0)
+        names = self.prob.info["unames"]
+        idx = []
+        for v in ([vars] if scal[0] else list(vars)):
+            if v not in names:
+                raise KeyError(f"{v!r} is not a perturbation unknown of {self.prob.M} (available: {names[:8]} ...)")
+            idx.append(names.index(v))
+        taus = np.ascontiguousarray(np.atleast_1d(taus), dtype=np.float64)
+        kq = np.atleast_1d(np.asarray(ks, dtype=np.float64))
+        kmin, kmax = self.ks[0], self.ks[-1]
+        if kq.min() < kmin:
+            raise ValueError(f"Requested wavenumber k = {kq.min()} is below the minimum solved wavenumber {kmin}")
+        if kq.max() > kmax:
+            raise ValueError(f"Requested wavenumber k = {kq.max()} is above the maximum solved wavenumber {kmax}")
+        U = self._states_at(taus)[:, :, idx]          # [nk_solved][nτ][nvars]
+        out = np.empty((len(idx), len(taus), len(kq)))
+        for ik, k in enumerate(kq):                   # neighboring_modes_indices, src/solve.jl:706-717
+            if k == kmin:
+                i1 = i2 = 0
+            elif k == kmax:
+                i1 = i2 = len(self.ks) - 1
+            else:
+                i2 = int(np.searchsorted(self.ks, k, side="left"))
+                i1 = i2 - 1
+            v = U[i1]
+            if i1 != i2:
+                w = (ktransform(k) - ktransform(self.ks[i1])) / (ktransform(self.ks[i2]) - ktransform(self.ks[i1]))
+                v = v + (U[i2] - U[i1]) * w
+            out[:, :, ik] = v.T
+        out = out[0] if scal[0] else out
+        if scal[1]:
+            out = out[..., 0, :]
+        if scal[2]:
+            out = out[..., 0]
+        return out
 
 
 def solve(prob, ks=None, bgopts=None, ptopts=None, ptivini=-math.inf, **kw):
@@ -882,7 +938,7 @@ def solve(prob, ks=None, bgopts=None, ptopts=None, ptivini=-math.inf, **kw):
     if ks is None or len(np.atleast_1d(ks)) == 0:
         return CosmologySolution(prob, bg, None, None)
     pts = solvept(prob, bg, ks, ptivini, **(ptopts or {}), **kw)
-    return CosmologySolution(prob, bg, np.atleast_1d(ks), pts)
+    return CosmologySolution(prob, bg, np.atleast_1d(np.asarray(ks, dtype=np.float64)), pts, ptivini, dict(ptopts or {}, **{k: v for k, v in kw.items() if k in ("reltol", "abstol", "maxiters", "msub")}))
 
 
 def issuccess(sol):
@@ -1031,6 +1087,115 @@ class ChebyshevInterpolator:
             B = T / T.sum(axis=1, keepdims=True)
         rows = hit.any(axis=1)
         B[rows] = hit[rows].astype(np.float64)
+        return B
+
+
+def _natural_spline_matrix(y, yq):
+    """B[nq, n] with (natural cubic spline through (y, f))(yq) = B f -- the spline is linear in the data (DataInterpolations.CubicSpline)."""
+    y, yq = np.asarray(y, dtype=np.float64), np.asarray(yq, dtype=np.float64)
+    n = len(y)
+    h = np.diff(y)
+    Mmap = np.zeros((n, n))  # second derivatives as a linear map of f; natural ends: M_0 = M_{n-1} = 0
+    if n > 2:
+        A = np.zeros((n - 2, n - 2))
+        R = np.zeros((n - 2, n))
+        for i in range(1, n - 1):
+            A[i - 1, i - 1] = 2 * (h[i - 1] + h[i])
+            if i > 1:
+                A[i - 1, i - 2] = h[i - 1]
+            if i < n - 2:
+                A[i - 1, i] = h[i]
+            R[i - 1, i - 1], R[i - 1, i], R[i - 1, i + 1] = 6 / h[i - 1], -6 / h[i - 1] - 6 / h[i], 6 / h[i]
+        Mmap[1:-1] = np.linalg.solve(A, R)
+    i = np.clip(np.searchsorted(y, yq, side="right") - 1, 0, n - 2)
+    t1, t0, hi = y[i + 1] - yq, yq - y[i], h[i]
+    B = (t1**3 / (6 * hi) - hi * t1 / 6)[:, None] * Mmap[i] + (t0**3 / (6 * hi) - hi * t0 / 6)[:, None] * Mmap[i + 1]
+    rows = np.arange(len(yq))
+    B[rows, i] += t1 / hi
+    B[rows, i + 1] += t0 / hi
+    return B
+
+
+class CubicSplineInterpolator:
+    """Natural cubic spline in y = f(x) through ascending nodes (reference src/observables/fourier.jl:199-231)."""
+
+    def __init__(self, xs, xmax=None, n=None, f=None):
+        if xmax is not None:  # CubicSplineInterpolator(xmin, xmax, n): n + 1 equispaced nodes
+            xs = np.linspace(float(xs), float(xmax), int(n) + 1)
+        self.xs = np.array(xs, dtype=np.float64)
+        if (np.diff(self.xs) <= 0).any():
+            raise ValueError("Input points must be sorted in ascending order")
+        self.f = f if f is not None else (lambda x: x)
+        self.ys = np.asarray(self.f(self.xs), dtype=np.float64)
+
+    def minimum(self):
+        return self.xs[0]
+
+    def maximum(self):
+        return self.xs[-1]
+
+    def matrix(self, x_fine):
+        return _natural_spline_matrix(self.ys, np.asarray(self.f(np.asarray(x_fine, dtype=np.float64)), dtype=np.float64))
+
+
+class EquispacedInterpolator:
+    """Barycentric interpolation on order + 1 equispaced nodes, weights (−1)^j binom(n, j) (reference src/observables/fourier.jl:549-571)."""
+
+    def __init__(self, xmin, xmax, order):
+        if not xmax > xmin:
+            raise ValueError(f"Interval {(xmin, xmax)} is not sorted")
+        self.xs = lingrid(xmin, xmax, length=order + 1)
+        self.ys = self.xs
+        self.ws = np.array([math.comb(order, j) * (1.0 if j % 2 == 0 else -1.0) for j in range(order + 1)])
+        self.f = lambda x: x
+
+    def minimum(self):
+        return self.xs[0]
+
+    def maximum(self):
+        return self.xs[-1]
+
+    matrix = ChebyshevInterpolator.matrix
+
+
+class PiecewiseChebyshevInterpolator:
+    """Chebyshev sub-grids on consecutive intervals sharing their end points (reference src/observables/fourier.jl:477-521); `xs` holds all
+    unique nodes in descending order, `iranges[j]` the slice of `xs` that belongs to sub-grid j (ascending sub-grid order)."""
+
+    def __init__(self, xbreaks, orders, f=None, finv=None):
+        N = len(orders)
+        if len(xbreaks) != N + 1:
+            raise ValueError(f"Need {N + 1} x-breaks for {N} intervals, got {len(xbreaks)}")
+        fs = list(f) if isinstance(f, (tuple, list)) else [f] * N
+        finvs = list(finv) if isinstance(finv, (tuple, list)) else [finv] * N
+        if len(fs) != N or len(finvs) != N:
+            raise ValueError(f"Need {N} f and f⁻¹")
+        self.subgrids = [ChebyshevInterpolator(xbreaks[j], xbreaks[j + 1], orders[j], f=fs[j], finv=finvs[j]) for j in range(N)]
+        xs = list(self.subgrids[-1].xs)
+        for j in range(N - 2, -1, -1):
+            xs += list(self.subgrids[j].xs[1:])
+        self.xs = np.array(xs)
+        self.iranges, i = [None] * N, 0
+        for j in range(N - 1, -1, -1):
+            n = len(self.subgrids[j].xs)
+            self.iranges[j] = slice(i, i + n)
+            i += n - 1
+
+    def minimum(self):
+        return self.xs[-1]
+
+    def maximum(self):
+        return self.xs[0]
+
+    def matrix(self, x_fine):
+        x_fine = np.asarray(x_fine, dtype=np.float64)
+        B = np.zeros((len(x_fine), len(self.xs)))
+        for g, r in zip(self.subgrids, self.iranges):  # a point on a shared break is written twice with the same value (the node's row)
+            m = (x_fine >= g.minimum()) & (x_fine <= g.maximum())
+            if m.any():
+                blk = np.zeros((int(m.sum()), len(self.xs)))
+                blk[:, r] = g.matrix(x_fine[m])
+                B[m] = blk
         return B
 
 

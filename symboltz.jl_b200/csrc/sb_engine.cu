@@ -365,6 +365,7 @@ struct SbSolveArgs {
     int nS, scale_k;
     // parameter lanes in lockstep (sbm_solvept_lanes): G warps of one CTA integrate the same mode for G cosmologies with ONE step controller
     int G;
+    double tendc;       // common end of the lockstep phase = the smallest end time of the lanes; each lane closes with a private step to its own
     double invdelta[8]; // 1/δ_j of lane j (δ_j = parameter step of the lane in the units of the wanted derivative); [0] unused
 };
 #define SB_GROUP_MAX 8
@@ -389,10 +390,12 @@ struct SbSolveArgs {
 #define SB_SM_COSMO (SB_SM_KP + 8 + 48)  // batched launches: the current mode's SbCosmo
 #define SB_SM_SBUF (SB_SM_COSMO + 16)    // fused sources: [3][SB_SWIN] values of the current window of save times
 #define SB_SWIN 16
-// SB_TMA (A/B switch, default off -- measured slower, profiles/integrate_r2.md): the 2 x 2 β-table rows of the six stage times of an
-// attempt are staged into shared memory by six bulk async copies (cp.async.bulk + mbarrier) instead of being read through L1 with __ldg
+// SB_TMA (north star: "tables ... staged to shared memory with TMA"): the 2 x 2 β-table rows of the six stage times of an attempt are
+// staged into shared memory by six 1.3 KB bulk async copies (cp.async.bulk + mbarrier, SASS UBLKCP) instead of being read through L1
+// with prefetch + __ldg.  Same-box A/B (profiles/integrate_r2.md, r2d): +1.8 % attempts/s on a saturated launch, −1.6 % latency of a
+// lone warp, neutral at the bench size; on.
 #ifndef SB_TMA
-#define SB_TMA 0
+#define SB_TMA 1
 #endif
 #if SB_TMA
 #define SB_SM_TAB ((SB_SM_SBUF + 3 * SB_SWIN + 1) & ~1) // 16-byte aligned: [6 slots][4 rows][NBETA]
@@ -459,10 +462,10 @@ struct SbSolveArgs {
 #define SB_NOPAR 4095
 #endif
 
-// SB_RCP (A/B switch): 1/x as MUFU.RCP64H seed + two Newton steps (not correctly rounded: results differ from the IEEE division in the last
-// bit, so it is off by default -- bit-identity with the queue/batch/lane variants does not depend on it, agreement with round 1 does)
+// SB_RCP: 1/x of the pivots (13 per attempt, all on the dependent chain of the factorisation) as MUFU.RCP64H seed + two Newton steps
+// instead of the IEEE division sequence with its slow-path branch.  Same-box A/B (r2d): +4 % attempts/s, −3.6 % lone-warp latency; on.
 #ifndef SB_RCP
-#define SB_RCP 0
+#define SB_RCP 1
 #endif
 __device__ __forceinline__ double sb_rcp(double x) {
 #if SB_RCP
@@ -1223,11 +1226,13 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
         const double k = A.ks[mode];
         double t = A.tini[mode];
         const double tend = CC.tend;
-        // GROUP: every decision that steers the step sequence is taken on the PRIMAL lane's end time and save times (each lane still
-        // integrates to its own end time and interpolates at its own save times: they differ by O(δ))
+        // GROUP: every decision that steers the step sequence is taken on COMMON data -- the smallest end time of the lanes and the primal
+        // lane's save times (each lane interpolates at its own save times, which differ by O(δ), and, after the last common step, closes
+        // with one private step to its own end time: its own "today")
         const SbCosmo* const C0 = GROUP ? A.cosmos + A.cosmo_of[mode - warp] : nullptr;
-        const double tend0 = GROUP ? C0->tend : tend;
+        const double tend0 = GROUP ? A.tendc : tend;
         const double* const saveat0 = GROUP ? C0->saveat : CC.saveat;
+        bool closing = false; // GROUP: the private closing step of this lane
         long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
         int rc = SB_RC_SUCCESS, isave = 0;
         double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
@@ -1339,7 +1344,8 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 }
                 bool last = false;
                 double dtc = dt; // the step as the (shared) controller sees it; dt is what this lane integrates over (differs only on the last step of a GROUP lane)
-                if (t + dt >= tend0 - 100 * 2.2e-16 * fabs(tend0)) { dtc = tend0 - t; dt = tend - t; last = true; }
+                if (GROUP && closing) last = true; // dt = tend − t was set when the lockstep phase ended
+                else if (t + dt >= tend0 - 100 * 2.2e-16 * fabs(tend0)) { dtc = tend0 - t; dt = GROUP ? dtc : tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
 #if SB_TMA
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar);
@@ -1462,7 +1468,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 __syncwarp();
                 // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
                 double es = 0; bool bad = false;
-                if (GROUP) {
+                if (GROUP && !closing) {
                     // publish (u_n, u_{n+1}, k_8) of this lane, then every warp forms the SAME norm over primal and partials:
                     // r_i = Dual(k8_i) / (abstol + reltol·max(‖u_n,i‖, ‖u_{n+1},i‖)), ‖x‖² = x² + Σ_j (∂_j x)², EEst² = Σ_i ‖r_i‖² / N
                     const int G = A.G;
@@ -1487,23 +1493,26 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
                 double EEst = sqrt(warp_sum(es) / SB_N);
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
+                if (GROUP && closing) { if (!isfinite(EEst)) { rc = SB_RC_UNSTABLE; break; } EEst = fmin(EEst, 1.0); } // the closing step (O(δ) long) is taken as it is
                 if (!isfinite(EEst)) { nreject++; dt = dtc / 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
                 double q = ctl.q_of(EEst);
                 if (EEst > 1) { nreject++; dt = ctl.reject(dtc); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
                 const double dtnew = ctl.accept(dtc, q, EEst);
-                const double tn = last ? tend : t + dt;
-                const double tn0 = GROUP ? (last ? tend0 : t + dtc) : tn;
-                if (isave < A.nsave && saveat0[isave] <= tn0) { // dense output (4th order), vectors stored over dT, f0, Zp
+                const bool common = GROUP && !closing;                                   // lockstep phase: decisions on common data
+                const double tn = last ? (common ? tend0 : tend) : t + dt;
+                const double tn0 = common ? (last ? tend0 : t + dtc) : tn;
+                const double* const svd = common ? saveat0 : CC.saveat;
+                if (isave < A.nsave && svd[isave] <= tn0) { // dense output (4th order), vectors stored over dT, f0, Zp
                     for (int i = lane; i < SB_N; i += SB_WARP) {
                         double a1 = 0, a2 = 0, a3 = 0;
                         for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
                         dT[i] = a1; f0[i] = a2; Zp[i] = a3;
                     }
-                    while (isave < A.nsave && saveat0[isave] <= tn0) {
+                    while (isave < A.nsave && svd[isave] <= tn0) {
                         const double ts = CC.saveat[isave];
                         const double th = (ts - t) / dt, t1 = 1 - th;
-                        const bool atend = GROUP ? (saveat0[isave] == tn0) : (ts == tn); // a save time that IS the step end takes the step result
+                        const bool atend = svd[isave] == tn0; // a save time that IS the step end takes the step result
                         for (int i = lane; i < SB_N; i += SB_WARP) {
                             const double un = U[i] + K[7 * SB_N + i];
                             const double v = atend ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
@@ -1523,7 +1532,10 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 bad = __any_sync(SB_FULL, bad);
                 __syncwarp();
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
-                if (last) break;
+                if (last) {
+                    if (GROUP && !closing && tend > t) { closing = true; dt = tend - t; jt = jend; moved = true; continue; } // private closing step to this lane's own end time
+                    break;
+                }
                 dt = dtnew;
                 jt = jend;
                 moved = true;
@@ -1536,6 +1548,15 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             continue;
         }
         for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
+        if (GROUP && rc == SB_RC_SUCCESS) // the lane whose end time IS the common one has no closing step: its save times at the end are due now
+            while (isave < A.nsave && CC.saveat[isave] <= t) {
+                if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = u[i];
+                if (SRC) {
+                    sb_source_point(S, CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, t, CC.taurec, A.scale_k, A.nS, u, up, bs, bs + SB_NB, sbuf + (isave & (SB_SWIN - 1)), SB_SWIN, lane);
+                    sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
+                }
+                isave++;
+            }
         for (; isave < A.nsave; isave++) { // save times the mode never reached (failed solve)
             if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
             if (SRC) { if (lane < A.nS) sbuf[lane * SB_SWIN + (isave & (SB_SWIN - 1))] = NAN; sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane); }
@@ -1725,11 +1746,13 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
 // controller whose error norm covers the primal and the partials (u^j − u^0)·invdelta[j] (see sb_integrate_kernel<.., GROUP>).
 // Arrays are laid out [mode][lane]: dks/dtini/dcosmo_of have nk·G entries with dks[m·G + j] = k_m and dcosmo_of[m·G + j] = j;
 // outputs likewise (duend[nk·G][N], dretcode[nk·G], dstats[nk·G][4], src->dS[nk·G][nS][nsave]).  dorder: optional order of the
-// nk groups.  invdelta: host array of G doubles ([0] unused).  Cost: G solves running side by side, i.e. (1 + p)× one solve.
+// nk groups.  invdelta: host array of G doubles ([0] unused); tend_common: the smallest end time (sbm_cosmo_t.tend) of the lanes -- the
+// lockstep phase ends there and every lane closes with one private step to its own end time.  Cost: G solves running side by side.
 int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol, double abstol,
-                      int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, void* stream, const sbm_src_t* src) {
+                      int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, double tend_common, void* stream,
+                      const sbm_src_t* src) {
     const int G = ncosmo;
-    if (G < 2 || G > SB_GROUP_MAX || !dcosmos || !dcosmo_of || !invdelta) return -1;
+    if (G < 2 || G > SB_GROUP_MAX || !dcosmos || !dcosmo_of || !invdelta || !(tend_common > 0)) return -1;
     if (nk <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SbSolveArgs A;
@@ -1741,7 +1764,7 @@ int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks
     A.S = fused ? src->dS : nullptr; A.nS = fused ? src->nS : 0; A.scale_k = fused ? src->scale_k : 0;
     A.nk = nk * G; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = (dusave || fused) ? nsave : 0;
     A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
-    A.G = G;
+    A.G = G; A.tendc = tend_common;
     for (int j = 0; j < SB_GROUP_MAX; j++) A.invdelta[j] = j < G ? invdelta[j] : 0.0;
     SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
     const size_t smem = ((size_t)G * SB_SM_DOUBLES + SB_XCH_HDR + (size_t)2 * G * 3 * SB_N) * sizeof(double);

@@ -606,3 +606,42 @@ def test_library_communicator_single_rank_and_sharded_api(sb, prob5, bg5):
     b = sb.spectrum_cmb(["TT", "EE"], prob5, jl, bgsol=bg5, group=comm)
     assert np.array_equal(a, b)
     comm.close()
+
+
+def test_solution_object_interpolates_in_time_and_k(sb, oracle, prob5, bg5, obg_same):
+    """`sol(vars, τs, ks)` (reference src/solve.jl:720-776): dense output in time for the solved modes, linear
+    interpolation in ln k between neighbouring modes; the reference's argument checks; spectrum_cmb through another k-interpolator
+    (natural cubic spline in ln k, src/observables/fourier.jl:199-231) on the same GPU kernels."""
+    ks = np.geomspace(0.5, 200.0, 12)
+    sol = sb.solve(prob5, ks)
+    assert sb.issuccess(sol)
+    taus = np.geomspace(1e-3, sol.bg.tau0 * 0.99, 9)
+    names = prob5.info["unames"]
+    vs = ["Phi", "dc", "F2"]
+    out = sol(vs, taus, ks[[0, 5, 11]])
+    direct = sb.solvept(prob5, sol.bg, ks[[0, 5, 11]], saveat=taus).usave
+    assert out.shape == (3, 9, 3)
+    for iv, v in enumerate(vs):
+        assert np.array_equal(out[iv], direct[:, :, names.index(v)].T)  # at a solved wavenumber: that mode's dense output
+    kmid = float(np.sqrt(ks[3] * ks[4]))
+    both = sb.solvept(prob5, sol.bg, ks[[3, 4]], saveat=taus).usave[:, :, names.index("dc")]
+    assert np.allclose(sol("dc", taus, kmid), 0.5 * (both[0] + both[1]), rtol=1e-12)  # midpoint in ln k
+    assert np.allclose(sol("dc", taus, kmid, ktransform=lambda k: k), both[0] + (both[1] - both[0]) * (kmid - ks[3]) / (ks[4] - ks[3]), rtol=1e-12)
+    assert np.ndim(sol("Phi", taus[2], kmid)) == 0 and sol(vs, taus[2], ks[:2]).shape == (3, 2)
+    osol = oracle.solvept(obg_same, ks[[0, 5]], saveat=taus)
+    ref = osol["usave"][:, :, 0]  # Φ is the first unknown of the oracle's state as well
+    assert np.abs(out[0][:, :2].T - ref).max() <= 1e-5 * np.abs(ref).max()
+    with pytest.raises(ValueError):
+        sol("Phi", taus, 0.1)
+    with pytest.raises(ValueError):
+        sol("Phi", taus, 500.0)
+    with pytest.raises(KeyError):
+        sol("nonsense", taus, 1.0)
+    with pytest.raises(RuntimeError):
+        sb.solve(prob5)("Phi", taus, 1.0)
+    # another k-interpolator on the same GPU path: natural cubic spline in ln k through 80 log-spaced nodes
+    ls = np.array([30, 200, 800])
+    jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * bg5.tau0)
+    cheb = sb.spectrum_cmb(["TT", "EE"], prob5, jl, bgsol=bg5)
+    cub = sb.spectrum_cmb(["TT", "EE"], prob5, jl, bgsol=bg5, kinterp=sb.CubicSplineInterpolator(np.geomspace(1e-2, 2e3, 80), f=np.log))
+    assert np.abs(cub / cheb - 1).max() < 0.05

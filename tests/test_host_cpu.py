@@ -346,3 +346,30 @@ def test_lockstep_background_is_smooth_in_the_parameters(sb, prob5, bg5):
     assert abs(part[1e-6][1] / part[2e-6][1] - 1) < 1e-5 and part[1e-6][1] < 0  # more matter -> earlier today
     with pytest.raises(RuntimeError):
         sb.solvebg_lock(upd([prob5.pars["Omega_c"] * 1.5]), bg5)  # a step that changes the number of solver steps is refused
+
+
+def test_alternative_k_interpolators(sb):
+    """the reference's other k-interpolators (src/observables/fourier.jl:199-231, 477-521, 549-571) as weight matrices
+    for the same GPU k-interpolation / fused line-of-sight kernels.  Known answers: the natural spline reproduces scipy's, barycentric
+    interpolation is exact for polynomials up to the order, the piecewise grid keeps the reference's node bookkeeping."""
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(2)
+    xq = np.sort(rng.uniform(1.0, 9.0, 50))
+    cs = sb.CubicSplineInterpolator(np.array([1.0, 1.5, 2.7, 4.0, 6.5, 9.0]), f=np.log)
+    fv = rng.standard_normal(6)
+    assert np.allclose(cs.matrix(xq) @ fv, CubicSpline(np.log(cs.xs), fv, bc_type="natural")(np.log(xq)), rtol=0, atol=1e-13)
+    assert np.allclose(cs.matrix(cs.xs), np.eye(6), atol=1e-14) and (cs.minimum(), cs.maximum()) == (1.0, 9.0)
+    assert len(sb.CubicSplineInterpolator(0.0, 1.0, n=4).xs) == 5
+    with pytest.raises(ValueError):
+        sb.CubicSplineInterpolator(np.array([2.0, 1.0]))
+    eq = sb.EquispacedInterpolator(1.0, 9.0, 5)
+    poly = lambda x: 3 - x + 0.2 * x**3 - 0.01 * x**5
+    assert np.allclose(eq.matrix(xq) @ poly(eq.xs), poly(xq), rtol=1e-11) and np.array_equal(eq.matrix(eq.xs), np.eye(6))
+    pw = sb.PiecewiseChebyshevInterpolator([1.0, 3.0, 9.0], [4, 6])
+    assert len(pw.xs) == 5 + 7 - 1 and (np.diff(pw.xs) < 0).all() and pw.minimum() == 1.0 and pw.maximum() == 9.0
+    assert pw.iranges[1] == slice(0, 7) and pw.iranges[0] == slice(6, 11) and pw.xs[6] == 3.0
+    p4 = lambda x: 1 + x - 0.3 * x**2 + 0.05 * x**4
+    assert np.allclose(pw.matrix(xq) @ p4(pw.xs), p4(xq), rtol=1e-11)
+    assert np.array_equal(pw.matrix(np.array([3.0]))[0], np.eye(11)[6])
+    with pytest.raises(ValueError):
+        sb.PiecewiseChebyshevInterpolator([1.0, 2.0], [3, 3])
