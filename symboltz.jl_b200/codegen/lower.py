@@ -579,18 +579,86 @@ def generate(m: Model):
         kids += [NONE] * (3 - len(kids))
         return kids[0] | (kids[1] << BITS) | (kids[2] << (2 * BITS))
 
-    def _paths(plist, rounds, lane0):
+    def _halfwarp_lanes(plist):
+        """Lanes of the (at most 32) paths of one round.  64-bit shared-memory accesses are served per half-warp and the sweeps address
+        (end of path) − q from every lane at once, so two paths of one half-warp whose ends (substitution sweeps, weight 2) or starts
+        (factorisation sweep, weight 1) are congruent modulo 16 doubles cost an extra wavefront per access: split the paths over the two
+        half-warps so that as few as possible collide (round 1 put them on lanes 0, 1, 2, ...: all in one half-warp, three colliding pairs
+        at N = 82, +50 % wavefronts in the sweeps, profiles/integrate_r2.md).  Lanes without a path get a dummy head (length 0) whose
+        unconditional loads fall into a bank none of the half-warp's paths uses."""
+        import random
+        n = len(plist)
+        ends = [inv[p[-1]] % 16 for p in plist]
+        starts = [inv[p[0]] % 16 for p in plist]
+        lens = [len(p) for p in plist]
+
+        def cost(side):
+            c = 0
+            for a in range(n):
+                for b in range(a):
+                    if side[a] == side[b]:
+                        w = min(lens[a], lens[b])
+                        c += (2 * w if ends[a] == ends[b] else 0) + (w if starts[a] == starts[b] else 0)
+            return c
+        rng = random.Random(4242)
+        best, bestc = None, None
+        for restart in range(30):
+            side = [(q + restart) % 2 for q in range(n)] if restart < 2 else [rng.randrange(2) for _ in range(n)]
+            while side.count(0) > 16 or side.count(1) > 16:
+                i = rng.randrange(n)
+                side[i] = 1 - side[i] if side.count(side[i]) > 16 else side[i]
+            c = cost(side)
+            for it in range(3000):
+                if c == 0:
+                    break
+                i = rng.randrange(n)
+                j = rng.randrange(n)
+                trial = list(side)
+                if rng.random() < 0.5:
+                    trial[i] = 1 - trial[i]
+                else:
+                    trial[i], trial[j] = trial[j], trial[i]
+                if trial.count(0) > 16 or trial.count(1) > 16:
+                    continue
+                tc = cost(trial)
+                if tc <= c:
+                    side, c = trial, tc
+            if bestc is None or c < bestc:
+                best, bestc = list(side), c
+            if bestc == 0:
+                break
+        lanes, nxt = [0] * n, [0, 16]
+        for q in range(n):
+            lanes[q] = nxt[best[q]]
+            nxt[best[q]] += 1
+        dummies = []
+        for h in (0, 1):
+            used = {ends[q] for q in range(n) if best[q] == h}
+            free = [r for r in range(16) if r not in used] or [0]
+            # a dummy of length 0 at `start` reads like a path that ends at start − 1; keep every offset (down to −PL − 1) inside [0, N)
+            start = next(i for i in range(PL + 2, N) if (i - 1) % 16 == free[len(free) // 2])
+            dummies.append(start)
+        return lanes, dummies
+
+    def _paths(plist, rounds, lane0, spread=False):
         head, kid = [0] * (rounds * 32), [NOKIDS] * (rounds * 32)
-        for q, p in enumerate(plist):
-            rd, lane = q // 32, (q + lane0) % 32
-            start = inv[p[0]]
-            assert [inv[v] for v in p] == list(range(start, start + len(p)))
-            par = L.parent[p[-1]]
-            par = NOPAR if par < 0 else inv[par]
-            head[rd * 32 + lane] = start | (len(p) << LSH) | (par << PSH)
-            kid[rd * 32 + lane] = _kids(p[0])
+        for rd in range(rounds):
+            chunk = plist[rd * 32:(rd + 1) * 32]
+            if spread and chunk:
+                lanes, dummies = _halfwarp_lanes(chunk)
+                for lane in range(32):
+                    head[rd * 32 + lane] = dummies[lane // 16] | (0 << LSH) | (NOPAR << PSH)
+            else:
+                lanes = [(q + lane0) % 32 for q in range(len(chunk))]
+            for p, lane in zip(chunk, lanes):
+                start = inv[p[0]]
+                assert [inv[v] for v in p] == list(range(start, start + len(p)))
+                par = L.parent[p[-1]]
+                par = NOPAR if par < 0 else inv[par]
+                head[rd * 32 + lane] = start | (len(p) << LSH) | (par << PSH)
+                kid[rd * 32 + lane] = _kids(p[0])
         return head, kid
-    p_head, p_kids = _paths(paths0, PR, 0)
+    p_head, p_kids = _paths(paths0, PR, 0, spread=True)
     r_head, r_kids = _paths(rpaths, max(1, TR), 8 * len(top_blocks) + len(singles))
     t_kids, t_vert = [NOKIDS] * 32, [NONE] * 32
     for q, v in enumerate(singles):

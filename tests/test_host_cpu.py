@@ -293,7 +293,7 @@ def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
         assert sorted(arr("sb_nat")) == list(range(N))
         bits8 = "#define SB_IDXBITS 8" in text
         heads = arr("sb_path_head")
-        covered, ends = set(), []
+        covered, ends, dummies = set(), [], []
         for slot, v in enumerate(heads):
             start, ln = (v & 255, (v >> 8) & 255) if bits8 else (v & 4095, (v >> 12) & 255)
             if ln:
@@ -301,9 +301,14 @@ def test_generated_path_layout_is_a_permutation_with_few_bank_collisions(sb):
                 assert start + ln <= N and not (rng_ & covered)
                 covered |= rng_
                 ends.append(((slot % 32) // 16, (start + ln - 1) % 16, ln))  # 64-bit accesses are served per half-warp
+            else:  # lane without a path: its unconditional loads (offsets down to −PL − 1 from start − 1) stay inside the arrays
+                assert int(re.search(r"#define SB_PL (\d+)", text).group(1)) + 2 <= start < N
+                dummies.append(((slot % 32) // 16, (start - 1) % 16))
         weight = sum(min(a[2], b[2]) for i, a in enumerate(ends) for b in ends[:i] if a[:2] == b[:2])
-        if M.lmax <= 10 and M.nx == 4:  # the models of BASELINE configs 1, 2 and 4 (16-17 paths: they can be kept apart)
-            assert weight <= 6, (M, weight, ends)
+        if M.lmax <= 10 and M.nx == 4:  # the models of BASELINE configs 1, 2 and 4 (16-17 paths split over the two half-warps): conflict-free sweeps
+            assert weight == 0, (M, weight, ends)
+            assert {e[0] for e in ends} == {0, 1}
+            assert not any((h, r) in {(e[0], e[1]) for e in ends} for (h, r) in set(d for d in dummies)), "a dummy lane shares a bank with a path"
 
 
 def test_build_cli_and_freshness_stamps(sb, prob5, tmp_path):
