@@ -646,3 +646,48 @@ def test_solution_object_interpolates_in_time_and_k(sb, oracle, prob5, bg5, obg_
     cheb = sb.spectrum_cmb(["TT", "EE"], prob5, jl, bgsol=bg5)
     cub = sb.spectrum_cmb(["TT", "EE"], prob5, jl, bgsol=bg5, kinterp=sb.CubicSplineInterpolator(np.geomspace(1e-2, 2e3, 80), f=np.log))
     assert np.abs(cub / cheb - 1).max() < 0.05
+
+
+def test_plan_restage_and_scheduled_sweep(sb, prob5, bg5):
+    """(a) `CMBPlan.stage(bg)` re-targets a plan at another cosmology with EVERYTHING that depends on it (knots,
+    parameters, interval look-up, fine k-grid, save times, χ, trapezoid and C_l weights): the re-staged plan equals `spectrum_cmb` of
+    that cosmology; a cosmology whose grids have other sizes is refused.  (b) `spectrum_matter_sweep(cost=...)` keeps several statically
+    scheduled launches in flight: each gets its share of the resident warps (`max_lists`), results stay bit-identical to the queue."""
+    import math
+    ls = np.array([10, 80, 300, 900])
+    jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * bg5.tau0 * 1.01)
+    plan = sb.CMBPlan(prob5, bg5, jl, modes=("TT", "EE", "TE"), direct=False)
+    a = plan.run_e2e()
+    assert np.allclose(a, sb.spectrum_cmb(["TT", "EE", "TE"], prob5, jl, bgsol=bg5), rtol=1e-12, atol=0)
+    upd = sb.parameter_updater(prob5, ["Omega_c", "ns", "h"])
+    staged = False
+    for shift in (2e-4, 1e-4, 3e-4, 5e-5, 4e-4):  # the fine k-grid has ceil((kmax − kmin)τ0/π) + 1 points: a shift of τ0 can change the count, which stage() refuses
+        p2 = upd([prob5.pars["Omega_c"] * math.exp(shift), prob5.pars["ns"] * 1.01, prob5.pars["h"] * math.exp(-shift / 2)])
+        b2 = sb.solvebg_lock(p2, bg5)  # same number of knots as the plan was built for
+        try:
+            plan.stage(b2)
+            staged = True
+            break
+        except ValueError:
+            continue
+    assert staged
+    b = plan.run_e2e()
+    ref = sb.spectrum_cmb(["TT", "EE", "TE"], p2, jl, bgsol=b2)
+    assert np.allclose(b, ref, rtol=1e-12, atol=0) and np.abs(b / a - 1).max() > 1e-4
+    pars = dict(prob5.pars)
+    pars["Omega_c"] *= 1.3
+    with pytest.raises(ValueError):
+        plan.stage(sb.solvebg(sb.CosmologyProblem(prob5.M, pars)))
+    # (b) scheduled sweep, two stream slots in flight
+    M = sb.w0waCDM(lmax=10)
+    prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+    names = ["h", "Omega_c", "w0", "wa"]
+    rng = np.random.default_rng(4)
+    th = np.array([0.6736, 0.2645, -0.9, 0.1]) * (1 + 0.04 * (rng.random((8, 4)) - 0.5))
+    ks = sb.loggrid(1e-4, 1.0, length=48) / sb.k0
+    P0, i0 = sb.spectrum_matter_sweep(prob, names, th, ks, chunk=2, return_info=True)
+    cost = lambda k: 200 + 2.5 * np.nan_to_num(k)
+    P1, i1 = sb.spectrum_matter_sweep(prob, names, th, ks, chunk=2, return_info=True, cost=cost)
+    assert i0["mode_failures"] == 0 and i1["mode_failures"] == 0 and i1["launches"] == 4
+    assert np.array_equal(P0, P1)
+    assert sb.spectrum_matter_sweep(prob, names, np.zeros((0, 4)), ks).shape == (0, len(ks))
