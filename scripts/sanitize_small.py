@@ -4,7 +4,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import symboltz.jl_b200 as sb
-for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10)):
+FAST = os.environ.get("SB_SANITIZE_FAST") == "1"  # memcheck in ≈2 minutes: one model, a coarse k-interpolator for the C_l call
+for M in ((sb.ΛCDM(lmax=5),) if FAST else (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10))):
     prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
     bg = sb.solvebg(prob)
     ks = np.array([0.5, 20.0, 300.0, 1500.0])
@@ -18,7 +19,7 @@ for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10)):
     print(M, "P(k)", P, "sched == queue", np.array_equal(s1.uend, s2.uend), "batch == queue", np.array_equal(b.sols[1].uend, s1.uend))
 ls = np.array([10, 100, 1000])
 jl = sb.SphericalBesselCache(ls, xmax=2.1e3 * bg.tau0)
-print(sb.spectrum_cmb(["TT", "EE"], prob, jl, bgsol=bg)[:, 0])
+print(sb.spectrum_cmb(["TT", "EE"], prob, jl, bgsol=bg, kinterp=sb.ChebyshevInterpolator(1e-2, 400.0, 10) if FAST else None)[:, 0])
 d = sb.solvebg_batch([prob, prob])
 print("device bg tau0", d[0].tau0, bg.tau0)
 # round 2: fused sources (queue, static schedule with parking, batched) and the lockstep parameter lanes
