@@ -1931,7 +1931,26 @@ def _lane_backgrounds(probs, bgsol=None):
     bg0 = bgsol if bgsol is not None else solvebg(probs[0])
     if not bg0.success:
         raise RuntimeError("sensitivity: the primal background solve failed")
-    return [bg0] + [solvebg_lock(p, bg0) for p in probs[1:]]
+    return [solvebg_lock(p, bg0) for p in probs]  # lane 0 too: the primal re-solved on its own steps shares the lanes' arithmetic path (rounding cancels in the quotients)
+
+
+def sensitivity_background(prob, names, delta=1e-6, bgsol=None):
+    """dτ0/dθ_j and dκ0/dθ_j (derivatives with respect to θ itself, as the reference's "Background differentiation test",
+    test/runtests.jl:480-491, which pushes ForwardDiff duals through `solvebg`): lockstep background lanes (`solvebg_lock`), one per
+    parameter, on the primal's step sequence -- the quotient is the derivative of the discrete solution map including the moving
+    event time.  Returns dict(tau0 = [p], kappa0 = [p])."""
+    bg0 = bgsol if bgsol is not None else solvebg(prob)
+    bg0 = solvebg_lock(prob, bg0)  # the primal re-solved on its own steps: the same arithmetic path as the lanes, so that rounding cancels in the quotient
+    upd = parameter_updater(prob, list(names))
+    th0 = np.array([prob.pars[n] for n in names], dtype=np.float64)
+    dt0, dk0 = np.zeros(len(names)), np.zeros(len(names))
+    for j in range(len(names)):
+        h = delta * max(abs(th0[j]), 1e-300)
+        th = th0.copy()
+        th[j] += h
+        lane = solvebg_lock(upd(th), bg0)
+        dt0[j], dk0[j] = (lane.tau0 - bg0.tau0) / h, (lane.kappa0 - bg0.kappa0) / h
+    return dict(tau0=dt0, kappa0=dk0)
 
 
 def sensitivity_matter(prob, names, ks, method="lanes", delta=None, central=False, norm_partials=True, relstep=1e-3, kτini=1e-2, τinimax=1e-4, bgsol=None, return_info=False, **kw):

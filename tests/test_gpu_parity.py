@@ -691,3 +691,12 @@ def test_plan_restage_and_scheduled_sweep(sb, prob5, bg5):
     assert i0["mode_failures"] == 0 and i1["mode_failures"] == 0 and i1["launches"] == 4
     assert np.array_equal(P0, P1)
     assert sb.spectrum_matter_sweep(prob, names, np.zeros((0, 4)), ks).shape == (0, len(ks))
+
+
+def test_matter_spectrum_converged_to_a_permille(sb, prob5):
+    """Reference "Matter power spectrum converged to 0.1%" (test/runtests.jl:624-630): P(k) at the default tolerances against
+    reltol = abstol = 1e-10 in background and perturbations, 100 k in 1e-1 … 1e4 H0/c starting at the first background time: every k within 1e-3."""
+    ks = 10 ** np.linspace(-1, 4, 100)
+    P0 = sb.spectrum_matter(prob5, ks, kτini=0.0, τinimax=0.0, bgsol=sb.solvebg(prob5, reltol=1e-10, abstol=1e-10), reltol=1e-10, abstol=1e-10, maxiters=1000000)
+    P = sb.spectrum_matter(prob5, ks)
+    assert np.isfinite(P0).all() and np.abs(P / P0 - 1).max() < 1e-3

@@ -378,3 +378,23 @@ def test_alternative_k_interpolators(sb):
     assert np.array_equal(pw.matrix(np.array([3.0]))[0], np.eye(11)[6])
     with pytest.raises(ValueError):
         sb.PiecewiseChebyshevInterpolator([1.0, 2.0], [3, 3])
+
+
+def test_background_differentiation(sb, prob5, bg5):
+    """Reference "Background differentiation test" (test/runtests.jl:480-491): dτ0/dθ for θ = (h, Ω_c, Ω_b, T0, Neff, m_eV, YHe, ln 10¹⁰As, n_s)
+    from the lockstep background lanes against central differences of independent tight-tolerance solves, atol 1e-2 (the reference's
+    bound; measured ≈1e-6); parameters that do not enter the expansion (YHe, A_s, n_s) have exactly vanishing derivatives."""
+    names = ["h", "Omega_c", "Omega_b", "T0", "Neff", "m_eV", "YHe", "ln_As1e10", "ns"]
+    g = sb.sensitivity_background(prob5, names, bgsol=bg5)["tau0"]
+    fd = np.zeros(len(names))
+    for j, n in enumerate(names):
+        x = prob5.pars[n]
+        h = 1e-4 * abs(x)
+        tp = sb.solvebg(sb.parameter_updater(prob5, [n])([x + h]), reltol=1e-11, abstol=1e-11).tau0
+        tm = sb.solvebg(sb.parameter_updater(prob5, [n])([x - h]), reltol=1e-11, abstol=1e-11).tau0
+        fd[j] = (tp - tm) / (2 * h)
+    assert np.abs(g - fd).max() < 1e-2, (g, fd)
+    assert np.abs(g[:6] / fd[:6] - 1).max() < 1e-3
+    # A_s and n_s do not enter the background at all: exactly zero.  YHe enters only the recombination unknowns; the expansion a(τ) shares
+    # the pivoted 5×5 solves with them, so τ0 moves in its last bits (1e-14 relative) and the quotient is rounding noise, not zero.
+    assert (g[-2:] == 0).all() and abs(g[-3]) < 1e-6 and (np.abs(fd[-3:]) < 1e-2).all()
