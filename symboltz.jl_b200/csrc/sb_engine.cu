@@ -467,6 +467,12 @@ struct SbSolveArgs {
 #ifndef SB_RCP
 #define SB_RCP 1
 #endif
+#ifndef SB_BSLOT   // slot-major basis sweep (TMA build only), see sb_basis_batch
+#define SB_BSLOT 1
+#endif
+#ifndef SB_NORMRCP // error norm: k8 · rcp(scale) instead of k8 / scale
+#define SB_NORMRCP 1
+#endif
 __device__ __forceinline__ double sb_rcp(double x) {
 #if SB_RCP
     double r;
@@ -601,6 +607,32 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
         asm volatile("{\n .reg .pred p;\n SB_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra SB_WAIT_%=;\n}" ::"r"(mbar), "r"(ph) : "memory");
         *parity = ph ^ 1u;
     }
+#if SB_BSLOT
+    // slot-major sweep on the lane's register-resident basis descriptors (S.bp): no integer division, no table load per item, the slot's
+    // Hermite weights are warp-uniform broadcasts; same expression per item as the item-major sweep below (bit-identical)
+    {
+        double kk[SB_NBR];
+        int be[SB_NBR];
+#pragma unroll
+        for (int r = 0; r < SB_NBR; r++) { be[r] = SB_LO16(S.bp[r]); kk[r] = kp[SB_HI16(S.bp[r])]; }
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            if (s == 0 && !with0) continue;
+            const double* sp = slotp + s * 8;
+            const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
+            const double* n0 = tabs + s * 4 * SB_NBETA;
+#pragma unroll
+            for (int r = 0; r < SB_NBR; r++) {
+                const int m = r * 32 + lane;
+                if (m < SB_NB) {
+                    const double v0 = n0[be[r]], d0 = n0[SB_NBETA + be[r]], v1 = n0[2 * SB_NBETA + be[r]], d1 = n0[3 * SB_NBETA + be[r]];
+                    bs[s * SB_NB + m] = kk[r] * (w1 * v0 + w2 * d0 + w3 * v1 + w4 * d1);
+                    if (s == 0) bdv[m] = kk[r] * (sp[5] * (v0 - v1) + sp[6] * d0 + sp[7] * d1);
+                }
+            }
+        }
+    }
+#else
     for (int q = s0 * SB_NB + lane; q < 6 * SB_NB; q += SB_WARP) {
         const int s = q / SB_NB, m = q - s * SB_NB;
         const double* sp = slotp + s * 8;
@@ -612,6 +644,7 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
         bs[q] = kk * (sp[1] * v0 + sp[2] * d0 + sp[3] * v1 + sp[4] * d1);
         if (s == 0) bdv[m] = kk * (sp[5] * (v0 - v1) + sp[6] * d0 + sp[7] * d1);
     }
+#endif
     return jend;
 #endif
     // pull the 2 x 2 table rows of every slot into L1 first (one round trip to L2 for the whole attempt instead of one per sweep iteration)
@@ -1486,11 +1519,19 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                             s0 += a0 * a0; s1 += a1 * a1; sk += ak * ak;
                         }
                         const double sc = abstol + reltol * fmax(sqrt(s0), sqrt(s1));
-                        const double r = sqrt(sk) / sc; // with vanishing partials this is |k8| / (abstol + reltol·max(|u_n|, |u_{n+1}|)): the plain norm, bit for bit
+#if SB_NORMRCP
+                        const double r = sqrt(sk) * sb_rcp(sc); // with vanishing partials this is |k8| · rcp(abstol + reltol·max(|u_n|, |u_{n+1}|)): the plain norm, bit for bit
+#else
+                        const double r = sqrt(sk) / sc;
+#endif
                         es += r * r;
                     }
                 } else
+#if SB_NORMRCP
+                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
+#else
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
+#endif
                 double EEst = sqrt(warp_sum(es) / SB_N);
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
                 if (GROUP && closing) { if (!isfinite(EEst)) { rc = SB_RC_UNSTABLE; break; } EEst = fmin(EEst, 1.0); } // the closing step (O(δ) long) is taken as it is
