@@ -462,6 +462,15 @@ def test_sensitivities_lockstep_lanes(sb, oracle, prob5):
         x = np.log(pars[n]); h = 1e-3 * max(abs(x), 1.0)
         fd = (olog(**{n: np.exp(x + h)}) - olog(**{n: np.exp(x - h)})) / (2 * h)
         assert np.abs(J[:, j] - fd).max() < 1e-3, (n, J[:, j], fd)
+    # the quotient converges to the true derivative: lanes at tight tolerance against central differences of tight-tolerance oracle solves
+    Jt = sb.sensitivity_matter(prob5, names[:2], ks, bgsol=sb.solvebg(prob5, reltol=1e-10, abstol=1e-10), reltol=1e-9, abstol=1e-9, maxiters=1000000)
+    def ologt(**over):
+        p = oracle.planck18(lmax=5, **over)
+        return np.log(oracle.spectrum_matter(oracle.Background(p, reltol=1e-10, abstol=1e-10), ks, reltol=1e-10, abstol=1e-10)[0])
+    for j, n in enumerate(names[:2]):
+        x = np.log(pars[n]); h = 1e-3
+        fdt = (ologt(**{n: np.exp(x + h)}) - ologt(**{n: np.exp(x - h)})) / (2 * h)
+        assert np.abs(Jt[:, j] - fdt).max() < 5e-5, (n, Jt[:, j], fdt)
     J2 = sb.sensitivity_matter(prob5, names, ks, delta=2e-5)
     J1 = sb.sensitivity_matter(prob5, names, ks, delta=1e-5)
     assert np.abs(J2 - J1).max() < 1e-4
