@@ -144,6 +144,18 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
 int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, double tend_common,
                       void* stream, const sbm_src_t* src);
+/* The single-cosmology solve with ONE CTA of SB_R warps per mode ("one CTA per k-mode") instead of one warp per mode: for launches with no
+ * more modes than sbm_split_capacity() (BASELINE config 1: 100 modes; the default 61-node C_l path), where the warp-per-mode mapping leaves
+ * most of the GPU idle and the run time is the slowest mode's sequential attempts.  The row-parallel phases of an attempt (basis sweep,
+ * Jacobian scatter, f-evaluations, stage combinations, error norm, dense output) are spread over the warps, the first solve's three
+ * columns go to three warps, path recurrences and the top block stay on one warp.  Arguments and results as sbm_solvept_src (src may be
+ * NULL), bit-identical to it.  Returns the grid size, -5 if the model has no split kernel (SB_R outside 2..4), or a negative error.
+ * (replaces the same solvept call sites, src/solve.jl:543-569) */
+int sbm_split_capacity(void);
+int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                      const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                      double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
+                      const sbm_src_t* src);
 /* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
  * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
  * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */

@@ -492,6 +492,13 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Row windows.  Row i of the state belongs to lane i % 32 and round i / 32.  The warp-per-mode kernels loop over all SB_R rounds; in the
+// split kernel (SPL) each warp of the CTA owns one round, rb, held in the round-0 slots of its SbLane (see SbLane::load_split).
+#define SB_WMAX SB_WDR(0)                                // rounds are ordered by decreasing row length: round 0 is the widest
+#define SB_NRL (SPL ? 1 : SB_R)                          // rounds this warp loops over
+#define SB_WDL(r) (SPL ? SB_WMAX : SB_WDR(r))            // ELL width of its round r
+#define SB_EOL(r) (SPL ? 0 : SB_EOFF(r))                 // first ELL slot of its round r
+#define SB_ROW(r) ((rb + (r)) * 32 + lane)               // state index of its row in round r
 // Per-lane schedules produced by the code generator, kept in registers for the lifetime of the kernel
 // (every loop over them is fully unrolled so that the arrays never become addressable local memory).
 struct SbLane {
@@ -506,6 +513,25 @@ struct SbLane {
     unsigned tv, dk;           // top vertex owned by this lane (block member: lane = block*8+row, or single root) and its forest children
     unsigned dkz;              // dk with absent children replaced by a top-block vertex (its multiplier mm is always 0): unconditional gathers
     unsigned bp[SB_NBR];       // basis m -> beta index | (kpow+3)<<8
+    // Split mode (sb_integrate_split_kernel): the warp owns ONE round of rows, rb; its ELL entries and hub-vector entries are loaded into
+    // the slots of "round 0" (width SB_WMAX, zero coefficients beyond the round's own width), so that the row loops below run over a single
+    // round with compile-time register indices.  Everything that is per lane, not per row (paths, top vertices, hub functionals, basis
+    // descriptors), is the same in every warp.
+    __device__ __forceinline__ void load_split(int lane, int rb) {
+        load(lane);
+        double ec0[SB_WMAX]; unsigned ei0[SB_WMAX]; double p0 = 0, q0 = 0; unsigned pq0 = 0;
+#pragma unroll
+        for (int r = 0; r < SB_R; r++) {
+            if (r == rb) {
+#pragma unroll
+                for (int w = 0; w < SB_WMAX; w++) { ec0[w] = (w < SB_WDR(r)) ? ec[SB_EOFF(r) + (w < SB_WDR(r) ? w : 0)] : 0.0; ei0[w] = (w < SB_WDR(r)) ? ei[SB_EOFF(r) + (w < SB_WDR(r) ? w : 0)] : 0u; }
+                p0 = pqc[2 * r]; q0 = pqc[2 * r + 1]; pq0 = pqi[r];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < SB_WMAX; w++) { ec[w] = ec0[w]; ei[w] = ei0[w]; }
+        pqc[0] = p0; pqc[1] = q0; pqi[0] = pq0;
+    }
     __device__ __forceinline__ void load(int lane) {
 #pragma unroll
         for (int e = 0; e < SB_ELLN; e++) { ec[e] = sb_ell_coef[e * 32 + lane]; ei[e] = sb_ell_idx[e * 32 + lane]; }
@@ -568,15 +594,18 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 // Batched look-up of the basis at the stage times of one Rosenbrock attempt: slots 1..5 = t + c_s·dt (and, if with0, slot 0 = t
 // together with ḃ(t)).  Lanes 0..5 locate their slot's table node in parallel and publish (node, w, hs, τ) through shared memory;
 // then all lanes sweep the (slot, basis) items, so that every L2 access of the attempt is in flight at once.
+// SPL (split kernel): every warp of the CTA locates the slots (identical values), warp `wsel == 0` issues the bulk copies, all warps wait for
+// them, and warp w sweeps the slots s with s % SB_R == wsel.
+template <bool SPL = false>
 __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x8*/, int lane,
-                                              double* tabs = nullptr, unsigned* parity = nullptr) {
+                                              double* tabs = nullptr, unsigned* parity = nullptr, int wsel = 0) {
     int jend = jt;
 #if SB_TMA
     const int s0t = with0 ? 0 : 1;
     const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
     constexpr unsigned ROWB = 4 * SB_NBETA * 8; // two nodes x (β, dβ/dτ): contiguous in the table
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((6 - s0t) * ROWB) : "memory");
+    if (lane == 0 && (!SPL || wsel == 0)) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((6 - s0t) * ROWB) : "memory");
 #endif
     if (lane < 6) {
         const double tau = t + ((lane == 0) ? 0.0 : cc[lane]) * dt;
@@ -592,7 +621,7 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
         sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
         jend = j;
 #if SB_TMA
-        if (lane >= s0t) {
+        if (lane >= s0t && (!SPL || wsel == 0)) {
             const double* src = tb.tab + ((size_t)j * tb.msub + sidx) * 2 * SB_NBETA;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
         }
@@ -618,6 +647,7 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             if (s == 0 && !with0) continue;
+            if (SPL && (s % SB_R) != wsel) continue;
             const double* sp = slotp + s * 8;
             const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
             const double* n0 = tabs + s * 4 * SB_NBETA;
@@ -674,9 +704,9 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
 
 // out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU.
 // FUSE: out = J(b)·U + radd[r] + hd·dT  (the stage right-hand side is assembled in the same pass: one store per row)
-template <bool FUSE>
+template <bool FUSE, bool SPL = false>
 __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, const double* U, double* out, int lane, const double* radd = nullptr, double hd = 0.0, const double* dT = nullptr,
-                                          double* hubs = nullptr /* out: Φ̇ = φᵀU, Ψ = ψᵀU */) {
+                                          double* hubs = nullptr /* out: Φ̇ = φᵀU, Ψ = ψᵀU */, int rb = 0) {
     double sphi = 0, spsi = 0;
 #pragma unroll
     for (int t = 0; t < SB_TPH; t++) sphi += S.phc[t] * b[SB_HI16(S.phi[t])] * U[SB_LO16(S.phi[t])];
@@ -684,32 +714,33 @@ __device__ __forceinline__ void sb_eval_f(const SbLane& S, const double* b, cons
     for (int t = 0; t < SB_TPS; t++) spsi += S.psc[t] * b[SB_HI16(S.psi[t])] * U[SB_LO16(S.psi[t])];
     // the butterfly reduction of the two hub sums is interleaved, level by level, with the (independent) ELL row sums so that
     // the shuffle latencies are covered by useful work; same operand order as warp_sum
-    double acc[SB_R];
+    double acc[SB_NRL];
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) {
+    for (int r = 0; r < SB_NRL; r++) {
         const int o = 16 >> r;
         double t1 = 0, t2 = 0;
         if (o > 0) { t1 = __shfl_xor_sync(SB_FULL, sphi, o); t2 = __shfl_xor_sync(SB_FULL, spsi, o); }
         double a_ = 0;
 #pragma unroll
-        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; a_ += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
+        for (int w = 0; w < SB_WDL(r); w++) { const int e = SB_EOL(r) + w; a_ += S.ec[e] * b[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
         acc[r] = a_;
         if (o > 0) { sphi += t1; spsi += t2; }
     }
 #pragma unroll
-    for (int o = (SB_R < 5 ? 16 >> SB_R : 0); o > 0; o >>= 1) { sphi += __shfl_xor_sync(SB_FULL, sphi, o); spsi += __shfl_xor_sync(SB_FULL, spsi, o); }
+    for (int o = (SB_NRL < 5 ? 16 >> SB_NRL : 0); o > 0; o >>= 1) { sphi += __shfl_xor_sync(SB_FULL, sphi, o); spsi += __shfl_xor_sync(SB_FULL, spsi, o); }
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) {
-        const int i = r * 32 + lane;
+    for (int r = 0; r < SB_NRL; r++) {
+        const int i = SB_ROW(r);
         double a_ = acc[r] + S.pqc[2 * r] * b[SB_LO16(S.pqi[r])] * sphi + S.pqc[2 * r + 1] * b[SB_HI16(S.pqi[r])] * spsi;
         if (FUSE) { if (i < SB_N) a_ += radd[r] + hd * dT[i]; }
         if (i < SB_N) out[i] = a_;
     }
     if (hubs) { hubs[0] = sphi; hubs[1] = spsi; }
-    __syncwarp();
+    if (!SPL) __syncwarp(); // split kernel: the caller follows with a CTA barrier
 }
 // ∂f/∂τ = J'u with J' = J_local(ḃ) + ṗ φᵀ + p φ̇ᵀ + q̇ ψᵀ + q ψ̇ᵀ
-__device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, const double* bd, const double* U, double* out, int lane) {
+template <bool SPL = false>
+__device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, const double* bd, const double* U, double* out, int lane, int rb = 0) {
     double sphi = 0, spsi = 0, sphid = 0, spsid = 0;
 #pragma unroll
     for (int t = 0; t < SB_TPH; t++) { double cu = S.phc[t] * U[SB_LO16(S.phi[t])]; sphi += cu * b[SB_HI16(S.phi[t])]; sphid += cu * bd[SB_HI16(S.phi[t])]; }
@@ -717,33 +748,34 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
     for (int t = 0; t < SB_TPS; t++) { double cu = S.psc[t] * U[SB_LO16(S.psi[t])]; spsi += cu * b[SB_HI16(S.psi[t])]; spsid += cu * bd[SB_HI16(S.psi[t])]; }
     sphi = warp_sum(sphi); spsi = warp_sum(spsi); sphid = warp_sum(sphid); spsid = warp_sum(spsid);
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) {
+    for (int r = 0; r < SB_NRL; r++) {
         const int pb = SB_LO16(S.pqi[r]), qb = SB_HI16(S.pqi[r]);
         double acc = S.pqc[2 * r] * (bd[pb] * sphi + b[pb] * sphid) + S.pqc[2 * r + 1] * (bd[qb] * spsi + b[qb] * spsid);
 #pragma unroll
-        for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; acc += S.ec[e] * bd[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
-        const int i = r * 32 + lane;
+        for (int w = 0; w < SB_WDL(r); w++) { const int e = SB_EOL(r) + w; acc += S.ec[e] * bd[SB_E_B(S.ei[e])] * U[SB_E_COL(S.ei[e])]; }
+        const int i = SB_ROW(r);
         if (i < SB_N) out[i] = acc;
     }
-    __syncwarp();
+    if (!SPL) __syncwarp();
 }
 
 
 // Factor B = x·I − J_local(b): phase-0 elimination paths (zero fill, no pivoting: the chains have sign-skew off-diagonals
 // and non-negative damping, so pivots only grow), then the top = root paths + explicit pivoted inverse of the top blocks.
 // Leaves 1/pivot in di, multipliers in mm, (entry towards the parent)/pivot in up, block inverses in blk.
-__device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane) {
+template <bool SPL = false>
+__device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane, int rb = 0, bool elim = true) {
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) mm[i] = 0; }
-    for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0;
-    __syncwarp();
+    for (int r = 0; r < SB_NRL; r++) { const int i = SB_ROW(r); if (i < SB_N) mm[i] = 0; }
+    if (!SPL || rb == 0) for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0;
+    if (SPL) __syncthreads(); else __syncwarp(); // the scatter below writes multipliers of rows other lanes (split: other warps) have just cleared
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) {
-        const int i = r * 32 + lane;
+    for (int r = 0; r < SB_NRL; r++) {
+        const int i = SB_ROW(r);
         double dacc = x, uacc = 0;
 #pragma unroll
-        for (int w = 0; w < SB_WDR(r); w++) {
-            const int e = SB_EOFF(r) + w;
+        for (int w = 0; w < SB_WDL(r); w++) {
+            const int e = SB_EOL(r) + w;
             const unsigned ix = S.ei[e];
             const double v = -S.ec[e] * b[SB_E_B(ix)];
             const int kind = SB_E_KIND(ix), tgt = SB_E_TGT(ix);
@@ -759,7 +791,8 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         }
         if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
-    __syncwarp();
+    if (SPL) __syncthreads(); else __syncwarp();
+    if (SPL && !elim) return; // split kernel: the eliminations below are one warp's work (the paths and the top block live on lanes, not rows)
     // phase 0: every vertex but the last of a path is finished here (multiplier and parent coupling scaled by 1/pivot); the
     // last one keeps its raw multiplier for the owner of its parent, which forms the Schur term mm_raw * (up/pivot)
 #pragma unroll
@@ -1608,6 +1641,295 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
     }
 }
 
+// ================================================================================================ split kernel
+// One CTA of SB_R warps per mode ("one CTA per k-mode"): for launches with fewer modes than SMs' worth of warps (BASELINE config 1: 100 modes;
+// the reference's default C_l path: 61) the warp-per-mode kernel leaves three of four sub-partitions idle and its attempt is a single
+// warp's dependent instruction stream.  Here warp w owns round rb of the rows (32 rows each): the row-parallel phases -- basis sweep,
+// Jacobian scatter, f-evaluations, stage combinations, error norm, dense output -- shrink to one round per warp, the three columns of the
+// first solve go to three warps, and the phases that live on lanes rather than rows (path recurrences, 5×5 block, single-column solves) stay
+// on warp 0, with CTA barriers at the phase boundaries.  Every warp carries the scalar control state and takes identical decisions from
+// shared data; sums over rows are formed per lane over the rounds in the single-warp order before the butterfly, so the results are
+// bit-identical to sb_integrate_kernel<false> (tests/test_gpu_parity.py::test_split_kernel_is_bit_identical).
+#if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1
+#define SB_HAVE_SPLIT 1
+#define SB_XS_SUM 8 // exchange area: [0] work index, [8 + r·32 + lane] per-lane partial sums of round r
+#define SB_XS_DOUBLES (SB_XS_SUM + 32 * SB_R)
+// Σ over all rows of a per-row quantity whose per-lane partial of this warp's round is v: per lane over the rounds in order, then the butterfly
+__device__ __forceinline__ double sb_split_sum(double v, double* xs, int rb, int lane) {
+    xs[SB_XS_SUM + rb * 32 + lane] = v;
+    __syncthreads();
+    double t = 0;
+#pragma unroll
+    for (int r = 0; r < SB_R; r++) t += xs[SB_XS_SUM + r * 32 + lane];
+    __syncthreads();
+    return warp_sum(t);
+}
+__global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(const __grid_constant__ SbSolveArgs A) {
+    constexpr bool SPL = true;
+    extern __shared__ __align__(16) double sm_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    constexpr int NT = SB_WARP * SB_R;
+    const int rb = SB_R - 1 - warp; // warp 0 also runs the serial phases: it takes the last (shortest, narrowest) round
+    const bool w0 = warp == 0;
+    double* const sm = sm_all;
+    double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *dT = sm + SB_SM_DT, *f0 = sm + SB_SM_F0, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP,
+           *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ, *bs = sm + SB_SM_BS, *bdv = sm + SB_SM_BD, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
+    double* const sbuf = sm + SB_SM_SBUF;
+    double* const tabs = sm + SB_SM_TAB;
+    double* const xs = sm + SB_SM_DOUBLES;
+    unsigned tpar = 0;
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_u32(sm + SB_SM_MBAR)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const double reltol = A.reltol, abstol = A.abstol;
+    const bool SRC = A.S != nullptr;
+    SbLane S;
+    S.load_split(lane, rb);
+    const SbCosmo& CC = A.c0;
+    const int i0 = rb * 32 + lane;         // this thread's row
+    const bool has = i0 < SB_N;
+    const int ic = has ? i0 : SB_N - 1;    // clamped: loads of absent rows read the last row (results discarded)
+
+    while (true) {
+        __syncthreads(); // every warp is done with the previous mode
+        if (tid == 0) reinterpret_cast<int*>(xs)[0] = atomicAdd(A.queue, 1);
+        __syncthreads();
+        const int qi = reinterpret_cast<const int*>(xs)[0];
+        if (qi >= A.nk) break;
+        const int mode = A.order ? A.order[qi] : qi;
+        const double k = A.ks[mode];
+        double t = A.tini[mode];
+        const double tend = CC.tend;
+        long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
+        int rc = SB_RC_SUCCESS, isave = 0, wstart = 0;
+        double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
+        double* Sout = SRC ? A.S + (size_t)mode * A.nS * A.nsave : nullptr;
+        if (!(k > 0) || !isfinite(k)) {
+            for (int i = tid; i < SB_N; i += NT) A.uend[(size_t)mode * SB_N + i] = NAN;
+            if (usave) for (int i = tid; i < A.nsave * SB_N; i += NT) usave[i] = NAN;
+            if (SRC) for (int i = tid; i < A.nsave * A.nS; i += NT) Sout[i] = NAN;
+            if (tid == 0) { A.retcode[mode] = SB_RC_UNSTABLE; for (int j = 0; j < 4; j++) A.stats[4 * mode + j] = 0; }
+            continue;
+        }
+        if (tid < 7) kp[tid] = pow(k, (double)(tid - 3));
+        SbController ctl; ctl.init();
+        double dt = 0;
+        int jt = 0;
+        if (tid == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
+        __syncthreads();
+        if (has) u[i0] = U[sb_nat[i0]];
+        __syncthreads();
+        // one save point from the state in `st` (all warps; st complete and visible on entry)
+        auto emit = [&](const double* st, double ts, bool valid) {
+            if (SRC) {
+                double* so = sbuf + (isave & (SB_SWIN - 1));
+                if (valid) {
+                    const double* sb = CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE;
+                    for (int m = tid; m < SB_NB; m += NT) {
+                        const unsigned pk = sb_basis_pack[m];
+                        const double kk = kp[SB_HI16(pk)];
+                        bs[m] = kk * __ldg(sb + 8 + SB_LO16(pk));
+                        bs[SB_NB + m] = kk * __ldg(sb + 8 + SB_NBETA + SB_LO16(pk));
+                    }
+                    __syncthreads();
+                    double hub[2];
+                    sb_eval_f<false, SPL>(S, bs, st, up, lane, nullptr, 0.0, nullptr, hub, rb); // u̇ into `up`
+                    __syncthreads();
+                    if (rb == 0) { // the rows of Π = F2 + G0 + G2 live in round 0; its warp closes the evaluation (same sums, same order as sb_source_point)
+                        const double* b = bs; const double* bd = bs + SB_NB;
+                        double a = 0, pdd = 0;
+#pragma unroll
+                        for (int tt = 0; tt < SB_TPS; tt++) a += S.psc[tt] * (bd[SB_HI16(S.psi[tt])] * st[SB_LO16(S.psi[tt])] + b[SB_HI16(S.psi[tt])] * up[SB_LO16(S.psi[tt])]);
+                        if (i0 == SB_J_F2 || i0 == SB_J_G0 || i0 == SB_J_G2) {
+#pragma unroll
+                            for (int w = 0; w < SB_WMAX; w++) pdd += S.ec[w] * (bd[SB_E_B(S.ei[w])] * st[SB_E_COL(S.ei[w])] + b[SB_E_B(S.ei[w])] * up[SB_E_COL(S.ei[w])]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(SB_FULL, a, o); pdd += __shfl_xor_sync(SB_FULL, pdd, o); }
+                        if (lane == 0) {
+                            const double Phd = hub[0], Psi = hub[1], Psid = a, Pigdd = pdd;
+                            const double Pig = st[SB_J_F2] + st[SB_J_G0] + st[SB_J_G2], Pigd = up[SB_J_F2] + up[SB_J_G0] + up[SB_J_G2];
+                            const double kd = __ldg(sb), kdd = __ldg(sb + 1), kddd = __ldg(sb + 2), ek = __ldg(sb + 3), chi = __ldg(sb + 4);
+                            const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek;
+                            const double thb = st[SB_J_TB], thbd = up[SB_J_TB];
+                            double ST = v * (st[SB_J_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
+                            double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
+                            if (A.scale_k) { ST *= k; SE *= k * k; }
+                            so[0] = ST;
+                            so[SB_SWIN] = SE;
+                            if (A.nS > 2) so[2 * SB_SWIN] = (ts >= CC.taurec) ? -(Psi + st[SB_J_PHI]) * (ts - CC.taurec) / (chi + ts - CC.taurec) / chi : 0.0 * Psi;
+                        }
+                    }
+                } else if (tid < A.nS) so[tid * SB_SWIN] = NAN;
+                __syncthreads();
+                if (w0) sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
+                __syncthreads();
+            }
+            isave++;
+        };
+        while (isave < A.nsave && CC.saveat[isave] <= t) { // save points at (or before) the start
+            const bool at = CC.saveat[isave] == t;
+            if (usave && has) usave[(size_t)isave * SB_N + sb_nat[i0]] = at ? u[i0] : NAN;
+            emit(u, t, at);
+        }
+        if (tend > t) {
+            jt = sb_interval(CC.tb, t);
+            jt = sb_basis_at(S, CC.tb, t, jt, kp, bs, bdv, lane); // (every warp: identical values into the same words)
+            __syncthreads();
+            sb_eval_f<false, SPL>(S, bs, u, f0, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
+            sb_eval_dT<SPL>(S, bs, bdv, u, dT, lane, rb);
+            __syncthreads();
+            { // automatic initial step (Hairer), order 5 -- sums over rows in the single-warp order
+                double d0 = 0, d1 = 0;
+                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d0 += (u[i0] / sk) * (u[i0] / sk); d1 += (f0[i0] / sk) * (f0[i0] / sk); }
+                d0 = sqrt(sb_split_sum(d0, xs, rb, lane) / SB_N); d1 = sqrt(sb_split_sum(d1, xs, rb, lane) / SB_N);
+                const double dtmax = tend - t;
+                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                dt0 = fmin(dt0, dtmax);
+                if (has) U[i0] = u[i0] + dt0 * f0[i0];
+                sb_basis_at(S, CC.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
+                __syncthreads();
+                sb_eval_f<false, SPL>(S, bs + SB_NB, U, K, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
+                __syncthreads();
+                double d2 = 0;
+                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; const double r = (K[i0] - f0[i0]) / sk; d2 += r * r; }
+                d2 = sqrt(sb_split_sum(d2, xs, rb, lane) / SB_N) / dt0;
+                const double dm = fmax(d1, d2);
+                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 5.0);
+                dt = fmin(fmin(100 * dt0, dt1), dtmax);
+            }
+            int jend = jt;
+            bool moved = false;
+            for (int it = 0;; it++) {
+                if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
+                bool last = false;
+                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
+                __syncthreads(); // the previous attempt's readers of bs / the staging area are done
+                jend = sb_basis_batch<SPL>(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar, warp);
+                __syncthreads();
+                if (moved) {
+                    sb_eval_f<false, SPL>(S, bs, u, f0, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
+                    sb_eval_dT<SPL>(S, bs, bdv, u, dT, lane, rb);
+                    moved = false; // (f0, dT complete after the barrier inside sb_factor)
+                }
+                // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0, meanwhile the others set up Z and the stage-1 right-hand side
+                sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0);
+                if (has) {
+                    Zp[i0] = S.pqc[0] * bs[SB_LO16(S.pqi[0])]; Zq[i0] = S.pqc[1] * bs[SB_HI16(S.pqi[0])];
+                    K[i0] = f0[i0] + dt * cd[0] * dT[i0];
+                }
+                __syncthreads();
+                // the three columns of the first solve: one per warp (with fewer than three warps, warp 0 takes the rest)
+                {
+                    double* const cols[3] = {Zp, Zq, K};
+#pragma unroll
+                    for (int c = 0; c < 3; c++) if ((c < SB_R ? c : 0) == warp) { double* const z1[1] = {cols[c]}; sb_bsolve<1>(S, z1, di, up, mm, blk, lane); }
+                }
+                nsolve += 3;
+                __syncthreads();
+                double m11, m12, m21, m22;
+                sb_hub_dots(S, bs, Zp, m11, m21, lane);
+                sb_hub_dots(S, bs, Zq, m12, m22, lane);
+                m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
+                const double idet = sb_rcp(m11 * m22 - m12 * m21);
+                const double idt = sb_rcp(dt);
+                double c1p = 0, c2p = 0;
+                for (int s = 1; s < 8; s++) {
+                    double* ks = K + s * SB_N;
+                    const double hd_ = dt * cd[s];
+                    double* kprev = ks - SB_N;
+                    double h1, h2;
+                    sb_hub_dots(S, bs, kprev, h1, h2, lane); // (every warp, from the complete k_{s-1}: same values)
+                    c1p = (m22 * h1 - m12 * h2) * idet; c2p = (-m21 * h1 + m11 * h2) * idet;
+                    const bool inc = s >= 6;
+                    const int nold = s - 1;
+                    double ua = inc ? U[ic] : u[ic], Racc = 0;
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        if (nold > j) {
+                            const double a_ = cA[s][j], c_ = cC[s][j] * idt;
+                            const double kj = K[j * SB_N + ic];
+                            if (j < 4 && !inc) ua = fma(a_, kj, ua);
+                            Racc = fma(c_, kj, Racc);
+                        }
+                    }
+                    {
+                        const double al = cA[s][s - 1], cl = cC[s][s - 1] * idt;
+                        const double kp_ = kprev[ic] + Zp[ic] * c1p + Zq[ic] * c2p;
+                        ua = fma(al, kp_, ua);
+                        Racc = fma(cl, kp_, Racc);
+                        __syncthreads(); // every warp has taken its hub dot products from the uncorrected k_{s-1}
+                        if (has) { kprev[i0] = kp_; U[i0] = ua; }
+                    }
+                    __syncthreads();
+                    sb_eval_f<true, SPL>(S, bs + cslot[s] * SB_NB, U, ks, lane, &Racc, hd_, dT, nullptr, rb); nf++;
+                    __syncthreads();
+                    if (w0) { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); }
+                    nsolve++;
+                    __syncthreads();
+                }
+                {
+                    double s1, s2;
+                    sb_hub_dots(S, bs, K + 7 * SB_N, s1, s2, lane);
+                    c1p = (m22 * s1 - m12 * s2) * idet; c2p = (-m21 * s1 + m11 * s2) * idet;
+                }
+                __syncthreads();
+                if (has) K[7 * SB_N + i0] += Zp[i0] * c1p + Zq[i0] * c2p;
+                // error estimate (own row; the sum over rows in the single-warp order)
+                double es = 0; bool bad = false;
+                if (has) {
+                    const double k8 = K[7 * SB_N + i0], un = U[i0] + k8;
+#if SB_NORMRCP
+                    const double r = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
+#else
+                    const double r = k8 / (abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
+#endif
+                    es += r * r;
+                }
+                const double EEst = sqrt(sb_split_sum(es, xs, rb, lane) / SB_N);
+                if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
+                const double q = ctl.q_of(EEst);
+                if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                naccept++;
+                const double dtnew = ctl.accept(dt, q, EEst);
+                const double tn = last ? tend : t + dt;
+                const double un_ = has ? U[i0] + K[7 * SB_N + i0] : 0.0;
+                if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order)
+                    double a1 = 0, a2 = 0, a3 = 0;
+                    for (int j = 0; j < 8; j++) { const double kj = K[j * SB_N + ic]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
+                    while (isave < A.nsave && CC.saveat[isave] <= tn) {
+                        const double ts = CC.saveat[isave];
+                        const double th = (ts - t) / dt, t1 = 1 - th;
+                        const double v = (ts == tn) ? un_ : t1 * u[ic] + th * (un_ + t1 * (a1 + th * (a2 + th * a3)));
+                        if (has) { if (usave) usave[(size_t)isave * SB_N + sb_nat[i0]] = v; if (SRC) di[i0] = v; }
+                        __syncthreads();
+                        emit(di, ts, true);
+                    }
+                }
+                if (has) { if (isnan(un_)) bad = true; }
+                bad = __syncthreads_or(bad);
+                if (has) u[i0] = un_;
+                t = tn;
+                if (bad) { rc = SB_RC_UNSTABLE; break; }
+                if (last) break;
+                dt = dtnew;
+                jt = jend;
+                moved = true;
+            }
+        }
+        __syncthreads();
+        if (has) A.uend[(size_t)mode * SB_N + sb_nat[i0]] = u[i0];
+        for (; isave < A.nsave;) { // save times the mode never reached (failed solve)
+            if (usave && has) usave[(size_t)isave * SB_N + i0] = NAN;
+            emit(u, t, false);
+        }
+        if (tid == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
+    }
+}
+#else
+#define SB_HAVE_SPLIT 0
+#endif
+
 // Δm(τ,k) for P(k): one thread per mode
 __global__ void sb_deltam_kernel(const double* __restrict__ P, SbSpline spl, double tau, int nk, const double* __restrict__ ks, const double* __restrict__ u, double* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1818,6 +2140,48 @@ int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks
     sb_integrate_kernel<true, true><<<grid, SB_WARP * G, smem, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
+}
+// The same solve as sbm_solvept_src with ONE CTA of SB_R warps per mode (sb_integrate_split_kernel): for launches that leave most of the GPU
+// idle under the warp-per-mode mapping (fewer modes than sbm_split_capacity()), where the time is the slowest mode's sequential attempts.
+// Bit-identical results.  Returns the grid size, -5 if this model has no split kernel, or a negative error.
+int sbm_split_capacity(void) { // modes that run concurrently under the split mapping (0: not available for this model)
+#if SB_HAVE_SPLIT
+    int dev, nsm, occ = 0;
+    const size_t smem = (size_t)(SB_SM_DOUBLES + SB_XS_DOUBLES) * sizeof(double);
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(sb_integrate_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_split_kernel, SB_WARP * SB_R, smem) != cudaSuccess) return 0;
+    return nsm * occ;
+#else
+    return 0;
+#endif
+}
+int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                      const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                      int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream, const sbm_src_t* src) {
+#if SB_HAVE_SPLIT
+    if (nk <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SbSolveArgs A;
+    memset(&A, 0, sizeof(A));
+    const bool fused = src && src->dS && nsave > 0;
+    if (fused && (src->nS < 2 || src->nS > 3 || !src->dsrcbg)) return -1;
+    A.c0 = SbCosmo{dP, SbSpline{nb, dt, dy, ddy}, SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab}, tend, dsaveat, fused ? src->dsrcbg : nullptr, fused ? src->taurec : 0.0};
+    A.S = fused ? src->dS : nullptr; A.nS = fused ? src->nS : 0; A.scale_k = fused ? src->scale_k : 0;
+    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = (dusave || fused) ? nsave : 0;
+    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
+    SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
+    const int cap = sbm_split_capacity();
+    if (cap <= 0) return -5;
+    const size_t smem = (size_t)(SB_SM_DOUBLES + SB_XS_DOUBLES) * sizeof(double);
+    const int grid = std::min(nk, cap);
+    sb_integrate_split_kernel<<<grid, SB_WARP * SB_R, smem, st>>>(A);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return grid;
+#else
+    return -5;
+#endif
 }
 // Per-save-time background table of the source evaluation: dsrcbg[nt][sbm_srcbg_stride()] (κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, the β_m and their
 // flow derivatives at dtaus[nt]); input of sbm_solvept_src / sbm_cosmo_t.srcbg and of sbm_sources.

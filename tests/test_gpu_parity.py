@@ -709,3 +709,31 @@ def test_matter_spectrum_converged_to_a_permille(sb, prob5):
     P0 = sb.spectrum_matter(prob5, ks, kτini=0.0, τinimax=0.0, bgsol=sb.solvebg(prob5, reltol=1e-10, abstol=1e-10), reltol=1e-10, abstol=1e-10, maxiters=1000000)
     P = sb.spectrum_matter(prob5, ks)
     assert np.isfinite(P0).all() and np.abs(P / P0 - 1).max() < 1e-3
+
+
+def test_split_kernel_is_bit_identical(sb, prob5, bg5):
+    """`sbm_solvept_split` (one CTA of SB_R warps per mode, chosen automatically for launches that fit the GPU once) against the warp-per-mode
+    kernel: final states, dense output, fused sources (2 and 3), step counters and return codes bit for bit -- including a failing k = 0
+    mode, a mode that hits maxiters, save times before the start, and both models the tests use (N = 47: 2 warps per mode; N = 82: 3)."""
+    import warnings
+    for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10)):
+        prob = prob5 if M.lmax == 5 else sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+        bg = bg5 if M.lmax == 5 else sb.solvebg(prob)
+        assert sb.split_capacity(prob) >= 148
+        ks = np.concatenate([[0.0], np.geomspace(0.3, 900.0, 40)])
+        taus = np.geomspace(bg.t[0], bg.tau0, 45)
+        taus[0], taus[-1] = bg.t[0], bg.t[-1]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for kw in (dict(), dict(saveat=taus), dict(saveat=taus, sources=dict(nS=3, scale_k=True), keep_states=False), dict(saveat=taus[5:], sources=dict(nS=2, scale_k=False)),
+                       dict(maxiters=150), dict(ptivini=lambda k: min(1e-2 / k, 1e-4) if k > 0 else 1e-4, saveat=taus)):
+                a = sb.solvept(prob, bg, ks, split=False, **kw)
+                b = sb.solvept(prob, bg, ks, split=True, **kw)
+                assert np.array_equal(a.retcode, b.retcode) and np.array_equal(a.stats, b.stats), kw
+                assert np.array_equal(a.uend, b.uend, equal_nan=True), kw
+                if a.d_usave is not None:
+                    assert np.array_equal(a.usave, b.usave, equal_nan=True), kw
+                if a.d_S is not None:
+                    assert np.array_equal(a.d_S.cpu().numpy(), b.d_S.cpu().numpy(), equal_nan=True), kw
+        auto = sb.solvept(prob, bg, ks[1:])  # the default picks the split mapping for a launch this small
+        assert np.array_equal(auto.uend, sb.solvept(prob, bg, ks[1:], split=False).uend)
