@@ -1,6 +1,6 @@
 # GPU run r2o: split kernel (one CTA of SB_R warps per mode for small launches): bit-identity test, all GPU tests, latency numbers
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "split_kernel" > gpurun_out/gputest_split_r2o.log 2>&1; tail -15 gpurun_out/gputest_split_r2o.log
+timeout 600 python scripts/split_diag.py > gpurun_out/split_diag_r2o.txt 2>&1; cat gpurun_out/split_diag_r2o.txt
 (time timeout 1200 python -m pytest tests -m gpu -q) > gpurun_out/gputest_r2o.log 2>&1; tail -12 gpurun_out/gputest_r2o.log
 python - > gpurun_out/split_latency_r2o.txt 2>&1 <<'PY'
 import sys, time

@@ -1163,6 +1163,28 @@ __device__ __forceinline__ void sb_source_flush(const double* sbuf, double* Sout
     }
 }
 
+// Pieces shared verbatim by the warp-per-mode and the split kernel.  Sums of two products are written with explicit fma so that the two
+// kernels contract them the same way (bit-identical results are tested: tests/test_gpu_parity.py::test_split_kernel_is_bit_identical).
+__device__ __forceinline__ double sb_dd_term(double c, double bd, double u, double b, double ud, double acc) { return fma(c, fma(bd, u, b * ud), acc); } // acc + c·(ḃu + bu̇)
+__device__ __forceinline__ void sb_source_close(const double* __restrict__ sb, double k, double tau, double taurec, int scale_k, int nS, double Phd, double Psi, double Psid, double Pig, double Pigd,
+                                                double Pigdd, double thb, double thbd, double F0, double Phi, double* out, int ostride) {
+    const double kd = __ldg(sb), kdd = __ldg(sb + 1), kddd = __ldg(sb + 2), ek = __ldg(sb + 3), chi = __ldg(sb + 4);
+    const double v = -kd * ek, vd = fma(kd, kd, -kdd) * ek, vdd = (fma(3 * kd, kdd, -kddd) - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
+    double ST = v * (F0 / 4 + Psi + Pig / 16);
+    ST = fma(ek, Psid + Phd, ST);
+    ST += fma(vd, thb, v * thbd) / (k * k);
+    ST = fma(3.0 / (16 * k * k), fma(vdd, Pig, fma(2 * vd, Pigd, v * Pigdd)), ST);
+    double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
+    if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
+    out[0] = ST;
+    out[ostride] = SE;
+    if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + Phi) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0 * Psi; // (0·Ψ: a failed mode stays NaN); τ0 = χ + τ
+}
+// Rodas5P dense output (4th order) at θ = (ts − t)/dt from u_n, u_{n+1} and the three combinations a_m = Σ_j H_mj k_j
+__device__ __forceinline__ double sb_dense(double th, double t1, double u, double un, double a1, double a2, double a3) {
+    return fma(th, fma(t1, fma(th, fma(th, a3, a2), a1), un), t1 * u);
+}
+
 // Warp-cooperative evaluation at one save time inside the integrator, on the integrator's own register-resident schedule (the
 // generated CSR tables of the stand-alone kernel live in global memory: walking them from here costs an L2 round trip per entry,
 // which made a source point as expensive as half a Rosenbrock attempt).  u: the saved state in the integrator's order, ud/b/bd:
@@ -1187,30 +1209,20 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
     // Ψ̇ = ψ̇ᵀu + ψᵀu̇ and Π̈ = Σ_{F2,G0,G2} (J̇_i u + J_i u̇) (rows without hub terms), reduced together
     double a = 0, pdd = 0;
 #pragma unroll
-    for (int t = 0; t < SB_TPS; t++) a += S.psc[t] * (bd[SB_HI16(S.psi[t])] * u[SB_LO16(S.psi[t])] + b[SB_HI16(S.psi[t])] * ud[SB_LO16(S.psi[t])]);
+    for (int t = 0; t < SB_TPS; t++) a = sb_dd_term(S.psc[t], bd[SB_HI16(S.psi[t])], u[SB_LO16(S.psi[t])], b[SB_HI16(S.psi[t])], ud[SB_LO16(S.psi[t])], a);
 #pragma unroll
     for (int r = 0; r < SB_R; r++) {
         const int i = r * 32 + lane;
         if (i == SB_J_F2 || i == SB_J_G0 || i == SB_J_G2) {
 #pragma unroll
-            for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; pdd += S.ec[e] * (bd[SB_E_B(S.ei[e])] * u[SB_E_COL(S.ei[e])] + b[SB_E_B(S.ei[e])] * ud[SB_E_COL(S.ei[e])]); }
+            for (int w = 0; w < SB_WDR(r); w++) { const int e = SB_EOFF(r) + w; pdd = sb_dd_term(S.ec[e], bd[SB_E_B(S.ei[e])], u[SB_E_COL(S.ei[e])], b[SB_E_B(S.ei[e])], ud[SB_E_COL(S.ei[e])], pdd); }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(SB_FULL, a, o); pdd += __shfl_xor_sync(SB_FULL, pdd, o); }
-    if (lane == 0) {
-        const double Psid = a, Pigdd = pdd;
-        const double Pig = u[SB_J_F2] + u[SB_J_G0] + u[SB_J_G2], Pigd = ud[SB_J_F2] + ud[SB_J_G0] + ud[SB_J_G2];
-        const double kd = __ldg(sb), kdd = __ldg(sb + 1), kddd = __ldg(sb + 2), ek = __ldg(sb + 3), chi = __ldg(sb + 4);
-        const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek; // v = d/dτ e^{−κ}
-        const double thb = u[SB_J_TB], thbd = ud[SB_J_TB];
-        double ST = v * (u[SB_J_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
-        double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
-        if (scale_k) { ST *= k; SE *= k * k; } // the LOS integrator is fed k·ST and k²·SE (src/observables/angular.jl:293)
-        out[0] = ST;
-        out[ostride] = SE;
-        if (nS > 2) out[2 * ostride] = (tau >= taurec) ? -(Psi + u[SB_J_PHI]) * (tau - taurec) / (chi + tau - taurec) / chi : 0.0 * Psi; // τ0 = χ + τ
-    }
+    if (lane == 0)
+        sb_source_close(sb, k, tau, taurec, scale_k, nS, Phd, Psi, a, u[SB_J_F2] + u[SB_J_G0] + u[SB_J_G2], ud[SB_J_F2] + ud[SB_J_G0] + ud[SB_J_G2], pdd, u[SB_J_TB], ud[SB_J_TB], u[SB_J_F0],
+                        u[SB_J_PHI], out, ostride);
     __syncwarp();
 }
 
@@ -1370,7 +1382,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             sb_eval_dT(S, bs, bdv, u, dT, lane);
             { // automatic initial step (Hairer), order 5
                 double d0 = 0, d1 = 0;
-                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; d0 += (u[i] / sk) * (u[i] / sk); d1 += (f0[i] / sk) * (f0[i] / sk); }
+                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; const double a0 = u[i] / sk, a1 = f0[i] / sk; d0 = fma(a0, a0, d0); d1 = fma(a1, a1, d1); } // (explicit fma chains: the split kernel forms the same sums)
                 d0 = sqrt(warp_sum(d0) / SB_N); d1 = sqrt(warp_sum(d1) / SB_N);
                 double dtmax = tend - t;
                 double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
@@ -1380,7 +1392,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 __syncwarp();
                 sb_eval_f<false>(S, bs + SB_NB, U, K, lane); nf++;
                 double d2 = 0;
-                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; double r = (K[i] - f0[i]) / sk; d2 += r * r; }
+                for (int i = lane; i < SB_N; i += SB_WARP) { double sk = abstol + fabs(u[i]) * reltol; double r = (K[i] - f0[i]) / sk; d2 = fma(r, r, d2); }
                 d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
                 double dm = fmax(d1, d2);
                 double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 5.0);
@@ -1557,13 +1569,13 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #else
                         const double r = sqrt(sk) / sc;
 #endif
-                        es += r * r;
+                        es = fma(r, r, es);
                     }
                 } else
 #if SB_NORMRCP
-                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
+                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i]), fabs(un))); es = fma(r, r, es); }
 #else
-                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es += r * r; }
+                for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es = fma(r, r, es); }
 #endif
                 double EEst = sqrt(warp_sum(es) / SB_N);
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
@@ -1580,7 +1592,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 if (isave < A.nsave && svd[isave] <= tn0) { // dense output (4th order), vectors stored over dT, f0, Zp
                     for (int i = lane; i < SB_N; i += SB_WARP) {
                         double a1 = 0, a2 = 0, a3 = 0;
-                        for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
+                        for (int j = 0; j < 8; j++) { double kj = K[j * SB_N + i]; a1 = fma(cH[0][j], kj, a1); a2 = fma(cH[1][j], kj, a2); a3 = fma(cH[2][j], kj, a3); }
                         dT[i] = a1; f0[i] = a2; Zp[i] = a3;
                     }
                     while (isave < A.nsave && svd[isave] <= tn0) {
@@ -1589,7 +1601,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                         const bool atend = svd[isave] == tn0; // a save time that IS the step end takes the step result
                         for (int i = lane; i < SB_N; i += SB_WARP) {
                             const double un = U[i] + K[7 * SB_N + i];
-                            const double v = atend ? un : t1 * u[i] + th * (un + t1 * (dT[i] + th * (f0[i] + th * Zp[i])));
+                            const double v = atend ? un : sb_dense(th, t1, u[i], un, dT[i], f0[i], Zp[i]);
                             if (usave) usave[(size_t)isave * SB_N + sb_nat[i]] = v;
                             if (SRC) di[i] = v;
                         }
@@ -1652,15 +1664,16 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 // bit-identical to sb_integrate_kernel<false> (tests/test_gpu_parity.py::test_split_kernel_is_bit_identical).
 #if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1
 #define SB_HAVE_SPLIT 1
+static_assert(SB_J_F2 < 32 && SB_J_G0 < 32 && SB_J_G2 < 32, "the split kernel closes the source evaluation on the warp of round 0");
 #define SB_XS_SUM 8 // exchange area: [0] work index, [8 + r·32 + lane] per-lane partial sums of round r
 #define SB_XS_DOUBLES (SB_XS_SUM + 32 * SB_R)
-// Σ over all rows of a per-row quantity whose per-lane partial of this warp's round is v: per lane over the rounds in order, then the butterfly
-__device__ __forceinline__ double sb_split_sum(double v, double* xs, int rb, int lane) {
+// Σ_rows v_row² where v is this thread's row value (0 for an absent row): per lane the fma chain over the rounds in the single-warp order, then the butterfly
+__device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, int lane) {
     xs[SB_XS_SUM + rb * 32 + lane] = v;
     __syncthreads();
     double t = 0;
 #pragma unroll
-    for (int r = 0; r < SB_R; r++) t += xs[SB_XS_SUM + r * 32 + lane];
+    for (int r = 0; r < SB_R; r++) { const double x = xs[SB_XS_SUM + r * 32 + lane]; t = fma(x, x, t); }
     __syncthreads();
     return warp_sum(t);
 }
@@ -1739,26 +1752,16 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                         const double* b = bs; const double* bd = bs + SB_NB;
                         double a = 0, pdd = 0;
 #pragma unroll
-                        for (int tt = 0; tt < SB_TPS; tt++) a += S.psc[tt] * (bd[SB_HI16(S.psi[tt])] * st[SB_LO16(S.psi[tt])] + b[SB_HI16(S.psi[tt])] * up[SB_LO16(S.psi[tt])]);
+                        for (int tt = 0; tt < SB_TPS; tt++) a = sb_dd_term(S.psc[tt], bd[SB_HI16(S.psi[tt])], st[SB_LO16(S.psi[tt])], b[SB_HI16(S.psi[tt])], up[SB_LO16(S.psi[tt])], a);
                         if (i0 == SB_J_F2 || i0 == SB_J_G0 || i0 == SB_J_G2) {
 #pragma unroll
-                            for (int w = 0; w < SB_WMAX; w++) pdd += S.ec[w] * (bd[SB_E_B(S.ei[w])] * st[SB_E_COL(S.ei[w])] + b[SB_E_B(S.ei[w])] * up[SB_E_COL(S.ei[w])]);
+                            for (int w = 0; w < SB_WMAX; w++) pdd = sb_dd_term(S.ec[w], bd[SB_E_B(S.ei[w])], st[SB_E_COL(S.ei[w])], b[SB_E_B(S.ei[w])], up[SB_E_COL(S.ei[w])], pdd);
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(SB_FULL, a, o); pdd += __shfl_xor_sync(SB_FULL, pdd, o); }
-                        if (lane == 0) {
-                            const double Phd = hub[0], Psi = hub[1], Psid = a, Pigdd = pdd;
-                            const double Pig = st[SB_J_F2] + st[SB_J_G0] + st[SB_J_G2], Pigd = up[SB_J_F2] + up[SB_J_G0] + up[SB_J_G2];
-                            const double kd = __ldg(sb), kdd = __ldg(sb + 1), kddd = __ldg(sb + 2), ek = __ldg(sb + 3), chi = __ldg(sb + 4);
-                            const double v = -kd * ek, vd = (-kdd + kd * kd) * ek, vdd = (-kddd + 3 * kd * kdd - kd * kd * kd) * ek;
-                            const double thb = st[SB_J_TB], thbd = up[SB_J_TB];
-                            double ST = v * (st[SB_J_F0] / 4 + Psi + Pig / 16) + ek * (Psid + Phd) + (vd * thb + v * thbd) / (k * k) + 3.0 / (16 * k * k) * (vdd * Pig + 2 * vd * Pigd + v * Pigdd);
-                            double SE = 3.0 / 16.0 * v * Pig / ((k * chi) * (k * chi));
-                            if (A.scale_k) { ST *= k; SE *= k * k; }
-                            so[0] = ST;
-                            so[SB_SWIN] = SE;
-                            if (A.nS > 2) so[2 * SB_SWIN] = (ts >= CC.taurec) ? -(Psi + st[SB_J_PHI]) * (ts - CC.taurec) / (chi + ts - CC.taurec) / chi : 0.0 * Psi;
-                        }
+                        if (lane == 0)
+                            sb_source_close(sb, k, ts, CC.taurec, A.scale_k, A.nS, hub[0], hub[1], a, st[SB_J_F2] + st[SB_J_G0] + st[SB_J_G2], up[SB_J_F2] + up[SB_J_G0] + up[SB_J_G2], pdd, st[SB_J_TB],
+                                            up[SB_J_TB], st[SB_J_F0], st[SB_J_PHI], so, SB_SWIN);
                     }
                 } else if (tid < A.nS) so[tid * SB_SWIN] = NAN;
                 __syncthreads();
@@ -1781,8 +1784,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
             __syncthreads();
             { // automatic initial step (Hairer), order 5 -- sums over rows in the single-warp order
                 double d0 = 0, d1 = 0;
-                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d0 += (u[i0] / sk) * (u[i0] / sk); d1 += (f0[i0] / sk) * (f0[i0] / sk); }
-                d0 = sqrt(sb_split_sum(d0, xs, rb, lane) / SB_N); d1 = sqrt(sb_split_sum(d1, xs, rb, lane) / SB_N);
+                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d0 = u[i0] / sk; d1 = f0[i0] / sk; }
+                d0 = sqrt(sb_split_sumsq(d0, xs, rb, lane) / SB_N); d1 = sqrt(sb_split_sumsq(d1, xs, rb, lane) / SB_N);
                 const double dtmax = tend - t;
                 double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
                 dt0 = fmin(dt0, dtmax);
@@ -1792,8 +1795,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 sb_eval_f<false, SPL>(S, bs + SB_NB, U, K, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
                 __syncthreads();
                 double d2 = 0;
-                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; const double r = (K[i0] - f0[i0]) / sk; d2 += r * r; }
-                d2 = sqrt(sb_split_sum(d2, xs, rb, lane) / SB_N) / dt0;
+                if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d2 = (K[i0] - f0[i0]) / sk; }
+                d2 = sqrt(sb_split_sumsq(d2, xs, rb, lane) / SB_N) / dt0;
                 const double dm = fmax(d1, d2);
                 const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 5.0);
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
@@ -1884,9 +1887,9 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
 #else
                     const double r = k8 / (abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
 #endif
-                    es += r * r;
+                    es = r;
                 }
-                const double EEst = sqrt(sb_split_sum(es, xs, rb, lane) / SB_N);
+                const double EEst = sqrt(sb_split_sumsq(es, xs, rb, lane) / SB_N);
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
                 const double q = ctl.q_of(EEst);
                 if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
@@ -1896,11 +1899,11 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 const double un_ = has ? U[i0] + K[7 * SB_N + i0] : 0.0;
                 if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order)
                     double a1 = 0, a2 = 0, a3 = 0;
-                    for (int j = 0; j < 8; j++) { const double kj = K[j * SB_N + ic]; a1 += cH[0][j] * kj; a2 += cH[1][j] * kj; a3 += cH[2][j] * kj; }
+                    for (int j = 0; j < 8; j++) { const double kj = K[j * SB_N + ic]; a1 = fma(cH[0][j], kj, a1); a2 = fma(cH[1][j], kj, a2); a3 = fma(cH[2][j], kj, a3); }
                     while (isave < A.nsave && CC.saveat[isave] <= tn) {
                         const double ts = CC.saveat[isave];
                         const double th = (ts - t) / dt, t1 = 1 - th;
-                        const double v = (ts == tn) ? un_ : t1 * u[ic] + th * (un_ + t1 * (a1 + th * (a2 + th * a3)));
+                        const double v = (ts == tn) ? un_ : sb_dense(th, t1, u[ic], un_, a1, a2, a3);
                         if (has) { if (usave) usave[(size_t)isave * SB_N + sb_nat[i0]] = v; if (SRC) di[i0] = v; }
                         __syncthreads();
                         emit(di, ts, true);
