@@ -594,35 +594,38 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 // Batched look-up of the basis at the stage times of one Rosenbrock attempt: slots 1..5 = t + c_s·dt (and, if with0, slot 0 = t
 // together with ḃ(t)).  Lanes 0..5 locate their slot's table node in parallel and publish (node, w, hs, τ) through shared memory;
 // then all lanes sweep the (slot, basis) items, so that every L2 access of the attempt is in flight at once.
-// SPL (split kernel): every warp of the CTA locates the slots (identical values), warp `wsel == 0` issues the bulk copies, all warps wait for
-// them, and warp w sweeps the slots s with s % SB_R == wsel.
-template <bool SPL = false>
+// Locate stage time tau in the table (search forward from knot interval j) and put the table node and the cubic-Hermite weights of
+// (v0, d0, v1, d1), plus the derivative weights, into sp[0..7]; returns the knot interval.
+__device__ __forceinline__ int sb_slot_locate(const SbTable& tb, double tau, int j, double* sp) {
+    while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
+    const double tj = __ldg(tb.t + j), hs = (__ldg(tb.t + j + 1) - tj) / tb.msub;
+    const double f = (tau - tj) / hs;
+    const int sidx = max(0, min((int)f, tb.msub - 1));
+    const double w = f - sidx, w1 = w - 1.0;
+    sp[0] = __longlong_as_double((long long)j * tb.msub + sidx);
+    sp[1] = (1 + 2 * w) * w1 * w1; sp[2] = w * w1 * w1 * hs; sp[3] = w * w * (3 - 2 * w); sp[4] = w * w * w1 * hs;
+    sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
+    return j;
+}
+__device__ __forceinline__ double sb_hermite_val(double kk, double w1, double v0, double w2, double d0, double w3, double v1, double w4, double d1) { return kk * (w1 * v0 + w2 * d0 + w3 * v1 + w4 * d1); }
+__device__ __forceinline__ double sb_hermite_der(double kk, double s5, double v0, double v1, double s6, double d0, double s7, double d1) { return kk * (s5 * (v0 - v1) + s6 * d0 + s7 * d1); }
 __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb, double t, double dt, int jt, bool with0, const double* kp, double* bs, double* bdv, double* slotp /*smem 6x8*/, int lane,
-                                              double* tabs = nullptr, unsigned* parity = nullptr, int wsel = 0) {
+                                              double* tabs = nullptr, unsigned* parity = nullptr) {
     int jend = jt;
 #if SB_TMA
     const int s0t = with0 ? 0 : 1;
     const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
     constexpr unsigned ROWB = 4 * SB_NBETA * 8; // two nodes x (β, dβ/dτ): contiguous in the table
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
-    if (lane == 0 && (!SPL || wsel == 0)) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((6 - s0t) * ROWB) : "memory");
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((6 - s0t) * ROWB) : "memory");
 #endif
     if (lane < 6) {
-        const double tau = t + ((lane == 0) ? 0.0 : cc[lane]) * dt;
-        int j = jt;
-        while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
-        const double tj = __ldg(tb.t + j), hs = (__ldg(tb.t + j + 1) - tj) / tb.msub;
-        const double f = (tau - tj) / hs;
-        const int sidx = max(0, min((int)f, tb.msub - 1));
-        const double w = f - sidx, w1 = w - 1.0;
-        double* sp = slotp + lane * 8; // table node and the cubic-Hermite weights of (v0, d0, v1, d1); slot 0 also the derivative weights
-        sp[0] = __longlong_as_double((long long)j * tb.msub + sidx);
-        sp[1] = (1 + 2 * w) * w1 * w1; sp[2] = w * w1 * w1 * hs; sp[3] = w * w * (3 - 2 * w); sp[4] = w * w * w1 * hs;
-        sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
-        jend = j;
+        const double tau = fma((lane == 0) ? 0.0 : cc[lane], dt, t);
+        double* sp = slotp + lane * 8;
+        jend = sb_slot_locate(tb, tau, jt, sp);
 #if SB_TMA
-        if (lane >= s0t && (!SPL || wsel == 0)) {
-            const double* src = tb.tab + ((size_t)j * tb.msub + sidx) * 2 * SB_NBETA;
+        if (lane >= s0t) {
+            const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
         }
 #endif
@@ -647,7 +650,6 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
 #pragma unroll
         for (int s = 0; s < 6; s++) {
             if (s == 0 && !with0) continue;
-            if (SPL && (s % SB_R) != wsel) continue;
             const double* sp = slotp + s * 8;
             const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
             const double* n0 = tabs + s * 4 * SB_NBETA;
@@ -656,8 +658,8 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
                 const int m = r * 32 + lane;
                 if (m < SB_NB) {
                     const double v0 = n0[be[r]], d0 = n0[SB_NBETA + be[r]], v1 = n0[2 * SB_NBETA + be[r]], d1 = n0[3 * SB_NBETA + be[r]];
-                    bs[s * SB_NB + m] = kk[r] * (w1 * v0 + w2 * d0 + w3 * v1 + w4 * d1);
-                    if (s == 0) bdv[m] = kk[r] * (sp[5] * (v0 - v1) + sp[6] * d0 + sp[7] * d1);
+                    bs[s * SB_NB + m] = sb_hermite_val(kk[r], w1, v0, w2, d0, w3, v1, w4, d1);
+                    if (s == 0) bdv[m] = sb_hermite_der(kk[r], sp[5], v0, v1, sp[6], d0, sp[7], d1);
                 }
             }
         }
@@ -1090,6 +1092,7 @@ __device__ __forceinline__ void sb_bsolve(const SbLane& S, double* const (&rr)[N
     __syncwarp();
 }
 
+__device__ __forceinline__ double sb_wcorr(double k, double zp, double c1, double zq, double c2) { return k + (zp * c1 + zq * c2); } // k + Z c (last stage)
 __device__ __forceinline__ void sb_hub_dots(const SbLane& S, const double* b, const double* r, double& s1, double& s2, int lane) {
     double a = 0, c = 0;
 #pragma unroll
@@ -1542,7 +1545,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                     c1p = (m22 * s1 - m12 * s2) * idet; c2p = (-m21 * s1 + m11 * s2) * idet;
                 }
 #pragma unroll
-                for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) K[7 * SB_N + i] += Zp[i] * c1p + Zq[i] * c2p; }
+                for (int r = 0; r < SB_R; r++) { const int i = r * 32 + lane; if (i < SB_N) K[7 * SB_N + i] = sb_wcorr(K[7 * SB_N + i], Zp[i], c1p, Zq[i], c2p); }
                 __syncwarp();
                 // error estimate: k8 (Rodas5P), RMS norm scaled by abstol + reltol·max(|u|,|unew|)
                 double es = 0; bool bad = false;
@@ -1665,8 +1668,10 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1
 #define SB_HAVE_SPLIT 1
 static_assert(SB_J_F2 < 32 && SB_J_G0 < 32 && SB_J_G2 < 32, "the split kernel closes the source evaluation on the warp of round 0");
-#define SB_XS_SUM 8 // exchange area: [0] work index, [8 + r·32 + lane] per-lane partial sums of round r
-#define SB_XS_DOUBLES (SB_XS_SUM + 32 * SB_R)
+#define SB_XS_SUM 8 // exchange area: ints [0] work index, [1] knot interval of t + dt; doubles [2], [3] the controller's powers; [8 + r·32 + lane] per-lane terms of round r
+#define SB_XS_KC (SB_XS_SUM + 32 * SB_R)   // corrected stage vectors k_1..k_7, [7][SB_N]
+#define SB_XS_BD5 (SB_XS_KC + 7 * SB_N)    // derivative basis at the last stage time, [SB_NB]
+#define SB_XS_DOUBLES (SB_XS_BD5 + SB_NB)
 // Σ_rows v_row² where v is this thread's row value (0 for an absent row): per lane the fma chain over the rounds in the single-warp order, then the butterfly
 __device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, int lane) {
     xs[SB_XS_SUM + rb * 32 + lane] = v;
@@ -1676,6 +1681,59 @@ __device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, i
     for (int r = 0; r < SB_R; r++) { const double x = xs[SB_XS_SUM + r * 32 + lane]; t = fma(x, x, t); }
     __syncthreads();
     return warp_sum(t);
+}
+#ifdef SB_SPLIT_PROF
+// cycle accounting of one attempt by phase (debug builds only: scripts/split_prof.py); slot i = cycles between mark i-1 and mark i, thread 0 of each CTA
+__device__ unsigned long long sb_split_prof[16];
+#define SB_PROF_DECL long long pc_ = clock64(); unsigned long long pf_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define SB_PROF(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - pc_); pc_ = c_; }
+#define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 12; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[12], (unsigned long long)(naccept + nreject)); }
+#else
+#define SB_PROF_DECL
+#define SB_PROF(i)
+#define SB_PROF_OUT
+#endif
+// Basis at the stage times 2..6 of an attempt (slots 1..5; slot 0, the time t, is carried over from the previous attempt's last stage time).
+// One warp locates the slots and issues the table-row copies ...
+__device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
+    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
+    constexpr unsigned ROWB = 4 * SB_NBETA * 8;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(5 * ROWB) : "memory");
+    if (lane >= 1 && lane < 6) {
+        double* sp = slotp + lane * 8;
+        const int j = sb_slot_locate(tb, fma(cc[lane], dt, t), jt, sp);
+        const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
+        if (lane == 5) *jend = j; // interval of t + dt: the next attempt's starting hint
+    }
+    __syncwarp();
+}
+// ... and all warps but warp 0 (which runs the eliminations meanwhile) wait for the rows and sweep the slots, `widx` of SB_R − 1 each
+__device__ __forceinline__ void sb_split_bar_others() { asm volatile("bar.sync 1, %0;" ::"n"(SB_WARP * (SB_R - 1)) : "memory"); }
+__device__ __forceinline__ void sb_split_basis_sweep(const SbLane& S, const double* kp, double* bs, double* bd5, const double* slotp, const double* tabs, unsigned ph, int lane, int widx) {
+    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
+    asm volatile("{\n .reg .pred p;\n SB_WAITS_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra SB_WAITS_%=;\n}" ::"r"(mbar), "r"(ph) : "memory");
+    double kk[SB_NBR];
+    int be[SB_NBR];
+#pragma unroll
+    for (int r = 0; r < SB_NBR; r++) { be[r] = SB_LO16(S.bp[r]); kk[r] = kp[SB_HI16(S.bp[r])]; }
+#pragma unroll
+    for (int s = 1; s < 6; s++) {
+        if ((s - 1) % (SB_R - 1) != widx) continue;
+        const double* sp = slotp + s * 8;
+        const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
+        const double* n0 = tabs + s * 4 * SB_NBETA;
+#pragma unroll
+        for (int r = 0; r < SB_NBR; r++) {
+            const int m = r * 32 + lane;
+            if (m < SB_NB) {
+                const double v0 = n0[be[r]], d0 = n0[SB_NBETA + be[r]], v1 = n0[2 * SB_NBETA + be[r]], d1 = n0[3 * SB_NBETA + be[r]];
+                bs[s * SB_NB + m] = sb_hermite_val(kk[r], w1, v0, w2, d0, w3, v1, w4, d1);
+                if (s == 5) bd5[m] = sb_hermite_der(kk[r], sp[5], v0, v1, sp[6], d0, sp[7], d1); // the next attempt's slot 0 derivative, if this one is accepted
+            }
+        }
+    }
 }
 __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(const __grid_constant__ SbSolveArgs A) {
     constexpr bool SPL = true;
@@ -1691,6 +1749,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
     double* const tabs = sm + SB_SM_TAB;
     double* const xs = sm + SB_SM_DOUBLES;
     unsigned tpar = 0;
+    SB_PROF_DECL
     if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_u32(sm + SB_SM_MBAR)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -1803,25 +1862,37 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
             }
             int jend = jt;
             bool moved = false;
+            double qoldp; // the controller's power of the previous error estimate, carried along (see below)
+            { double q0 = ctl.qold; asm volatile("" : "+d"(q0)); qoldp = pow(q0, 2.0 / 25.0); } // (opaque argument: evaluated by the device routine like every later one, not folded at compile time)
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
-                __syncthreads(); // the previous attempt's readers of bs / the staging area are done
-                jend = sb_basis_batch<SPL>(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar, warp);
-                __syncthreads();
+                SB_PROF(0)
+                __syncthreads(); // the previous attempt's readers of bs / the staging area are done; u and slot 0 of the basis (time t) are in place
+                SB_PROF(1)
                 if (moved) {
                     sb_eval_f<false, SPL>(S, bs, u, f0, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
                     sb_eval_dT<SPL>(S, bs, bdv, u, dT, lane, rb);
-                    moved = false; // (f0, dT complete after the barrier inside sb_factor)
+                    moved = false; // (f0, dT are only read on the thread's own row)
                 }
-                // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0, meanwhile the others set up Z and the stage-1 right-hand side
+                SB_PROF(2)
+                // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0.  Meanwhile the other warps set up Z and the
+                // stage-1 right-hand side and bring in the basis at the stage times 2..6 (table rows by TMA, Hermite sweep): none of it is on warp 0's path.
                 sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0);
                 if (has) {
                     Zp[i0] = S.pqc[0] * bs[SB_LO16(S.pqi[0])]; Zq[i0] = S.pqc[1] * bs[SB_HI16(S.pqi[0])];
                     K[i0] = f0[i0] + dt * cd[0] * dT[i0];
                 }
+                if (!w0) {
+                    if (warp == 1) sb_split_basis_issue(CC.tb, t, dt, jt, kp + 8, tabs, reinterpret_cast<int*>(xs) + 1, lane);
+                    sb_split_bar_others(); // slot descriptors visible to the sweeping warps
+                    sb_split_basis_sweep(S, kp, bs, xs + SB_XS_BD5, kp + 8, tabs, tpar, lane, warp - 1);
+                }
+                tpar ^= 1u;
                 __syncthreads();
+                jend = reinterpret_cast<const int*>(xs)[1];
+                SB_PROF(3)
                 // the three columns of the first solve: one per warp (with fewer than three warps, warp 0 takes the rest)
                 {
                     double* const cols[3] = {Zp, Zq, K};
@@ -1830,6 +1901,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 }
                 nsolve += 3;
                 __syncthreads();
+                SB_PROF(4)
                 double m11, m12, m21, m22;
                 sb_hub_dots(S, bs, Zp, m11, m21, lane);
                 sb_hub_dots(S, bs, Zq, m12, m22, lane);
@@ -1837,12 +1909,14 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 const double idet = sb_rcp(m11 * m22 - m12 * m21);
                 const double idt = sb_rcp(dt);
                 double c1p = 0, c2p = 0;
+                double* const KC = xs + SB_XS_KC; // k_j with the Woodbury correction applied: every later use is on the thread's own row, so no barrier guards it
+                SB_PROF(5)
                 for (int s = 1; s < 8; s++) {
                     double* ks = K + s * SB_N;
                     const double hd_ = dt * cd[s];
                     double* kprev = ks - SB_N;
                     double h1, h2;
-                    sb_hub_dots(S, bs, kprev, h1, h2, lane); // (every warp, from the complete k_{s-1}: same values)
+                    sb_hub_dots(S, bs, kprev, h1, h2, lane); // (every warp, from the complete uncorrected k_{s-1}: same values)
                     c1p = (m22 * h1 - m12 * h2) * idet; c2p = (-m21 * h1 + m11 * h2) * idet;
                     const bool inc = s >= 6;
                     const int nold = s - 1;
@@ -1851,7 +1925,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     for (int j = 0; j < 6; j++) {
                         if (nold > j) {
                             const double a_ = cA[s][j], c_ = cC[s][j] * idt;
-                            const double kj = K[j * SB_N + ic];
+                            const double kj = KC[j * SB_N + ic];
                             if (j < 4 && !inc) ua = fma(a_, kj, ua);
                             Racc = fma(c_, kj, Racc);
                         }
@@ -1861,45 +1935,58 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                         const double kp_ = kprev[ic] + Zp[ic] * c1p + Zq[ic] * c2p;
                         ua = fma(al, kp_, ua);
                         Racc = fma(cl, kp_, Racc);
-                        __syncthreads(); // every warp has taken its hub dot products from the uncorrected k_{s-1}
-                        if (has) { kprev[i0] = kp_; U[i0] = ua; }
+                        if (has) { KC[(s - 1) * SB_N + i0] = kp_; U[i0] = ua; }
                     }
                     __syncthreads();
+                    SB_PROF(6)
                     sb_eval_f<true, SPL>(S, bs + cslot[s] * SB_NB, U, ks, lane, &Racc, hd_, dT, nullptr, rb); nf++;
                     __syncthreads();
+                    SB_PROF(7)
                     if (w0) { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); }
                     nsolve++;
                     __syncthreads();
+                    SB_PROF(8)
                 }
                 {
                     double s1, s2;
                     sb_hub_dots(S, bs, K + 7 * SB_N, s1, s2, lane);
                     c1p = (m22 * s1 - m12 * s2) * idet; c2p = (-m21 * s1 + m11 * s2) * idet;
                 }
-                __syncthreads();
-                if (has) K[7 * SB_N + i0] += Zp[i0] * c1p + Zq[i0] * c2p;
+                const double k8 = sb_wcorr(K[7 * SB_N + ic], Zp[ic], c1p, Zq[ic], c2p);
                 // error estimate (own row; the sum over rows in the single-warp order)
                 double es = 0; bool bad = false;
                 if (has) {
-                    const double k8 = K[7 * SB_N + i0], un = U[i0] + k8;
+                    const double un = U[i0] + k8;
 #if SB_NORMRCP
-                    const double r = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
+                    es = k8 * sb_rcp(abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
 #else
-                    const double r = k8 / (abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
+                    es = k8 / (abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
 #endif
-                    es = r;
                 }
                 const double EEst = sqrt(sb_split_sumsq(es, xs, rb, lane) / SB_N);
+                SB_PROF(9)
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
-                const double q = ctl.q_of(EEst);
+                // step controller (SbController::q_of): its two powers, EEst^(7/50) and -- for the NEXT attempt's q -- max(EEst, 1e-4)^(2/25), on two warps at once
+                {
+                    double pw = 0;
+                    if (warp == 0) pw = pow(EEst, 7.0 / 50.0);
+                    else if (warp == 1) pw = pow(fmax(EEst, 1e-4), 2.0 / 25.0);
+                    if (lane == 0 && warp < 2) xs[2 + warp] = pw;
+                    __syncthreads();
+                }
+                const double pw1 = xs[2], pw2 = xs[3];
+                double q = 0.1;
+                if (EEst != 0.0) { ctl.q11 = pw1; q = fmax(0.1, fmin(5.0, (pw1 / qoldp) / 0.9)); }
                 if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
                 const double dtnew = ctl.accept(dt, q, EEst);
+                qoldp = pw2;
+                SB_PROF(10)
                 const double tn = last ? tend : t + dt;
-                const double un_ = has ? U[i0] + K[7 * SB_N + i0] : 0.0;
+                const double un_ = has ? U[i0] + k8 : 0.0;
                 if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order)
                     double a1 = 0, a2 = 0, a3 = 0;
-                    for (int j = 0; j < 8; j++) { const double kj = K[j * SB_N + ic]; a1 = fma(cH[0][j], kj, a1); a2 = fma(cH[1][j], kj, a2); a3 = fma(cH[2][j], kj, a3); }
+                    for (int j = 0; j < 8; j++) { const double kj = (j < 7) ? KC[j * SB_N + ic] : k8; a1 = fma(cH[0][j], kj, a1); a2 = fma(cH[1][j], kj, a2); a3 = fma(cH[2][j], kj, a3); }
                     while (isave < A.nsave && CC.saveat[isave] <= tn) {
                         const double ts = CC.saveat[isave];
                         const double th = (ts - t) / dt, t1 = 1 - th;
@@ -1915,9 +2002,12 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 t = tn;
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
                 if (last) break;
+                // the basis at the new time is the one of the last stage time (c = 1): slot 5 -> slot 0, with the derivative kept by the sweep
+                for (int m = tid; m < SB_NB; m += NT) { bs[m] = bs[5 * SB_NB + m]; bdv[m] = xs[SB_XS_BD5 + m]; }
                 dt = dtnew;
                 jt = jend;
                 moved = true;
+                SB_PROF(11)
             }
         }
         __syncthreads();
@@ -1926,6 +2016,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
             if (usave && has) usave[(size_t)isave * SB_N + i0] = NAN;
             emit(u, t, false);
         }
+        SB_PROF_OUT
         if (tid == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
     }
 }
@@ -2147,6 +2238,14 @@ int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks
 // The same solve as sbm_solvept_src with ONE CTA of SB_R warps per mode (sb_integrate_split_kernel): for launches that leave most of the GPU
 // idle under the warp-per-mode mapping (fewer modes than sbm_split_capacity()), where the time is the slowest mode's sequential attempts.
 // Bit-identical results.  Returns the grid size, -5 if this model has no split kernel, or a negative error.
+#ifdef SB_SPLIT_PROF
+int sbm_split_prof(unsigned long long* out, int reset) {
+    SB_CUDA_CHECK(cudaDeviceSynchronize());
+    SB_CUDA_CHECK(cudaMemcpyFromSymbol(out, sb_split_prof, sizeof(sb_split_prof)));
+    if (reset) { unsigned long long z[16] = {0}; SB_CUDA_CHECK(cudaMemcpyToSymbol(sb_split_prof, z, sizeof(z))); }
+    return 0;
+}
+#endif
 int sbm_split_capacity(void) { // modes that run concurrently under the split mapping (0: not available for this model)
 #if SB_HAVE_SPLIT
     int dev, nsm, occ = 0;
