@@ -430,6 +430,10 @@ struct SbSolveArgs {
 #ifndef SB_Z3
 #define SB_Z3 1
 #endif
+// Division-free pivots along the phase-0 paths (see sb_factor); the sequential form is kept for long paths (register arrays of SB_PL entries)
+#ifndef SB_PATH_CONT
+#define SB_PATH_CONT (SB_PL <= 12)
+#endif
 #ifndef SB_KEEP_MAX
 #define SB_KEEP_MAX 24 // doubles per lane that sb_bsolve may hold across its top step (see KEEP there)
 #endif
@@ -762,38 +766,63 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
 }
 
 
+#ifdef SB_SPLIT_PROF
+// cycle accounting of one attempt by phase (debug builds only: scripts/split_prof.py); slot i = cycles between mark i-1 and mark i, thread 0 of each CTA
+__device__ unsigned long long sb_split_prof[24];
+#define SB_PROF_DECL long long pc_ = clock64(); unsigned long long pf_[20] = {0};
+#define SB_PROF(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - pc_); pc_ = c_; }
+#define SB_PROF_PARM , unsigned long long* pf_ = nullptr, long long* pcp_ = nullptr
+#define SB_PROF_PASS , pf_, &pc_
+#define SB_PROF_F(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - *pcp_); *pcp_ = c_; }
+#define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 20; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[20], (unsigned long long)(naccept + nreject)); }
+#else
+#define SB_PROF_DECL
+#define SB_PROF_PARM
+#define SB_PROF_PASS
+#define SB_PROF_F(i)
+#define SB_PROF(i)
+#define SB_PROF_OUT
+#endif
 // Factor B = x·I − J_local(b): phase-0 elimination paths (zero fill, no pivoting: the chains have sign-skew off-diagonals
 // and non-negative damping, so pivots only grow), then the top = root paths + explicit pivoted inverse of the top blocks.
 // Leaves 1/pivot in di, multipliers in mm, (entry towards the parent)/pivot in up, block inverses in blk.
 template <bool SPL = false>
-__device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane, int rb = 0, bool elim = true) {
+__device__ __forceinline__ void sb_factor(const SbLane& S, double x, const double* b, double* di, double* up, double* mm, double* blk, int lane, int rb = 0, bool elim = true SB_PROF_PARM) {
+    if (!SPL) { // (split kernel: every multiplier slot is either rewritten by the scatter below or structurally zero, so mm is cleared once per mode, and blk by
+                // warp 0 after the attempt's last solve -- see sb_integrate_split_kernel)
 #pragma unroll
-    for (int r = 0; r < SB_NRL; r++) { const int i = SB_ROW(r); if (i < SB_N) mm[i] = 0; }
-    if (!SPL || rb == 0) for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0;
-    if (SPL) __syncthreads(); else __syncwarp(); // the scatter below writes multipliers of rows other lanes (split: other warps) have just cleared
+        for (int r = 0; r < SB_NRL; r++) { const int i = SB_ROW(r); if (i < SB_N) mm[i] = 0; }
+        for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0;
+        __syncwarp(); // the scatter below writes multipliers of rows other lanes have just cleared
+    }
 #pragma unroll
     for (int r = 0; r < SB_NRL; r++) {
         const int i = SB_ROW(r);
         double dacc = x, uacc = 0;
+        // branch-free: all loads first, then selects and a predicated store per entry (adding 0.0 leaves the sums bit for bit as they were;
+        // a branch per entry kept each load behind the previous entry's reconvergence point)
+        double v[SB_WMAX]; // (round 0 is the widest)
+#pragma unroll
+        for (int w = 0; w < SB_WDL(r); w++) { const int e = SB_EOL(r) + w; v[w] = -S.ec[e] * b[SB_E_B(S.ei[e])]; }
 #pragma unroll
         for (int w = 0; w < SB_WDL(r); w++) {
             const int e = SB_EOL(r) + w;
             const unsigned ix = S.ei[e];
-            const double v = -S.ec[e] * b[SB_E_B(ix)];
             const int kind = SB_E_KIND(ix), tgt = SB_E_TGT(ix);
-            if (kind == 0) dacc += v;
-            else if (kind == 1) uacc += v;
-            else if (S.ec[e] != 0.0) { // multiplier (target < N) or top-block entry (target >= N: blk follows mm)
+            dacc += (kind == 0) ? v[w] : 0.0;
+            uacc += (kind == 1) ? v[w] : 0.0;
+            if (kind >= 2 && S.ec[e] != 0.0) { // multiplier (target < N) or top-block entry (target >= N: blk follows mm)
 #if SB_UNIQUE_TARGETS
-                mm[tgt] = v;
+                mm[tgt] = v[w];
 #else
-                mm[tgt] += v;
+                mm[tgt] += v[w];
 #endif
             }
         }
         if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
     if (SPL) __syncthreads(); else __syncwarp();
+    if (SPL) { SB_PROF_F(12) }
     if (SPL && !elim) return; // split kernel: the eliminations below are one warp's work (the paths and the top block live on lanes, not rows)
     // phase 0: every vertex but the last of a path is finished here (multiplier and parent coupling scaled by 1/pivot); the
     // last one keeps its raw multiplier for the owner of its parent, which forms the Schur term mm_raw * (up/pivot)
@@ -802,6 +831,33 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         const int start = SB_P_START(S.ph[rd]), len = SB_P_LEN(S.ph[rd]);
         if (len > 0) {
             double* dip = di + start; double* mmp = mm + start; double* upp = up + start;
+#if SB_PATH_CONT
+            // Pivots of the tridiagonal path as ratios of continuants: p_i = a_i p_{i-1} − (m_{i-1} u_{i-1}) p_{i-2}, d_i = p_i / p_{i-1}.  The dependent
+            // chain is ONE fma per vertex (the product with p_{i-2} is ready a step earlier) instead of multiply, fma and a Newton reciprocal; the
+            // reciprocals of the p_i are independent of one another.  Sign-skew off-diagonals (m u < 0) and non-negative damping make every term of the
+            // recurrence positive: no cancellation.  Growth is bounded by (1/(γ dt) + damping)^SB_PL, far inside the double range for SB_PL <= 12.
+            double pp[SB_PL], mr[SB_PL], ur[SB_PL];
+#pragma unroll
+            for (int pos = 0; pos < SB_PL; pos++) { mr[pos] = 0; ur[pos] = 0; pp[pos] = 1.0; if (pos < len) { mr[pos] = mmp[pos]; ur[pos] = upp[pos]; pp[pos] = dip[pos]; } }
+            {
+                double pm2 = 1.0, pm1 = pp[0];
+#pragma unroll
+                for (int pos = 1; pos < SB_PL; pos++) {
+                    const double p = fma(pp[pos], pm1, -((mr[pos - 1] * ur[pos - 1]) * pm2)); // (past the end of the path: 1·p_{i-1} − 0)
+                    pp[pos] = p; pm2 = pm1; pm1 = p;
+                }
+            }
+            double dv[SB_PL]; // 1/d_pos = p_{pos-1} / p_pos: straight-line, so that the reciprocals pipeline (past the end of the path: unused)
+            dv[0] = sb_rcp(pp[0]);
+#pragma unroll
+            for (int pos = 1; pos < SB_PL; pos++) dv[pos] = pp[pos - 1] * sb_rcp(pp[pos]);
+#pragma unroll
+            for (int pos = 0; pos < SB_PL; pos++) if (pos < len) dip[pos] = dv[pos];
+#pragma unroll
+            for (int pos = 0; pos < SB_PL; pos++) { const double uv = ur[pos] * dv[pos]; if (pos < len) upp[pos] = uv; }
+#pragma unroll
+            for (int pos = 0; pos < SB_PL; pos++) { const double mv = mr[pos] * dv[pos]; if (pos + 1 < len) mmp[pos] = mv; } // (the last vertex keeps its raw multiplier for the owner of its parent)
+#else
             double dinv = sb_rcp(dip[0]);
             dip[0] = dinv;
 #pragma unroll
@@ -815,9 +871,11 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
                 }
             }
             upp[len - 1] *= dinv;
+#endif
         }
     }
     __syncwarp();
+    if (SPL) { SB_PROF_F(13) }
     // top: root paths (fed by phase-0 paths only) ...
 #pragma unroll
     for (int rd = 0; rd < SB_TR; rd++) { // (no such paths in the ΛCDM / w0waCDM models: SB_TR = 0)
@@ -852,10 +910,21 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         double dj = 1.0;
         if (S.tv != SB_NOKID) {
             dj = di[S.tv];
+            // branch-free gather: an absent child reads this lane's own vertex instead and its term is dropped by a select (a branch per child
+            // kept each child's loads behind the previous child's reconvergence point)
+            double mrv[3], div[3], upv[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); if (ch != SB_NOKID) { const double mr = mm[ch]; mm[ch] = mr * di[ch]; dj = fma(-mr, up[ch], dj); } }
+            for (int c = 0; c < 3; c++) { const int ch = SB_KID(S.dk, c); const int cs = (ch != SB_NOKID) ? ch : (int)S.tv; mrv[c] = mm[cs]; div[c] = di[cs]; upv[c] = up[cs]; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int ch = SB_KID(S.dk, c);
+                const double tnew = fma(-mrv[c], upv[c], dj);
+                if (ch != SB_NOKID) mm[ch] = mrv[c] * div[c];
+                dj = (ch != SB_NOKID) ? tnew : dj;
+            }
             if (i >= nb) { di[S.tv] = sb_rcp(dj); up[S.tv] = 0; }
         }
+        if (SPL) { SB_PROF_F(14) }
 #if SB_GJ_INPLACE
         // In-place Gauss-Jordan: the column of the pivot is overwritten by the corresponding column of the inverse, so only the
         // SB_TOPMAX entries of the pivot row travel per step (the augmented form [A | I] moves twice as many).  Rows are not
@@ -863,7 +932,11 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         // register row is column p_kx (= who of step kx) of the inverse; the scatter at the end undoes that.
         double Ar[SB_TOPMAX];
 #pragma unroll
-        for (int j = 0; j < SB_TOPMAX; j++) Ar[j] = (i == j) ? ((i < nb) ? dj : 1.0) : ((i < nb && j < nb) ? blk[off + i * nb + j] : 0.0);
+        for (int j = 0; j < SB_TOPMAX; j++) { // (unconditional loads from a clamped index, then selects)
+            const bool inb = i < nb && j < nb;
+            const double bv = blk[inb ? off + i * nb + j : 0];
+            Ar[j] = (i == j) ? ((i < nb) ? dj : 1.0) : (inb ? bv : 0.0);
+        }
         int myrow = -1; // pivot column this lane's row was used for (= its row index in the inverse)
         unsigned perm = 0; // who of every step, 3 bits each
         const int base = lane & ~7;
@@ -875,8 +948,10 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             // several blocks would need, measured slower than the shuffle search below.)
             unsigned key = 0;
             if (myrow < 0 && i < SB_TOPMAX && bb == 0) key = (((unsigned)__double2hiint(Ar[kx]) & 0x7FFFFFF0u)) | (unsigned)(8 - i);
+            const double cinv = sb_rcp(Ar[kx]); // every candidate's reciprocal, formed while the search is in flight (same value as rcp of the broadcast pivot)
             const int who = 8 - (int)(__reduce_max_sync(SB_FULL, key) & 15u);
 #else
+            const double cinv = sb_rcp(Ar[kx]);
             double best = (myrow < 0 && i < SB_TOPMAX) ? fabs(Ar[kx]) : -1.0; int who = i;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(SB_FULL, best, o); const int ow = __shfl_xor_sync(SB_FULL, who, o); if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; } }
@@ -884,8 +959,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
             const bool isp = (i == who);
             if (isp) myrow = kx;
             perm |= (unsigned)who << (3 * kx);
-            const double piv = __shfl_sync(SB_FULL, Ar[kx], base + who);
-            const double inv = sb_rcp(piv);
+            const double inv = __shfl_sync(SB_FULL, cinv, base + who);
             const double l = isp ? 0.0 : Ar[kx];
 #pragma unroll
             for (int j = 0; j < SB_TOPMAX; j++) {
@@ -932,6 +1006,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
     }
 #endif
     __syncwarp();
+    if (SPL) { SB_PROF_F(15) }
 }
 
 // r <- B^{-1} r for NR right-hand sides at once (independent recurrences interleave: the solve is latency-bound), in three
@@ -1665,7 +1740,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 // on warp 0, with CTA barriers at the phase boundaries.  Every warp carries the scalar control state and takes identical decisions from
 // shared data; sums over rows are formed per lane over the rounds in the single-warp order before the butterfly, so the results are
 // bit-identical to sb_integrate_kernel<false> (tests/test_gpu_parity.py::test_split_kernel_is_bit_identical).
-#if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1
+#if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1 && SB_UNIQUE_TARGETS
 #define SB_HAVE_SPLIT 1
 static_assert(SB_J_F2 < 32 && SB_J_G0 < 32 && SB_J_G2 < 32, "the split kernel closes the source evaluation on the warp of round 0");
 #define SB_XS_SUM 8 // exchange area: ints [0] work index, [1] knot interval of t + dt; doubles [2], [3] the controller's powers; [8 + r·32 + lane] per-lane terms of round r
@@ -1682,17 +1757,6 @@ __device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, i
     __syncthreads();
     return warp_sum(t);
 }
-#ifdef SB_SPLIT_PROF
-// cycle accounting of one attempt by phase (debug builds only: scripts/split_prof.py); slot i = cycles between mark i-1 and mark i, thread 0 of each CTA
-__device__ unsigned long long sb_split_prof[16];
-#define SB_PROF_DECL long long pc_ = clock64(); unsigned long long pf_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#define SB_PROF(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - pc_); pc_ = c_; }
-#define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 12; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[12], (unsigned long long)(naccept + nreject)); }
-#else
-#define SB_PROF_DECL
-#define SB_PROF(i)
-#define SB_PROF_OUT
-#endif
 // Basis at the stage times 2..6 of an attempt (slots 1..5; slot 0, the time t, is carried over from the previous attempt's last stage time).
 // One warp locates the slots and issues the table-row copies ...
 __device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
@@ -1788,6 +1852,8 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
         double dt = 0;
         int jt = 0;
         if (tid == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
+        if (has) mm[i0] = 0; // multiplier slots: cleared once per mode (and after a non-finite attempt), see sb_factor
+        for (int i = tid; i < SB_TOPSTORE; i += NT) blk[i] = 0;
         __syncthreads();
         if (has) u[i0] = U[sb_nat[i0]];
         __syncthreads();
@@ -1879,7 +1945,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 SB_PROF(2)
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0.  Meanwhile the other warps set up Z and the
                 // stage-1 right-hand side and bring in the basis at the stage times 2..6 (table rows by TMA, Hermite sweep): none of it is on warp 0's path.
-                sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0);
+                sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0 SB_PROF_PASS);
                 if (has) {
                     Zp[i0] = S.pqc[0] * bs[SB_LO16(S.pqi[0])]; Zq[i0] = S.pqc[1] * bs[SB_HI16(S.pqi[0])];
                     K[i0] = f0[i0] + dt * cd[0] * dT[i0];
@@ -1947,6 +2013,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     __syncthreads();
                     SB_PROF(8)
                 }
+                if (w0) for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0; // the top block's storage is clean for the next factorisation (its last reader, the solve above, is warp 0 itself)
                 {
                     double s1, s2;
                     sb_hub_dots(S, bs, K + 7 * SB_N, s1, s2, lane);
@@ -1965,7 +2032,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 }
                 const double EEst = sqrt(sb_split_sumsq(es, xs, rb, lane) / SB_N);
                 SB_PROF(9)
-                if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
+                if (!isfinite(EEst)) { nreject++; dt /= 5; if (has) mm[i0] = 0; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; } // (0·NaN may sit in structurally-zero slots)
                 // step controller (SbController::q_of): its two powers, EEst^(7/50) and -- for the NEXT attempt's q -- max(EEst, 1e-4)^(2/25), on two warps at once
                 {
                     double pw = 0;
@@ -2242,7 +2309,7 @@ int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks
 int sbm_split_prof(unsigned long long* out, int reset) {
     SB_CUDA_CHECK(cudaDeviceSynchronize());
     SB_CUDA_CHECK(cudaMemcpyFromSymbol(out, sb_split_prof, sizeof(sb_split_prof)));
-    if (reset) { unsigned long long z[16] = {0}; SB_CUDA_CHECK(cudaMemcpyToSymbol(sb_split_prof, z, sizeof(z))); }
+    if (reset) { unsigned long long z[24] = {0}; SB_CUDA_CHECK(cudaMemcpyToSymbol(sb_split_prof, z, sizeof(z))); }
     return 0;
 }
 #endif
