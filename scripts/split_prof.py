@@ -6,9 +6,9 @@ import symboltz.jl_b200 as sb
 M = sb.ΛCDM(lmax=10); prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M)); bg = sb.solvebg(prob)
 lib = C.CDLL(os.path.abspath(sys.argv[1] if len(sys.argv) > 1 else "scripts/variants/prof.so"))
 prob.lib = lib
-names = ["accept path tail -> attempt start", "barrier at the attempt start", "f0, dT after a move", "sb_factor (rows, eliminations on warp 0 | Z, K1, basis slots 1-5 on the others) + barrier",
+names = ["accept path tail (or reject + wait for the controller warp) -> attempt start", "barrier at the attempt start", "f0, dT after a move", "sb_factor (rows, eliminations on warp 0 | Z, K1, basis slots 1-5 on the others) + barrier",
          "3-column solve + barrier", "hub dots of Z, 2x2 inverse", "stages: hub dots + accumulation + barrier (x7)", "stages: f-evaluation + barrier (x7)", "stages: B-solve on warp 0 + barrier (x7)",
-         "k8 correction + error norm", "controller (one pow per warp) + barrier", "accept: dense output, state update, slot 5 -> slot 0",
+         "k8 correction + error norm", "pick-up of the controller warp's answer after an accepted step", "accept: dense output, state update, slot 5 -> slot 0",
          "  (in sb_factor) clear, row scatter, 2 barriers", "  (in sb_factor) phase-0 path eliminations", "  (in sb_factor) top: gather of the children's Schur terms", "  (in sb_factor) 5x5 pivoted Gauss-Jordan"]
 ks = sb.loggrid(1e-4, 1.0, length=100) / sb.k0
 f = lambda k: min(1e-2 / k, 1e-4)

@@ -708,6 +708,16 @@ __device__ __forceinline__ int sb_basis_batch(const SbLane& S, const SbTable& tb
     return jend;
 }
 
+// Barriers of the split kernel (sb_integrate_split_kernel): its SB_R row warps synchronise on named barrier 2; the controller warp, which
+// only computes the step controller's powers, is not part of it (barriers 3 and 4 are its mailbox, barrier 1 joins the warps that sweep the basis).
+#define SB_SPLIT_NT (SB_WARP * SB_R)
+#define SB_SPLIT_THREADS (SB_SPLIT_NT + SB_WARP)
+__device__ __forceinline__ void sb_rows_sync() { asm volatile("bar.sync 2, %0;" ::"n"(SB_SPLIT_NT) : "memory"); }
+__device__ __forceinline__ bool sb_rows_or(bool p) {
+    unsigned r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 p, %1, 0;\n bar.red.or.pred q, 2, %2, p;\n selp.u32 %0, 1, 0, q;\n}" : "=r"(r) : "r"((unsigned)p), "n"(SB_SPLIT_NT) : "memory");
+    return r != 0;
+}
 // out = J(b)·U : owned ELL rows + the two hub functionals Φ̇ = φᵀU, Ψ = ψᵀU.
 // FUSE: out = J(b)·U + radd[r] + hd·dT  (the stage right-hand side is assembled in the same pass: one store per row)
 template <bool FUSE, bool SPL = false>
@@ -821,7 +831,7 @@ __device__ __forceinline__ void sb_factor(const SbLane& S, double x, const doubl
         }
         if (i < SB_N) { di[i] = dacc; up[i] = uacc; } // di holds the raw diagonal until the vertex is eliminated
     }
-    if (SPL) __syncthreads(); else __syncwarp();
+    if (SPL) sb_rows_sync(); else __syncwarp();
     if (SPL) { SB_PROF_F(12) }
     if (SPL && !elim) return; // split kernel: the eliminations below are one warp's work (the paths and the top block live on lanes, not rows)
     // phase 0: every vertex but the last of a path is finished here (multiplier and parent coupling scaled by 1/pivot); the
@@ -1743,18 +1753,21 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #if SB_TMA && SB_BSLOT && SB_R >= 2 && SB_R <= 4 && SB_TR == 0 && SB_NTOP == 1 && SB_UNIQUE_TARGETS
 #define SB_HAVE_SPLIT 1
 static_assert(SB_J_F2 < 32 && SB_J_G0 < 32 && SB_J_G2 < 32, "the split kernel closes the source evaluation on the warp of round 0");
-#define SB_XS_SUM 8 // exchange area: ints [0] work index, [1] knot interval of t + dt; doubles [2], [3] the controller's powers; [8 + r·32 + lane] per-lane terms of round r
+#define SB_XS_SUM 8 // exchange area: ints [0] work index, [1] knot interval of t + dt; doubles [2..5] the controller warp's mailbox; [8 + r·32 + lane] per-lane terms of round r
+#define SB_XS_P1 2  // EEst^(7/50) of the current command
+#define SB_XS_CMD 3 // command to the controller warp: the error estimate (NaN: exit)
+#define SB_XS_P2 4  // max(EEst, 1e-4)^(2/25), double-buffered by command parity
 #define SB_XS_KC (SB_XS_SUM + 32 * SB_R)   // corrected stage vectors k_1..k_7, [7][SB_N]
 #define SB_XS_BD5 (SB_XS_KC + 7 * SB_N)    // derivative basis at the last stage time, [SB_NB]
 #define SB_XS_DOUBLES (SB_XS_BD5 + SB_NB)
 // Σ_rows v_row² where v is this thread's row value (0 for an absent row): per lane the fma chain over the rounds in the single-warp order, then the butterfly
 __device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, int lane) {
     xs[SB_XS_SUM + rb * 32 + lane] = v;
-    __syncthreads();
+    sb_rows_sync();
     double t = 0;
 #pragma unroll
     for (int r = 0; r < SB_R; r++) { const double x = xs[SB_XS_SUM + r * 32 + lane]; t = fma(x, x, t); }
-    __syncthreads();
+    sb_rows_sync();
     return warp_sum(t);
 }
 // Basis at the stage times 2..6 of an attempt (slots 1..5; slot 0, the time t, is carried over from the previous attempt's last stage time).
@@ -1799,11 +1812,11 @@ __device__ __forceinline__ void sb_split_basis_sweep(const SbLane& S, const doub
         }
     }
 }
-__global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(const __grid_constant__ SbSolveArgs A) {
+__global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel(const __grid_constant__ SbSolveArgs A) {
     constexpr bool SPL = true;
     extern __shared__ __align__(16) double sm_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-    constexpr int NT = SB_WARP * SB_R;
+    constexpr int NT = SB_SPLIT_NT; // row threads
     const int rb = SB_R - 1 - warp; // warp 0 also runs the serial phases: it takes the last (shortest, narrowest) round
     const bool w0 = warp == 0;
     double* const sm = sm_all;
@@ -1817,21 +1830,48 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
     if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb_smem_u32(sm + SB_SM_MBAR)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (warp == SB_R) {
+        // Controller warp.  The step controller (SbController::q_of) needs EEst^(7/50) -- 1.3 k cycles of one warp's time in pow() -- before the next step
+        // size is known, and max(EEst, 1e-4)^(2/25) for the step after that.  The row warps post EEst as soon as the error norm is formed (barrier 3) and go
+        // on with everything of an accepted step that does not depend on the new step size (dense output, state update, f0 and dT at the new time);
+        // they pick the power up at barrier 4.  NaN is the exit command.
+        int par = 0;
+        while (true) {
+            asm volatile("bar.sync 3, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
+            const double E = xs[SB_XS_CMD];
+            if (E != E) break;
+            const double p1 = pow(E, 7.0 / 50.0);
+            if (lane == 0) xs[SB_XS_P1] = p1;
+            __threadfence_block();
+            asm volatile("bar.arrive 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
+            const double p2 = pow(fmax(E, 1e-4), 2.0 / 25.0);
+            if (lane == 0) xs[SB_XS_P2 + par] = p2;
+            par ^= 1;
+        }
+        return;
+    }
     const double reltol = A.reltol, abstol = A.abstol;
     const bool SRC = A.S != nullptr;
     SbLane S;
     S.load_split(lane, rb);
+    int cpar = 0; // parity of the next command to the controller warp
+    auto ctl_send = [&](double E) {
+        if (tid == 0) xs[SB_XS_CMD] = E;
+        __threadfence_block();
+        asm volatile("bar.arrive 3, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
+        cpar ^= 1;
+    };
     const SbCosmo& CC = A.c0;
     const int i0 = rb * 32 + lane;         // this thread's row
     const bool has = i0 < SB_N;
     const int ic = has ? i0 : SB_N - 1;    // clamped: loads of absent rows read the last row (results discarded)
 
     while (true) {
-        __syncthreads(); // every warp is done with the previous mode
+        sb_rows_sync(); // every warp is done with the previous mode
         if (tid == 0) reinterpret_cast<int*>(xs)[0] = atomicAdd(A.queue, 1);
-        __syncthreads();
+        sb_rows_sync();
         const int qi = reinterpret_cast<const int*>(xs)[0];
-        if (qi >= A.nk) break;
+        if (qi >= A.nk) { ctl_send(NAN); break; }
         const int mode = A.order ? A.order[qi] : qi;
         const double k = A.ks[mode];
         double t = A.tini[mode];
@@ -1854,9 +1894,9 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
         if (tid == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
         if (has) mm[i0] = 0; // multiplier slots: cleared once per mode (and after a non-finite attempt), see sb_factor
         for (int i = tid; i < SB_TOPSTORE; i += NT) blk[i] = 0;
-        __syncthreads();
+        sb_rows_sync();
         if (has) u[i0] = U[sb_nat[i0]];
-        __syncthreads();
+        sb_rows_sync();
         // one save point from the state in `st` (all warps; st complete and visible on entry)
         auto emit = [&](const double* st, double ts, bool valid) {
             if (SRC) {
@@ -1869,10 +1909,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                         bs[m] = kk * __ldg(sb + 8 + SB_LO16(pk));
                         bs[SB_NB + m] = kk * __ldg(sb + 8 + SB_NBETA + SB_LO16(pk));
                     }
-                    __syncthreads();
+                    sb_rows_sync();
                     double hub[2];
                     sb_eval_f<false, SPL>(S, bs, st, up, lane, nullptr, 0.0, nullptr, hub, rb); // u̇ into `up`
-                    __syncthreads();
+                    sb_rows_sync();
                     if (rb == 0) { // the rows of Π = F2 + G0 + G2 live in round 0; its warp closes the evaluation (same sums, same order as sb_source_point)
                         const double* b = bs; const double* bd = bs + SB_NB;
                         double a = 0, pdd = 0;
@@ -1889,9 +1929,9 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                                             up[SB_J_TB], st[SB_J_F0], st[SB_J_PHI], so, SB_SWIN);
                     }
                 } else if (tid < A.nS) so[tid * SB_SWIN] = NAN;
-                __syncthreads();
+                sb_rows_sync();
                 if (w0) sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
-                __syncthreads();
+                sb_rows_sync();
             }
             isave++;
         };
@@ -1903,10 +1943,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
         if (tend > t) {
             jt = sb_interval(CC.tb, t);
             jt = sb_basis_at(S, CC.tb, t, jt, kp, bs, bdv, lane); // (every warp: identical values into the same words)
-            __syncthreads();
+            sb_rows_sync();
             sb_eval_f<false, SPL>(S, bs, u, f0, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
             sb_eval_dT<SPL>(S, bs, bdv, u, dT, lane, rb);
-            __syncthreads();
+            sb_rows_sync();
             { // automatic initial step (Hairer), order 5 -- sums over rows in the single-warp order
                 double d0 = 0, d1 = 0;
                 if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d0 = u[i0] / sk; d1 = f0[i0] / sk; }
@@ -1916,9 +1956,9 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 dt0 = fmin(dt0, dtmax);
                 if (has) U[i0] = u[i0] + dt0 * f0[i0];
                 sb_basis_at(S, CC.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
-                __syncthreads();
+                sb_rows_sync();
                 sb_eval_f<false, SPL>(S, bs + SB_NB, U, K, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
-                __syncthreads();
+                sb_rows_sync();
                 double d2 = 0;
                 if (has) { const double sk = abstol + fabs(u[i0]) * reltol; d2 = (K[i0] - f0[i0]) / sk; }
                 d2 = sqrt(sb_split_sumsq(d2, xs, rb, lane) / SB_N) / dt0;
@@ -1930,12 +1970,24 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
             bool moved = false;
             double qoldp; // the controller's power of the previous error estimate, carried along (see below)
             { double q0 = ctl.qold; asm volatile("" : "+d"(q0)); qoldp = pow(q0, 2.0 / 25.0); } // (opaque argument: evaluated by the device routine like every later one, not folded at compile time)
+            bool pend = false;  // the controller's answer to the last accepted step is still outstanding (dt holds that step's size meanwhile)
+            double Epend = 0;   // its error estimate
+            int pslot = 0, qslot = -1; // mailbox slot of the pending command's second power; slot from which qoldp is due
+            // the controller's answer: the new step size after an accepted (dt / q) or a rejected step, exactly as SbController computes it
+            auto ctl_resolve = [&](double E, bool rejected, double dtstep) {
+                asm volatile("bar.sync 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
+                if (qslot >= 0) { qoldp = xs[SB_XS_P2 + qslot]; qslot = -1; } // (of the last accepted step before this one: written before the controller warp took this command)
+                const double pw1 = xs[SB_XS_P1];
+                double q = 0.1;
+                if (E != 0.0) { ctl.q11 = pw1; q = fmax(0.1, fmin(5.0, (pw1 / qoldp) / 0.9)); }
+                if (rejected) return ctl.reject(dtstep);
+                qslot = pslot;
+                return ctl.accept(dtstep, q, E);
+            };
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
-                bool last = false;
-                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
                 SB_PROF(0)
-                __syncthreads(); // the previous attempt's readers of bs / the staging area are done; u and slot 0 of the basis (time t) are in place
+                sb_rows_sync(); // the previous attempt's readers of bs / the staging area are done; u and slot 0 of the basis (time t) are in place
                 SB_PROF(1)
                 if (moved) {
                     sb_eval_f<false, SPL>(S, bs, u, f0, lane, nullptr, 0.0, nullptr, nullptr, rb); nf++;
@@ -1943,6 +1995,10 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     moved = false; // (f0, dT are only read on the thread's own row)
                 }
                 SB_PROF(2)
+                if (pend) { dt = ctl_resolve(Epend, false, dt); pend = false; }
+                bool last = false;
+                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
+                SB_PROF(10)
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0.  Meanwhile the other warps set up Z and the
                 // stage-1 right-hand side and bring in the basis at the stage times 2..6 (table rows by TMA, Hermite sweep): none of it is on warp 0's path.
                 sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0 SB_PROF_PASS);
@@ -1956,7 +2012,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     sb_split_basis_sweep(S, kp, bs, xs + SB_XS_BD5, kp + 8, tabs, tpar, lane, warp - 1);
                 }
                 tpar ^= 1u;
-                __syncthreads();
+                sb_rows_sync();
                 jend = reinterpret_cast<const int*>(xs)[1];
                 SB_PROF(3)
                 // the three columns of the first solve: one per warp (with fewer than three warps, warp 0 takes the rest)
@@ -1966,7 +2022,7 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     for (int c = 0; c < 3; c++) if ((c < SB_R ? c : 0) == warp) { double* const z1[1] = {cols[c]}; sb_bsolve<1>(S, z1, di, up, mm, blk, lane); }
                 }
                 nsolve += 3;
-                __syncthreads();
+                sb_rows_sync();
                 SB_PROF(4)
                 double m11, m12, m21, m22;
                 sb_hub_dots(S, bs, Zp, m11, m21, lane);
@@ -1987,14 +2043,17 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                     const bool inc = s >= 6;
                     const int nold = s - 1;
                     double ua = inc ? U[ic] : u[ic], Racc = 0;
+                    // branch-free: all six loads at once, absent terms enter as exact zeros (same bits as skipping them); with a branch per term each
+                    // load waited behind the previous term, and the hub butterfly above could not overlap any of it
+                    double kjv[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) kjv[j] = KC[j * SB_N + ic];
 #pragma unroll
                     for (int j = 0; j < 6; j++) {
-                        if (nold > j) {
-                            const double a_ = cA[s][j], c_ = cC[s][j] * idt;
-                            const double kj = KC[j * SB_N + ic];
-                            if (j < 4 && !inc) ua = fma(a_, kj, ua);
-                            Racc = fma(c_, kj, Racc);
-                        }
+                        const double kj = (nold > j) ? kjv[j] : 0.0;
+                        const double a_ = cA[s][j], c_ = cC[s][j] * idt;
+                        if (j < 4) ua = fma(inc ? 0.0 : a_, kj, ua);
+                        Racc = fma(c_, kj, Racc);
                     }
                     {
                         const double al = cA[s][s - 1], cl = cC[s][s - 1] * idt;
@@ -2003,14 +2062,14 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                         Racc = fma(cl, kp_, Racc);
                         if (has) { KC[(s - 1) * SB_N + i0] = kp_; U[i0] = ua; }
                     }
-                    __syncthreads();
+                    sb_rows_sync();
                     SB_PROF(6)
                     sb_eval_f<true, SPL>(S, bs + cslot[s] * SB_NB, U, ks, lane, &Racc, hd_, dT, nullptr, rb); nf++;
-                    __syncthreads();
+                    sb_rows_sync();
                     SB_PROF(7)
                     if (w0) { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); }
                     nsolve++;
-                    __syncthreads();
+                    sb_rows_sync();
                     SB_PROF(8)
                 }
                 if (w0) for (int i = lane; i < SB_TOPSTORE; i += SB_WARP) blk[i] = 0; // the top block's storage is clean for the next factorisation (its last reader, the solve above, is warp 0 itself)
@@ -2033,22 +2092,15 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                 const double EEst = sqrt(sb_split_sumsq(es, xs, rb, lane) / SB_N);
                 SB_PROF(9)
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (has) mm[i0] = 0; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; } // (0·NaN may sit in structurally-zero slots)
-                // step controller (SbController::q_of): its two powers, EEst^(7/50) and -- for the NEXT attempt's q -- max(EEst, 1e-4)^(2/25), on two warps at once
-                {
-                    double pw = 0;
-                    if (warp == 0) pw = pow(EEst, 7.0 / 50.0);
-                    else if (warp == 1) pw = pow(fmax(EEst, 1e-4), 2.0 / 25.0);
-                    if (lane == 0 && warp < 2) xs[2 + warp] = pw;
-                    __syncthreads();
+                if (EEst > 1) { // rejected: nothing to overlap, the answer is needed at once
+                    nreject++;
+                    pslot = cpar; ctl_send(EEst);
+                    dt = ctl_resolve(EEst, true, dt);
+                    if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; }
+                    continue;
                 }
-                const double pw1 = xs[2], pw2 = xs[3];
-                double q = 0.1;
-                if (EEst != 0.0) { ctl.q11 = pw1; q = fmax(0.1, fmin(5.0, (pw1 / qoldp) / 0.9)); }
-                if (EEst > 1) { nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
-                const double dtnew = ctl.accept(dt, q, EEst);
-                qoldp = pw2;
-                SB_PROF(10)
+                if (!last) { pslot = cpar; ctl_send(EEst); pend = true; Epend = EEst; } // the new step size is picked up after f0, dT of the next attempt
                 const double tn = last ? tend : t + dt;
                 const double un_ = has ? U[i0] + k8 : 0.0;
                 if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order)
@@ -2059,25 +2111,25 @@ __global__ void __launch_bounds__(SB_WARP* SB_R, 1) sb_integrate_split_kernel(co
                         const double th = (ts - t) / dt, t1 = 1 - th;
                         const double v = (ts == tn) ? un_ : sb_dense(th, t1, u[ic], un_, a1, a2, a3);
                         if (has) { if (usave) usave[(size_t)isave * SB_N + sb_nat[i0]] = v; if (SRC) di[i0] = v; }
-                        __syncthreads();
+                        sb_rows_sync();
                         emit(di, ts, true);
                     }
                 }
                 if (has) { if (isnan(un_)) bad = true; }
-                bad = __syncthreads_or(bad);
+                bad = sb_rows_or(bad);
                 if (has) u[i0] = un_;
                 t = tn;
                 if (bad) { rc = SB_RC_UNSTABLE; break; }
                 if (last) break;
                 // the basis at the new time is the one of the last stage time (c = 1): slot 5 -> slot 0, with the derivative kept by the sweep
                 for (int m = tid; m < SB_NB; m += NT) { bs[m] = bs[5 * SB_NB + m]; bdv[m] = xs[SB_XS_BD5 + m]; }
-                dt = dtnew;
                 jt = jend;
                 moved = true;
                 SB_PROF(11)
             }
+            if (pend) { asm volatile("bar.sync 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory"); pend = false; } // (left the loop with an answer outstanding: take it off the barrier)
         }
-        __syncthreads();
+        sb_rows_sync();
         if (has) A.uend[(size_t)mode * SB_N + sb_nat[i0]] = u[i0];
         for (; isave < A.nsave;) { // save times the mode never reached (failed solve)
             if (usave && has) usave[(size_t)isave * SB_N + i0] = NAN;
@@ -2320,7 +2372,7 @@ int sbm_split_capacity(void) { // modes that run concurrently under the split ma
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(sb_integrate_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_split_kernel, SB_WARP * SB_R, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_integrate_split_kernel, SB_SPLIT_THREADS, smem) != cudaSuccess) return 0;
     return nsm * occ;
 #else
     return 0;
@@ -2345,7 +2397,7 @@ int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* 
     if (cap <= 0) return -5;
     const size_t smem = (size_t)(SB_SM_DOUBLES + SB_XS_DOUBLES) * sizeof(double);
     const int grid = std::min(nk, cap);
-    sb_integrate_split_kernel<<<grid, SB_WARP * SB_R, smem, st>>>(A);
+    sb_integrate_split_kernel<<<grid, SB_SPLIT_THREADS, smem, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
 #else
