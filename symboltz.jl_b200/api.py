@@ -455,7 +455,7 @@ class PerturbationSolution:
         return bool((self.retcode == 0).all())
 
 
-def build_schedule(cost, nlists, min_piece=24):
+def build_schedule(cost, nlists, min_piece=24, attempts=None):
     """Static preemptive schedule of independent modes over `nlists` resident warps (McNaughton's wrap-around rule).
 
     The reference spawns one dynamic task per mode (src/solve.jl:566); the kernel's default is the same thing, an atomic queue
@@ -464,9 +464,12 @@ def build_schedule(cost, nlists, min_piece=24):
     (`cost[i]`, any positive estimate) and cut into `nlists` equal chunks of length T = max(Σcost / nlists, max cost).
     A mode that straddles a cut runs its FIRST attempts (the part after the cut) as the first item of the next list, parks,
     and is finished as the LAST item of the previous list, so the two pieces never overlap in time when the estimate is exact.
-    Pieces shorter than `min_piece` attempts are not split off.  Returns (items[nitems, 3] int32 = (mode, quota, cont),
-    ibeg[nlists + 1] int32, T)."""
-    cost = np.maximum(np.asarray(cost, dtype=np.float64), 1.0)
+    Pieces shorter than `min_piece` attempts are not split off.  `attempts` (optional): the modes' attempted steps when `cost` is in
+    other units (e.g. measured time per mode): the quota of a split-off piece is an attempt count, so the cut position is converted
+    with the mode's own attempts per unit of cost.  Returns (items[nitems, 3] int32 = (mode, quota, cont), ibeg[nlists + 1] int32, T)."""
+    cost = np.asarray(cost, dtype=np.float64)
+    apc = np.ones(len(cost)) if attempts is None else np.maximum(np.asarray(attempts, dtype=np.float64), 1.0) / np.maximum(cost, 1e-300)  # attempts per unit of cost
+    cost = np.maximum(cost, 1.0 / apc)
     nk = len(cost)
     order = np.argsort(-cost, kind="stable")
     T = max(cost.sum() / nlists, cost.max()) * (1 + 1e-12)
@@ -481,7 +484,7 @@ def build_schedule(cost, nlists, min_piece=24):
         if end <= cut or w == nlists - 1:
             lists[w].append((m, 0, 0))
         else:
-            p1, p2 = cut - pos, end - cut  # before / after the cut
+            p1, p2 = (cut - pos) * apc[m], (end - cut) * apc[m]  # before / after the cut, in attempts
             if p2 < min_piece:
                 lists[w].append((m, 0, 0))
             elif p1 < min_piece:
@@ -553,7 +556,7 @@ def split_capacity(prob):
 
 
 def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None, sources=None,
-            keep_states=True, split=None):
+            keep_states=True, split=None, cost_attempts=None):
     """Perturbation solve over independent k-modes on the GPU (reference solvept, src/solve.jl:543-569).
     ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527).
     cost: optional per-mode estimate of attempted steps (array or vectorised callable ks -> cost, e.g. a ModeCostModel): run under the static preemptive
@@ -601,7 +604,7 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         cvec = np.asarray(cost(ks) if callable(cost) else cost, dtype=np.float64) * np.ones(nk)
         wpc = int(prob.lib.sbm_warps_per_cta())
         nlists = max(wpc, min(resident_warps(prob), nk) // wpc * wpc)
-        items, ibeg, _ = build_schedule(np.nan_to_num(cvec, nan=1.0), nlists)
+        items, ibeg, _ = build_schedule(np.nan_to_num(cvec, nan=1.0), nlists, attempts=cost_attempts)
         ditems, dibeg = torch.from_numpy(items).to(dev), torch.from_numpy(ibeg).to(dev)
         dcont = torch.empty(nk * int(prob.lib.sbm_cont_stride()), dtype=torch.float64, device=dev)
         dflags = torch.zeros(nk, dtype=torch.int32, device=dev)

@@ -434,6 +434,16 @@ struct SbSolveArgs {
 #ifndef SB_PATH_CONT
 #define SB_PATH_CONT (SB_PL <= 12)
 #endif
+// Stage loop of the warp-per-mode kernel: absent tableau terms as exact zeros instead of (warp-uniform) branches / the loop unrolled (A/B: profiles/integrate_r2.md)
+#ifndef SB_STAGE_BF
+#define SB_STAGE_BF 0
+#endif
+#ifndef SB_STAGE_UNROLL
+#define SB_STAGE_UNROLL 0 // unrolled: +2.5 % attempts/s on a saturated launch WITHOUT save times, but with the 300 save times of the C_l workload the step goes from 57.5 to 84 ms (the source evaluation's code no longer stays in the instruction cache next to a 7x larger stage body); the select form SB_STAGE_BF: -0.2 %
+#endif
+#ifndef SB_SPLIT_UNROLL
+#define SB_SPLIT_UNROLL 0
+#endif
 #ifndef SB_KEEP_MAX
 #define SB_KEEP_MAX 24 // doubles per lane that sb_bsolve may hold across its top step (see KEEP there)
 #endif
@@ -1314,6 +1324,12 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
     __syncwarp();
 }
 
+#ifdef SB_TIME_PROF
+// wall-clock accounting of a scheduled launch (debug builds only: scripts/sched_prof.py): per list (start, end, time spent waiting for a parked mode), per mode (ns over its pieces)
+__device__ unsigned long long sb_tp_list[4096 * 3];
+__device__ unsigned long long sb_tp_mode[8192];
+__device__ __forceinline__ unsigned long long sb_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 // Persistent kernel: one warp per k-mode (SB_WARPS_PER_CTA independent warps per CTA), modes pulled from an atomic work
 // queue in the given order (host sorts by descending k, i.e. descending cost).  FP64 throughout.
 // BATCH: every mode carries its own cosmology (A.cosmos[A.cosmo_of[mode]], staged in shared memory per mode) -- one launch over
@@ -1358,7 +1374,14 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 
     int item = 0, item_end = 0;
     if (A.items) { item = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5)]; item_end = A.ibeg[blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5) + 1]; }
+#ifdef SB_TIME_PROF
+    const unsigned long long tp0 = sb_now(); unsigned long long tpw = 0, tpi = tp0; int tpm = -1;
+#define SB_TP_ITEM if (!GROUP && lane == 0 && tpm >= 0 && tpm < 8192) { const unsigned long long n_ = sb_now(); atomicAdd(&sb_tp_mode[tpm], n_ - tpi); tpi = n_; }
+#else
+#define SB_TP_ITEM
+#endif
     while (true) {
+        SB_TP_ITEM
         // work: either the atomic queue over whole modes, or this warp's static item list.  An item is a mode with an attempt
         // quota (> 0: park the mode after that many attempts and publish a continuation record) or a continuation (cont = 1:
         // wait for the record and integrate to the end).  Parking happens right after an accepted step, where the only live
@@ -1369,6 +1392,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             if (item >= item_end) break;
             mode = A.items[3 * item]; quota = A.items[3 * item + 1]; resume = A.items[3 * item + 2];
             item++;
+#ifdef SB_TIME_PROF
+            tpm = mode; tpi = sb_now();
+#endif
         } else if (GROUP) {
             __syncthreads(); // every lane is done with the previous mode (and with the exchange area)
             if (threadIdx.x == 0) reinterpret_cast<int*>(xch)[0] = atomicAdd(A.queue, 1);
@@ -1382,6 +1408,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             qi = __shfl_sync(SB_FULL, qi, 0);
             if (qi >= A.nk) break;
             mode = A.order ? A.order[qi] : qi;
+#ifdef SB_TIME_PROF
+            tpm = mode; tpi = sb_now();
+#endif
         }
         if (BATCH) {
             __syncwarp();
@@ -1427,6 +1456,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t1 - t0 > 5000000000ull) { f = 3; break; }
                 }
+#ifdef SB_TIME_PROF
+                tpw += sb_now() - t0;
+#endif
             }
             f = __shfl_sync(SB_FULL, f, 0);
             __threadfence();
@@ -1551,6 +1583,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve.  The hub dot products of the
                 // rank-2 correction k_s += Z c and the correction itself are applied lazily in (A) of the next stage: no extra pass, no extra barrier.
                 double c1p = 0, c2p = 0;
+#if SB_STAGE_UNROLL
+#pragma unroll
+#endif
                 for (int s = 0; s < 8; s++) {
                     double* ks = K + s * SB_N;
                     const double hd_ = dt * cd[s];
@@ -1569,6 +1604,19 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                         for (int t = 0; t < SB_TPH; t++) h1 += S.phc[t] * bs[SB_HI16(S.phi[t])] * kprev[SB_LO16(S.phi[t])];
 #pragma unroll
                         for (int t = 0; t < SB_TPS; t++) h2 += S.psc[t] * bs[SB_HI16(S.psi[t])] * kprev[SB_LO16(S.psi[t])];
+#if SB_STAGE_BF
+#define SB_STAGE_TERM(j, WITHU)                                                                                   \
+    {                                                                                                             \
+        const bool on_ = nold > (j);                                                                              \
+        const double a_ = inc ? 0.0 : cA[s][j], c_ = cC[s][j] * idt;                                              \
+        _Pragma("unroll") for (int r = 0; r < SB_R; r++) {                                                        \
+            const double kl = K[(j) * SB_N + ii[r]];                                                              \
+            const double kj = on_ ? kl : 0.0;                                                                     \
+            if (WITHU) ua[r] = fma(a_, kj, ua[r]);                                                                \
+            Racc[r] = fma(c_, kj, Racc[r]);                                                                       \
+        }                                                                                                         \
+    }
+#else
 #define SB_STAGE_TERM(j, WITHU)                                                                                   \
     if (nold > (j)) {                                                                                             \
         const double a_ = cA[s][j], c_ = cC[s][j] * idt;                                                          \
@@ -1578,6 +1626,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             Racc[r] = fma(c_, kj, Racc[r]);                                                                       \
         }                                                                                                         \
     }
+#endif
 #define SB_LEVEL_ISSUE(o) t1 = __shfl_xor_sync(SB_FULL, h1, o); t2 = __shfl_xor_sync(SB_FULL, h2, o);
 #define SB_LEVEL_ADD h1 += t1; h2 += t2;
                         SB_LEVEL_ISSUE(16)
@@ -1739,6 +1788,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
         if (quota > 0 && lane == 0) atomicExch(A.flags + mode, 2);
         __syncwarp();
     }
+#ifdef SB_TIME_PROF
+    if (!GROUP && lane == 0) { const int w_ = blockIdx.x * SB_WARPS_PER_CTA + (threadIdx.x >> 5); if (w_ < 4096) { sb_tp_list[3 * w_] = tp0; sb_tp_list[3 * w_ + 1] = sb_now(); sb_tp_list[3 * w_ + 2] = tpw; } }
+#endif
 }
 
 // ================================================================================================ split kernel
@@ -2033,6 +2085,9 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
                 double c1p = 0, c2p = 0;
                 double* const KC = xs + SB_XS_KC; // k_j with the Woodbury correction applied: every later use is on the thread's own row, so no barrier guards it
                 SB_PROF(5)
+#if SB_SPLIT_UNROLL
+#pragma unroll
+#endif
                 for (int s = 1; s < 8; s++) {
                     double* ks = K + s * SB_N;
                     const double hd_ = dt * cd[s];
@@ -2357,6 +2412,15 @@ int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks
 // The same solve as sbm_solvept_src with ONE CTA of SB_R warps per mode (sb_integrate_split_kernel): for launches that leave most of the GPU
 // idle under the warp-per-mode mapping (fewer modes than sbm_split_capacity()), where the time is the slowest mode's sequential attempts.
 // Bit-identical results.  Returns the grid size, -5 if this model has no split kernel, or a negative error.
+#ifdef SB_TIME_PROF
+int sbm_time_prof(unsigned long long* lists, unsigned long long* modes, int reset) {
+    SB_CUDA_CHECK(cudaDeviceSynchronize());
+    SB_CUDA_CHECK(cudaMemcpyFromSymbol(lists, sb_tp_list, sizeof(sb_tp_list)));
+    SB_CUDA_CHECK(cudaMemcpyFromSymbol(modes, sb_tp_mode, sizeof(sb_tp_mode)));
+    if (reset) { void* p_; SB_CUDA_CHECK(cudaGetSymbolAddress(&p_, sb_tp_list)); SB_CUDA_CHECK(cudaMemset(p_, 0, sizeof(sb_tp_list))); SB_CUDA_CHECK(cudaGetSymbolAddress(&p_, sb_tp_mode)); SB_CUDA_CHECK(cudaMemset(p_, 0, sizeof(sb_tp_mode))); }
+    return 0;
+}
+#endif
 #ifdef SB_SPLIT_PROF
 int sbm_split_prof(unsigned long long* out, int reset) {
     SB_CUDA_CHECK(cudaDeviceSynchronize());
