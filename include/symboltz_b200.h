@@ -144,11 +144,12 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
 int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, double tend_common,
                       void* stream, const sbm_src_t* src);
-/* The single-cosmology solve with ONE CTA of SB_R warps per mode ("one CTA per k-mode") instead of one warp per mode: for launches with no
+/* The single-cosmology solve with ONE CTA per mode ("one CTA per k-mode": SB_R row warps + one warp that computes the step controller's powers) instead of one warp per mode: for launches with no
  * more modes than sbm_split_capacity() (BASELINE config 1: 100 modes; the default 61-node C_l path), where the warp-per-mode mapping leaves
  * most of the GPU idle and the run time is the slowest mode's sequential attempts.  The row-parallel phases of an attempt (basis sweep,
  * Jacobian scatter, f-evaluations, stage combinations, error norm, dense output) are spread over the warps, the first solve's three
- * columns go to three warps, path recurrences and the top block stay on one warp.  Arguments and results as sbm_solvept_src (src may be
+ * columns go to three warps, path recurrences and the top block stay on one warp while the others fetch and sweep the basis of the later stage
+ * times.  8 us instead of 13 us per Rosenbrock attempt on a B200 (profiles/integrate_r2.md).  Arguments and results as sbm_solvept_src (src may be
  * NULL), bit-identical to it.  Returns the grid size, -5 if the model has no split kernel (SB_R outside 2..4), or a negative error.
  * (replaces the same solvept call sites, src/solve.jl:543-569) */
 int sbm_split_capacity(void);

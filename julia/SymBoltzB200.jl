@@ -89,12 +89,22 @@ function SymBoltz.solvept(ptprob, bgsol, ks::AbstractArray, ptivini, ::B200Rodas
             rc = ccall((:sbm_srcbg, lib), Cint, (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}), dP, nb, dt, dy_, ddy, ns, dsave, dsb, st)
             rc == 0 || error("sbm_srcbg failed ($rc)")
         end
-        rc = ccall((:sbm_solvept_src, lib), Cint,
-                   (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, CuPtr{Int32}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64},
-                    CuPtr{Int32}, Cdouble, Cint, CuPtr{Float64}, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, Cint, Ptr{Cvoid}, Ptr{SbmSrc}),
-                   dP, nb, dt, dy_, ddy, msub, length(lut), s0, dsl, dlut, dtab, nk, dks, dtini, dorder, ts[end], ns, dsave, reltol, abstol, maxiters,
-                   CU_NULL, duend, dret, dstats, dqueue, 0, st, (sources && ns > 0) ? src : C_NULL)
-        rc >= 0 || error("sbm_solvept_src failed ($rc)")
+        srcp = (sources && ns > 0) ? src : C_NULL
+        # few modes (config 1, the default 61-node C_l path): one CTA per mode, same results bit for bit, about half the latency
+        if 0 < nk <= ccall((:sbm_split_capacity, lib), Cint, ())
+            rc = ccall((:sbm_solvept_split, lib), Cint,
+                       (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, CuPtr{Int32}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64},
+                        CuPtr{Int32}, Cdouble, Cint, CuPtr{Float64}, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, Ptr{Cvoid}, Ptr{SbmSrc}),
+                       dP, nb, dt, dy_, ddy, msub, length(lut), s0, dsl, dlut, dtab, nk, dks, dtini, dorder, ts[end], ns, dsave, reltol, abstol, maxiters,
+                       CU_NULL, duend, dret, dstats, dqueue, st, srcp)
+        else
+            rc = ccall((:sbm_solvept_src, lib), Cint,
+                       (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, CuPtr{Int32}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64},
+                        CuPtr{Int32}, Cdouble, Cint, CuPtr{Float64}, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, Cint, Ptr{Cvoid}, Ptr{SbmSrc}),
+                       dP, nb, dt, dy_, ddy, msub, length(lut), s0, dsl, dlut, dtab, nk, dks, dtini, dorder, ts[end], ns, dsave, reltol, abstol, maxiters,
+                       CU_NULL, duend, dret, dstats, dqueue, 0, st, srcp)
+        end
+        rc >= 0 || error("sbm_solvept failed ($rc)")
         CUDA.synchronize()
     end
     ret = Array(dret)
