@@ -290,7 +290,7 @@ def main():
 
     extras = {}
     if not args.no_extras:
-        extras = run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl)
+        extras = run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl, model)
 
     if rank == 0:
         value = world * nmodes * args.steps / T_res
@@ -350,7 +350,7 @@ def main():
         dist.destroy_process_group()
 
 
-def run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl):
+def run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl, model=None):
     """Workloads timed beside the headline (same process, after it): each guarded, a failure is reported as text, never fatal."""
     import warnings
     ex = {}
@@ -407,16 +407,22 @@ def run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl):
                 warnings.simplefilter("ignore")
                 bg0 = sb.solvebg(prob0)
                 jl0 = jl if rank == 0 else sb.SphericalBesselCache(LS, xcut=2e3 * bg0.tau0 * 1.02)
-                sb.spectrum_cmb(list(MODES), prob0, jl0, bgsol=bg0, direct=True)
+                # work distribution inside a rank (chosen by solvept): with no more modes than the split mapping holds, one CTA per mode; above that the
+                # atomic queue over the resident warps (with ~1000 modes per rank every mode has a warp of its own: a static schedule has nothing to
+                # balance and measured 47.0 instead of 44.8 ms at N = 2, profiles/scaling_r2.md)
+                nk_rank = -(-len(sb.cmb_grids(bg0)[0]) // world)
+                sched = {}
+                sb.spectrum_cmb(list(MODES), prob0, jl0, bgsol=bg0, direct=True, **sched)
                 ts = []
                 for _ in range(3):
                     sync()
                     t0 = time.perf_counter()
-                    sb.spectrum_cmb(list(MODES), prob0, jl0, bgsol=bg0, direct=True)
+                    sb.spectrum_cmb(list(MODES), prob0, jl0, bgsol=bg0, direct=True, **sched)
                     torch.cuda.synchronize()
                     ts.append(maxtime(time.perf_counter() - t0))
             ex["strong_single_cosmology"] = {"workload": "the headline cosmology's C_l with its ~2020 modes strided over the ranks: NCCL all-reduce (disjoint supports = all-gather) of S[nk][2][300] (9.7 MB), LOS on contiguous fine-k slices, NCCL all-reduce of the partial C_l sums [3][129]",
-                                             "ms": 1e3 * float(np.median(ts)), "ranks": world, "limiter": "latency of the slowest mode (its sequential Rosenbrock attempts), not the collectives"}
+                                             "ms": 1e3 * float(np.median(ts)), "ranks": world, "modes_per_rank": nk_rank, "work_distribution": ("one CTA per mode (split kernel)" if nk_rank <= sb.split_capacity(prob0) else "atomic queue, one warp per mode"),
+                                             "limiter": "latency of the slowest mode (its sequential Rosenbrock attempts), not the collectives"}
         except Exception as e:
             ex["strong_single_cosmology"] = {"error": repr(e)}
     # (4) BASELINE configs[3]: w0waCDM sweep sharded by cosmology, NCCL gather of P(k)
