@@ -1324,6 +1324,14 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
     __syncwarp();
 }
 
+// Initial state of a mode (generated closed-form initial conditions on the background at τini).  One compiled copy for every integrator kernel: inlined,
+// the several hundred generated expressions were contracted into FMAs differently in different kernels (nx = 8: two unknowns off by an ulp between the
+// warp-per-mode and the split kernel), and results must not depend on which kernel runs a mode.
+__device__ __noinline__ void sb_initial_state(const SbSpline& spl, const double* P, double t, double k, double* U) {
+    double y[5];
+    sb_spl_eval(spl, t, y, nullptr);
+    sb_initial(t, k, y, P, U);
+}
 #ifdef SB_TIME_PROF
 // wall-clock accounting of a scheduled launch (debug builds only: scripts/sched_prof.py): per list (start, end, time spent waiting for a parked mode), per mode (ns over its pieces)
 __device__ unsigned long long sb_tp_list[4096 * 3];
@@ -1476,7 +1484,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             naccept = (long long)__ldcg(c + SB_N + 7); nreject = (long long)__ldcg(c + SB_N + 8); nf = (long long)__ldcg(c + SB_N + 9); nsolve = (long long)__ldcg(c + SB_N + 10);
             __syncwarp();
         } else {
-        if (lane == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
+        if (lane == 0) sb_initial_state(CC.spl, CC.P, t, k, U); // natural order
         __syncwarp();
         for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]]; // -> the integrator's path-contiguous order
         __syncwarp();
@@ -1943,7 +1951,7 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
         SbController ctl; ctl.init();
         double dt = 0;
         int jt = 0;
-        if (tid == 0) { double y[5]; sb_spl_eval(CC.spl, t, y, nullptr); sb_initial(t, k, y, CC.P, U); } // natural order
+        if (tid == 0) sb_initial_state(CC.spl, CC.P, t, k, U); // natural order
         if (has) mm[i0] = 0; // multiplier slots: cleared once per mode (and after a non-finite attempt), see sb_factor
         for (int i = tid; i < SB_TOPSTORE; i += NT) blk[i] = 0;
         sb_rows_sync();

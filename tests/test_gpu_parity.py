@@ -714,9 +714,10 @@ def test_matter_spectrum_converged_to_a_permille(sb, prob5):
 def test_split_kernel_is_bit_identical(sb, prob5, bg5):
     """`sbm_solvept_split` (one CTA of SB_R warps per mode, chosen automatically for launches that fit the GPU once) against the warp-per-mode
     kernel: final states, dense output, fused sources (2 and 3), step counters and return codes bit for bit -- including a failing k = 0
-    mode, a mode that hits maxiters, save times before the start, and both models the tests use (N = 47: 2 warps per mode; N = 82: 3)."""
+    mode, a mode that hits maxiters, save times before the start, for 2, 3 and 4 row warps per mode (N = 47; N = 82 and the w0waCDM model of config 4,
+    N = 84; nx = 8, N = 126), each plus the controller warp."""
     import warnings
-    for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10)):
+    for M in (sb.ΛCDM(lmax=5), sb.ΛCDM(lmax=10), sb.w0waCDM(lmax=10), sb.ΛCDM(lmax=10, nx=8)):
         prob = prob5 if M.lmax == 5 else sb.CosmologyProblem(M, sb.parameters_Planck18(M))
         bg = bg5 if M.lmax == 5 else sb.solvebg(prob)
         assert sb.split_capacity(prob) >= 148
