@@ -157,6 +157,16 @@ int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* 
                       const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
                       double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
                       const sbm_src_t* src);
+/* The single-cosmology solve with TRBDF2 instead of Rodas5P: the reference's `ptalg(prob; accuracy = 0)` (src/solve.jl:333-335; solvept's `alg`
+ * option, src/solve.jl:543).  Published scheme (Bank et al. 1985, Hosea & Shampine 1996): trapezoidal stage to t + (2 - sqrt 2) dt, BDF2 stage to t + dt,
+ * each ONE linear solve with J at the stage time (the system is linear in u), third-order companion error estimate filtered through the last stage's
+ * matrix, Gustafsson's predictive step controller, cubic-Hermite dense output; OrdinaryDiffEq.jl's own step selection is not pinned (dependency absent).
+ * Arguments and results as sbm_solvept_src (src may be NULL; stats[3] counts linear solves).  One warp per mode, atomic queue.  Returns the grid size
+ * or a negative error. */
+int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                       const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                       double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
+                       const sbm_src_t* src);
 /* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
  * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
  * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */

@@ -450,6 +450,89 @@ struct Controller { // PI controller, OrdinaryDiffEq defaults for an order-5 ada
     double reject(double dt) { return dt / std::min(1 / qmin, q11 / gamma); }
 };
 
+// TRBDF2 (Bank et al. 1985; Hosea & Shampine 1996): the reference's `ptalg(prob; accuracy = 0)` (src/solve.jl:333-335) hands the perturbations to
+// OrdinaryDiffEq.jl's TRBDF2 with NLNewton(κ = 1).  OrdinaryDiffEq is an un-vendored dependency (absent from /root/reference) and there is no Julia
+// here, so this restates the PUBLISHED scheme -- PARITY UNPINNED against Julia's step selection.  The system is linear in u, so each implicit stage is
+// solved exactly as one linear system with J at the stage time (a converged Newton iteration), not with a frozen, reused W.
+//   γ = 2 − √2, d = γ/2, ω = √2/4;  stage 2 (trapezoidal rule to t + γ dt):  (I − d dt J_γ) u_γ = u_n + d dt f_n
+//   stage 3 (BDF2 to t + dt):  (I − d dt J_1) u_{n+1} = u_γ/(γ(2−γ)) − (1−γ)² u_n/(γ(2−γ));   f of a stage follows from its own equation (FSAL)
+//   error estimate: dt Σ (b_i − b̂_i) f_i with the third-order companion b̂ = ((1−ω)/3, (3ω+1)/3, d/3), filtered through (I − d dt J_1)^{-1}
+//   dense output: cubic Hermite on (u_n, f_n, u_{n+1}, f_{n+1}).
+template <class Sys> struct TRBDF2 {
+    Sys& sys; int n;
+    std::vector<double> W, Wp, f0, fg, f1, ug, unew, est, tmp, rhs;
+    std::vector<int> perm;
+    SparseLU lu;
+    Stats st;
+    bool have_f0 = false;
+    explicit TRBDF2(Sys& s) : sys(s), n(s.n), W(n * n), Wp(n * n), f0(n), fg(n), f1(n), ug(n), unew(n), est(n), tmp(n), rhs(n), perm(n) {
+        for (int i = 0; i < n; i++) perm[i] = i;
+        sys.ordering(perm.data());
+    }
+    void solve_inplace(double* b) {
+        for (int i = 0; i < n; i++) tmp[i] = b[perm[i]];
+        lu.solve(tmp.data());
+        for (int i = 0; i < n; i++) b[perm[i]] = tmp[i];
+    }
+    bool factor(double ts, const double* u, double x) { // x I − J(ts), symmetrically permuted
+        sys.jac(ts, u, W.data()); st.njac++;
+        for (int i = 0; i < n; i++) { const double* Wi = &W[(size_t)perm[i] * n]; double* Pi = &Wp[(size_t)i * n]; for (int j = 0; j < n; j++) Pi[j] = -Wi[perm[j]]; Pi[i] += x; }
+        return lu.factor(n, Wp.data());
+    }
+    bool step(double t, const double* u, double dt) {
+        const double g = 2 - std::sqrt(2.0), d = g / 2, w = std::sqrt(2.0) / 4, x = 1 / (d * dt);
+        const double a = 1 / (g * (2 - g)), b = (1 - g) * (1 - g) / (g * (2 - g));
+        if (!have_f0) { sys.f(t, u, f0.data()); st.nf++; have_f0 = true; }
+        if (!factor(t + g * dt, u, x)) return false;
+        for (int i = 0; i < n; i++) ug[i] = x * u[i] + f0[i];
+        solve_inplace(ug.data());
+        for (int i = 0; i < n; i++) fg[i] = x * (ug[i] - u[i]) - f0[i];
+        if (!factor(t + dt, u, x)) return false;
+        for (int i = 0; i < n; i++) { rhs[i] = a * ug[i] - b * u[i]; unew[i] = x * rhs[i]; }
+        solve_inplace(unew.data());
+        for (int i = 0; i < n; i++) f1[i] = x * (unew[i] - rhs[i]);
+        const double e1 = (4 * w - 1) / 3, e2 = -1.0 / 3, e3 = 2 * d / 3;
+        for (int i = 0; i < n; i++) est[i] = x * (dt * (e1 * f0[i] + e2 * fg[i] + e3 * f1[i]));
+        solve_inplace(est.data());
+        return true;
+    }
+    void accept() { f0 = f1; } // first-same-as-last
+    double errnorm(const double* u, double abstol, double reltol) const {
+        double s = 0;
+        for (int i = 0; i < n; i++) { double sc = abstol + reltol * std::max(std::fabs(u[i]), std::fabs(unew[i])); double r = est[i] / sc; s += r * r; }
+        return std::sqrt(s / n);
+    }
+    void interp(const double* u0, double th, double dt, double* out) const {
+        for (int i = 0; i < n; i++) {
+            const double du = unew[i] - u0[i];
+            out[i] = (1 - th) * u0[i] + th * unew[i] + th * (th - 1) * ((1 - 2 * th) * du + (th - 1) * dt * f0[i] + th * dt * f1[i]);
+        }
+    }
+};
+// Step-size control of the implicit methods: Gustafsson's predictive controller in the form OrdinaryDiffEq uses for its Newton-based methods
+// (restated from the published controller, same caveat as above); exponent 1/3 for TRBDF2's O(dt³) estimate, one "Newton iteration" per stage.
+struct PredictiveController {
+    double gamma = 0.9, qmin = 0.2, qmax = 10, qsteady_min = 1, qsteady_max = 1.2, expo = 1.0 / 3;
+    double qold = 1, dtacc = 0, erracc = 0; long success_iter = 0;
+    double q_of(double EEst) {
+        if (EEst == 0) return qold = 1 / qmax;
+        return qold = std::max(1 / qmax, std::min(1 / qmin, std::pow(EEst, expo) / gamma));
+    }
+    double accept(double dt, double q, double EEst) {
+        double qacc = q;
+        if (success_iter > 0) {
+            double qgus = (dtacc / dt) * std::pow(EEst * EEst / erracc, expo);
+            qgus = std::max(1 / qmax, std::min(1 / qmin, qgus / gamma));
+            qacc = std::max(q, qgus);
+        }
+        if (qsteady_min <= qacc && qacc <= qsteady_max) qacc = 1;
+        success_iter++;
+        dtacc = dt; erracc = std::max(1e-2, EEst);
+        return dt / qacc;
+    }
+    double reject(double dt) { return success_iter == 0 ? 0.1 * dt : dt / qold; }
+};
+
 // ------------------------------------------------------------------ background system and solve
 struct BgSys {
     const Derived& D; int n = 5;
@@ -730,8 +813,12 @@ struct PtSys {
 };
 
 // Solve one mode. saveat may be empty (then only the final state is returned in uend).
+// the same driver for TRBDF2 (see the struct): initial step as for Rodas5P with the method's order
+static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
+                             long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats);
 static int solve_mode(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
-                      long maxiters, int nsave, const double* saveat, double* usave /*nsave×N*/, double* uend /*N*/, long* stats /*4*/) {
+                      long maxiters, int nsave, const double* saveat, double* usave /*nsave×N*/, double* uend /*N*/, long* stats /*4*/, int alg = 0) {
+    if (alg == 1) return solve_mode_trbdf2(D, spl, k, tini, tend, reltol, abstol, maxiters, nsave, saveat, usave, uend, stats);
     PtSys sys(D, spl, k);
     int n = sys.n;
     Rodas5P<PtSys> R(sys);
@@ -764,6 +851,69 @@ static int solve_mode(const Derived& D, const Spline& spl, double k, double tini
                 isave++;
             }
             t = tn; u = R.unew;
+            bool bad = false; for (int i = 0; i < n; i++) if (std::isnan(u[i])) bad = true;
+            if (bad) { rc = RC_UNSTABLE; break; }
+            if (last) break;
+            dt = dtnew;
+        }
+    }
+    std::copy(u.begin(), u.end(), uend);
+    for (; isave < nsave; isave++) for (int i = 0; i < n; i++) usave[(long)isave * n + i] = NAN;
+    if (stats) { stats[0] = R.st.naccept; stats[1] = R.st.nreject; stats[2] = R.st.nf; stats[3] = R.st.njac; }
+    return rc;
+}
+
+static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
+                             long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats) {
+    PtSys sys(D, spl, k);
+    int n = sys.n;
+    TRBDF2<PtSys> R(sys);
+    PredictiveController ctl;
+    std::vector<double> u(n);
+    int rc = RC_SUCCESS, isave = 0;
+    if (!(k > 0) || !std::isfinite(k)) { for (int i = 0; i < n; i++) uend[i] = NAN; for (long i = 0; i < (long)nsave * n; i++) usave[i] = NAN; if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0; return RC_UNSTABLE; }
+    pt_initial(D, spl, tini, k, u.data());
+    double t = tini;
+    while (isave < nsave && saveat[isave] <= t) { if (saveat[isave] == t) std::copy(u.begin(), u.end(), usave + (long)isave * n); else for (int i = 0; i < n; i++) usave[(long)isave * n + i] = NAN; isave++; }
+    if (tend > tini) {
+        double dt;
+        { // Hairer's initial step with the method's order (2): same recipe as Rodas5P::initdt, exponent 1/(order + 1)
+            std::vector<double> sk(n), fa(n), fb(n), u1(n);
+            sys.f(t, u.data(), fa.data()); R.st.nf++;
+            double d0 = 0, d1 = 0;
+            for (int i = 0; i < n; i++) { sk[i] = abstol + std::fabs(u[i]) * reltol; d0 += (u[i] / sk[i]) * (u[i] / sk[i]); d1 += (fa[i] / sk[i]) * (fa[i] / sk[i]); }
+            d0 = std::sqrt(d0 / n); d1 = std::sqrt(d1 / n);
+            double dtmax = tend - t;
+            double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            dt0 = std::min(dt0, dtmax);
+            for (int i = 0; i < n; i++) u1[i] = u[i] + dt0 * fa[i];
+            sys.f(t + dt0, u1.data(), fb.data()); R.st.nf++;
+            double d2 = 0;
+            for (int i = 0; i < n; i++) { double r = (fb[i] - fa[i]) / sk[i]; d2 += r * r; }
+            d2 = std::sqrt(d2 / n) / dt0;
+            double dm = std::max(d1, d2);
+            double dt1 = (dm <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2 + std::log10(dm)) / 3.0);
+            dt = std::min(std::min(100 * dt0, dt1), dtmax);
+        }
+        for (long it = 0;; it++) {
+            if (it >= maxiters) { rc = RC_MAXITERS; break; }
+            bool last = false;
+            if (t + dt >= tend - 100 * 2.2e-16 * std::fabs(tend)) { dt = tend - t; last = true; }
+            if (!R.step(t, u.data(), dt)) { rc = RC_UNSTABLE; break; }
+            double EEst = R.errnorm(u.data(), abstol, reltol);
+            if (!std::isfinite(EEst)) { R.st.nreject++; dt /= 5; if (dt < 1e-15 * std::fabs(t)) { rc = RC_UNSTABLE; break; } continue; }
+            double q = ctl.q_of(EEst);
+            if (EEst > 1) { R.st.nreject++; dt = ctl.reject(dt); if (dt < 1e-15 * std::fabs(t)) { rc = RC_DTMIN; break; } continue; }
+            R.st.naccept++;
+            double dtnew = ctl.accept(dt, q, EEst);
+            double tn = last ? tend : t + dt;
+            while (isave < nsave && saveat[isave] <= tn) {
+                double* out = usave + (long)isave * n;
+                if (saveat[isave] == tn) std::copy(R.unew.begin(), R.unew.end(), out);
+                else R.interp(u.data(), (saveat[isave] - t) / dt, dt, out);
+                isave++;
+            }
+            t = tn; u = R.unew; R.accept();
             bool bad = false; for (int i = 0; i < n; i++) if (std::isnan(u[i])) bad = true;
             if (bad) { rc = RC_UNSTABLE; break; }
             if (last) break;
@@ -896,6 +1046,28 @@ void sbo_solvept(const SboParams* p, int nb, const double* t, const double* y, c
         std::vector<double> dummy((size_t)std::max(1, nsave) * N);
         double* us = usave ? usave + (size_t)i * nsave * N : dummy.data();
         retcode[i] = solve_mode(D, spl, ks[i], tini[i], tau0, reltol, abstol, maxiters, nsave, saveat, us, uend + (size_t)i * N, stats ? stats + 4 * i : nullptr);
+    }
+}
+
+// sbo_solvept with a choice of integrator: alg 0 = Rodas5P (the reference's default, ptalg accuracy = 2), 1 = TRBDF2 (accuracy = 0)
+void sbo_solvept_alg(const SboParams* p, int nb, const double* t, const double* y, const double* dy, double tau0, double kappa0,
+                     int nk, const double* ks, const double* tini, int nsave, const double* saveat, double reltol, double abstol, long maxiters,
+                     int nthreads, double* usave, double* uend, int* retcode, long* stats, int alg) {
+    Derived D; derive(*p, D); D.tau0 = tau0; D.kappa0 = kappa0;
+    Spline spl{nb, t, y, dy};
+    int N = D.N;
+    std::vector<int> order(nk);
+    for (int i = 0; i < nk; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return ks[a] > ks[b]; });
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int j = 0; j < nk; j++) {
+        int i = order[j];
+        std::vector<double> dummy((size_t)std::max(1, nsave) * N);
+        double* us = usave ? usave + (size_t)i * nsave * N : dummy.data();
+        retcode[i] = solve_mode(D, spl, ks[i], tini[i], tau0, reltol, abstol, maxiters, nsave, saveat, us, uend + (size_t)i * N, stats ? stats + 4 * i : nullptr, alg);
     }
 }
 

@@ -556,7 +556,7 @@ def split_capacity(prob):
 
 
 def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat=None, maxiters=100000, msub=16, nctas=0, warn=True, sync=True, trace=0, cost=None, sources=None,
-            keep_states=True, split=None, cost_attempts=None):
+            keep_states=True, split=None, cost_attempts=None, alg="Rodas5P"):
     """Perturbation solve over independent k-modes on the GPU (reference solvept, src/solve.jl:543-569).
     ks in H0/c.  ptivini: number or callable k -> τini (clamped to the background span, src/solve.jl:527).
     cost: optional per-mode estimate of attempted steps (array or vectorised callable ks -> cost, e.g. a ModeCostModel): run under the static preemptive
@@ -566,7 +566,9 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     states never leave the SM (sol.d_usave is None).
     split: None (default) = choose the mapping by the size of the launch: with no more modes than `split_capacity(prob)` (296 on a B200 for
     the nx = 4 models) every mode gets a CTA of SB_R warps (`sbm_solvept_split`: the row-parallel phases of an attempt are spread over the
-    warps; ≈25 % lower latency, bit-identical results), otherwise one warp per mode; True / False force one or the other."""
+    warps; ≈40 % lower latency, bit-identical results), otherwise one warp per mode; True / False force one or the other.
+    alg: "Rodas5P" (the reference's default, `ptalg(prob; accuracy = 2)`) or "TRBDF2" (`accuracy = 0`, src/solve.jl:333-335: second order, three linear
+    solves and no f-evaluation per step; the published scheme -- OrdinaryDiffEq.jl's own step selection cannot be pinned here; one warp per mode, queue only)."""
     _require_cuda()
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
     nk = len(ks)
@@ -600,7 +602,15 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         dsave, usave, ns = None, None, 0
     srcp = C.byref(src) if src is not None else None
     dtrace = torch.zeros((trace, 3), dtype=torch.float64, device=dev) if trace else None  # debug: (t, dt, EEst) of mode 0
-    if cost is not None and nk > 0:
+    if alg not in ("Rodas5P", "TRBDF2"):
+        raise ValueError(f"unknown perturbation integrator {alg!r}: Rodas5P or TRBDF2 (KenCarp4 is not built)")
+    if alg == "TRBDF2":
+        if cost is not None or trace or nctas or split is True:
+            raise ValueError("TRBDF2 runs one warp per mode from the atomic queue: no cost=, trace=, nctas= or split=True")
+        rc = prob.lib.sbm_solvept_trbdf2(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+                                         C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
+                                         _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _stream(), srcp)
+    elif cost is not None and nk > 0:
         cvec = np.asarray(cost(ks) if callable(cost) else cost, dtype=np.float64) * np.ones(nk)
         wpc = int(prob.lib.sbm_warps_per_cta())
         nlists = max(wpc, min(resident_warps(prob), nk) // wpc * wpc)

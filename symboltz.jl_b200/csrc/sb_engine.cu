@@ -2206,6 +2206,196 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
 #define SB_HAVE_SPLIT 0
 #endif
 
+// ================================================================================================ TRBDF2
+// The reference's `ptalg(prob; accuracy = 0)` (src/solve.jl:333-335) integrates the perturbations with OrdinaryDiffEq.jl's TRBDF2 instead of Rodas5P.
+// OrdinaryDiffEq is an un-vendored dependency and there is no Julia here, so this is the PUBLISHED scheme (Bank et al. 1985, Hosea & Shampine 1996)
+// on this engine's linear algebra -- parity with Julia's step selection is unpinned; the oracle carries the same restatement (oracle/sbref.cpp, TRBDF2).
+// The system is linear in u: each implicit stage is ONE linear solve with J at the stage time (a converged Newton iteration), W = I/(d dt) − J = B − pφᵀ − qψᵀ.
+//   γ = 2 − √2, d = γ/2, ω = √2/4, x = 1/(d dt)
+//   stage 2 (trapezoidal rule to t + γ dt):  (x − J_γ) u_γ = x u_n + f_n,            f_γ = x (u_γ − u_n) − f_n
+//   stage 3 (BDF2 to t + dt):                (x − J_1) u_1 = x r,  r = a u_γ − b u_n,  f_1 = x (u_1 − r)   (first-same-as-last: no f-evaluation per step)
+//   error estimate: (x − J_1)^{-1} x dt Σ (b_i − b̂_i) f_i, third-order companion b̂ = ((1−ω)/3, (3ω+1)/3, d/3); Gustafsson's predictive controller
+//   dense output / save points: cubic Hermite on (u_n, f_n, u_1, f_1); sources at the save times as in sb_integrate_kernel.
+// One warp per mode, atomic queue, same shared-memory layout as sb_integrate_kernel (K holds f_n, f_γ, f_1, r, the estimate and u_1).
+__global__ void __launch_bounds__(SB_WARP, 4) sb_trbdf2_kernel(const __grid_constant__ SbSolveArgs A) {
+    extern __shared__ __align__(16) double sm_all[];
+    const int lane = threadIdx.x & 31;
+    double* const sm = sm_all;
+    double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP, *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ,
+           *bs = sm + SB_SM_BS, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
+    double* const sbuf = sm + SB_SM_SBUF;
+    double *f0 = K, *fg = K + SB_N, *f1 = K + 2 * SB_N, *rv = K + 3 * SB_N, *ev = K + 4 * SB_N, *un = K + 5 * SB_N;
+    const double reltol = A.reltol, abstol = A.abstol;
+    const bool SRC = A.S != nullptr;
+    SbLane S;
+    S.load(lane);
+    const SbCosmo& CC = A.c0;
+    const double G = 2.0 - 1.4142135623730951, D = 0.5 * G, OM = 0.25 * 1.4142135623730951;
+    const double BA = 1.0 / (G * (2 - G)), BB = (1 - G) * (1 - G) / (G * (2 - G));
+    const double E1 = (4 * OM - 1) / 3, E2 = -1.0 / 3, E3 = 2 * D / 3;
+    while (true) {
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(A.queue, 1);
+        qi = __shfl_sync(SB_FULL, qi, 0);
+        if (qi >= A.nk) break;
+        const int mode = A.order ? A.order[qi] : qi;
+        const double k = A.ks[mode];
+        double t = A.tini[mode];
+        const double tend = CC.tend;
+        long long naccept = 0, nreject = 0, nf = 0, nsolve = 0;
+        int rc = SB_RC_SUCCESS, isave = 0, wstart = 0;
+        double* usave = A.usave ? A.usave + (size_t)mode * A.nsave * SB_N : nullptr;
+        double* Sout = SRC ? A.S + (size_t)mode * A.nS * A.nsave : nullptr;
+        __syncwarp();
+        if (!(k > 0) || !isfinite(k)) {
+            for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + i] = NAN;
+            if (usave) for (int i = lane; i < A.nsave * SB_N; i += SB_WARP) usave[i] = NAN;
+            if (SRC) for (int i = lane; i < A.nsave * A.nS; i += SB_WARP) Sout[i] = NAN;
+            if (lane == 0) { A.retcode[mode] = SB_RC_UNSTABLE; for (int j = 0; j < 4; j++) A.stats[4 * mode + j] = 0; }
+            continue;
+        }
+        if (lane < 7) kp[lane] = pow(k, (double)(lane - 3));
+        if (lane == 0) sb_initial_state(CC.spl, CC.P, t, k, U);
+        __syncwarp();
+        for (int i = lane; i < SB_N; i += SB_WARP) u[i] = U[sb_nat[i]];
+        __syncwarp();
+        // one save point from the state `st` (shared memory, integrator order)
+        auto emit = [&](const double* st, double ts, bool valid) {
+            if (SRC) {
+                double* so = sbuf + (isave & (SB_SWIN - 1));
+                if (valid) sb_source_point(S, CC.srcbg + (size_t)isave * SB_SRCBG_STRIDE, kp, k, ts, CC.taurec, A.scale_k, A.nS, st, up, bs, bs + SB_NB, so, SB_SWIN, lane);
+                else if (lane < A.nS) so[lane * SB_SWIN] = NAN;
+                sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave, wstart, false, lane);
+            }
+            isave++;
+        };
+        while (isave < A.nsave && CC.saveat[isave] <= t) {
+            const bool at = CC.saveat[isave] == t;
+            if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + sb_nat[i]] = at ? u[i] : NAN;
+            emit(u, t, at);
+        }
+        if (tend > t) {
+            int jt = sb_interval(CC.tb, t);
+            jt = sb_basis_at(S, CC.tb, t, jt, kp, bs, nullptr, lane);
+            __syncwarp();
+            sb_eval_f<false>(S, bs, u, f0, lane); nf++;
+            double dt;
+            { // automatic initial step (Hairer) with the method's order 2
+                double d0 = 0, d1 = 0;
+                for (int i = lane; i < SB_N; i += SB_WARP) { const double sk = abstol + fabs(u[i]) * reltol; const double a0 = u[i] / sk, a1 = f0[i] / sk; d0 = fma(a0, a0, d0); d1 = fma(a1, a1, d1); }
+                d0 = sqrt(warp_sum(d0) / SB_N); d1 = sqrt(warp_sum(d1) / SB_N);
+                const double dtmax = tend - t;
+                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                dt0 = fmin(dt0, dtmax);
+                for (int i = lane; i < SB_N; i += SB_WARP) U[i] = u[i] + dt0 * f0[i];
+                sb_basis_at(S, CC.tb, t + dt0, jt, kp, bs + SB_NB, nullptr, lane);
+                __syncwarp();
+                sb_eval_f<false>(S, bs + SB_NB, U, fg, lane); nf++;
+                double d2 = 0;
+                for (int i = lane; i < SB_N; i += SB_WARP) { const double sk = abstol + fabs(u[i]) * reltol; const double r = (fg[i] - f0[i]) / sk; d2 = fma(r, r, d2); }
+                d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
+                const double dm = fmax(d1, d2);
+                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 3.0);
+                dt = fmin(fmin(100 * dt0, dt1), dtmax);
+                __syncwarp();
+            }
+            double qold = 1, dtacc = 0, erracc = 0; long long success_iter = 0; // Gustafsson's predictive controller (oracle: PredictiveController)
+            double m11 = 0, m12 = 0, m21 = 0, m22 = 0, idet = 0;
+            // factor x − J(ts) with the basis of time ts left in slot 0, and the Woodbury data (Z = B^{-1}[p q], 2×2 inverse); solves r in place
+            auto factor_solve = [&](double ts, double x, int jh, double* r) {
+                const int j = sb_basis_at(S, CC.tb, ts, jh, kp, bs, nullptr, lane);
+                __syncwarp();
+                sb_factor(S, x, bs, di, up, mm, blk, lane);
+#pragma unroll
+                for (int rr = 0; rr < SB_R; rr++) {
+                    const int i = rr * 32 + lane;
+                    if (i < SB_N) { Zp[i] = S.pqc[2 * rr] * bs[SB_LO16(S.pqi[rr])]; Zq[i] = S.pqc[2 * rr + 1] * bs[SB_HI16(S.pqi[rr])]; }
+                }
+                __syncwarp();
+                { double* const zz[3] = {Zp, Zq, r}; sb_bsolve<3>(S, zz, di, up, mm, blk, lane); }
+                nsolve += 3;
+                sb_hub_dots(S, bs, Zp, m11, m21, lane);
+                sb_hub_dots(S, bs, Zq, m12, m22, lane);
+                m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
+                idet = sb_rcp(m11 * m22 - m12 * m21);
+                return j;
+            };
+            auto woodbury = [&](double* r) { // r += Z M^{-1} [φᵀr; ψᵀr]
+                double h1, h2;
+                sb_hub_dots(S, bs, r, h1, h2, lane);
+                const double c1 = (m22 * h1 - m12 * h2) * idet, c2 = (-m21 * h1 + m11 * h2) * idet;
+                __syncwarp();
+                for (int i = lane; i < SB_N; i += SB_WARP) r[i] = sb_wcorr(r[i], Zp[i], c1, Zq[i], c2);
+                __syncwarp();
+            };
+            for (int it = 0;; it++) {
+                if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
+                bool last = false;
+                if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
+                const double x = 1.0 / (D * dt);
+                for (int i = lane; i < SB_N; i += SB_WARP) U[i] = fma(x, u[i], f0[i]);
+                __syncwarp();
+                const int jg = factor_solve(t + G * dt, x, jt, U);
+                woodbury(U);
+                for (int i = lane; i < SB_N; i += SB_WARP) { fg[i] = x * (U[i] - u[i]) - f0[i]; const double r = BA * U[i] - BB * u[i]; rv[i] = r; un[i] = x * r; }
+                __syncwarp();
+                const int jn = factor_solve(last ? tend : t + dt, x, jg, un);
+                woodbury(un);
+                for (int i = lane; i < SB_N; i += SB_WARP) { const double f = x * (un[i] - rv[i]); f1[i] = f; ev[i] = x * (dt * (E1 * f0[i] + E2 * fg[i] + E3 * f)); }
+                __syncwarp();
+                { double* const e1[1] = {ev}; sb_bsolve<1>(S, e1, di, up, mm, blk, lane); } nsolve++;
+                woodbury(ev);
+                double es = 0; bool bad = false;
+                for (int i = lane; i < SB_N; i += SB_WARP) { const double r = ev[i] * sb_rcp(abstol + reltol * fmax(fabs(u[i]), fabs(un[i]))); es = fma(r, r, es); }
+                const double EEst = sqrt(warp_sum(es) / SB_N);
+                if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
+                const double q = qold = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, pow(EEst, 1.0 / 3) / 0.9));
+                if (EEst > 1) { nreject++; dt = (success_iter == 0) ? 0.1 * dt : dt / qold; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                naccept++;
+                double qacc = q;
+                if (success_iter > 0) {
+                    double qgus = (dtacc / dt) * pow(EEst * EEst / erracc, 1.0 / 3);
+                    qgus = fmax(0.1, fmin(5.0, qgus / 0.9));
+                    qacc = fmax(q, qgus);
+                }
+                if (1.0 <= qacc && qacc <= 1.2) qacc = 1;
+                success_iter++;
+                dtacc = dt; erracc = fmax(1e-2, EEst);
+                const double dtnew = dt / qacc;
+                const double tn = last ? tend : t + dt;
+                while (isave < A.nsave && CC.saveat[isave] <= tn) { // cubic Hermite on (u_n, f_n, u_1, f_1)
+                    const double ts = CC.saveat[isave];
+                    const double th = (ts - t) / dt;
+                    const bool atend = ts == tn;
+                    for (int i = lane; i < SB_N; i += SB_WARP) {
+                        const double du = un[i] - u[i];
+                        const double v = atend ? un[i] : (1 - th) * u[i] + th * un[i] + th * (th - 1) * ((1 - 2 * th) * du + (th - 1) * dt * f0[i] + th * dt * f1[i]);
+                        if (usave) usave[(size_t)isave * SB_N + sb_nat[i]] = v;
+                        if (SRC) di[i] = v;
+                    }
+                    __syncwarp();
+                    emit(di, ts, true);
+                }
+                for (int i = lane; i < SB_N; i += SB_WARP) { const double v = un[i]; if (isnan(v)) bad = true; u[i] = v; f0[i] = f1[i]; }
+                t = tn;
+                bad = __any_sync(SB_FULL, bad);
+                __syncwarp();
+                if (bad) { rc = SB_RC_UNSTABLE; break; }
+                if (last) break;
+                dt = dtnew;
+                jt = jn;
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < SB_N; i += SB_WARP) A.uend[(size_t)mode * SB_N + sb_nat[i]] = u[i];
+        while (isave < A.nsave) { // save times the mode never reached (failed solve)
+            if (usave) for (int i = lane; i < SB_N; i += SB_WARP) usave[(size_t)isave * SB_N + i] = NAN;
+            emit(u, t, false);
+        }
+        if (lane == 0) { A.retcode[mode] = rc; A.stats[4 * mode] = naccept; A.stats[4 * mode + 1] = nreject; A.stats[4 * mode + 2] = nf; A.stats[4 * mode + 3] = nsolve; }
+    }
+}
+
 // Δm(τ,k) for P(k): one thread per mode
 __global__ void sb_deltam_kernel(const double* __restrict__ P, SbSpline spl, double tau, int nk, const double* __restrict__ ks, const double* __restrict__ u, double* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2475,6 +2665,32 @@ int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* 
 #else
     return -5;
 #endif
+}
+// The single-cosmology solve with TRBDF2 instead of Rodas5P (reference ptalg(prob; accuracy = 0), src/solve.jl:333-335): arguments and results as
+// sbm_solvept_src (stats[3] counts the linear solves); one warp per mode, atomic queue.
+int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                       const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                       int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream, const sbm_src_t* src) {
+    if (nk <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SbSolveArgs A;
+    memset(&A, 0, sizeof(A));
+    const bool fused = src && src->dS && nsave > 0;
+    if (fused && (src->nS < 2 || src->nS > 3 || !src->dsrcbg)) return -1;
+    A.c0 = SbCosmo{dP, SbSpline{nb, dt, dy, ddy}, SbTable{nb, msub, nlut, s0, 1.0 / dsl, dt, dlut, dtab}, tend, dsaveat, fused ? src->dsrcbg : nullptr, fused ? src->taurec : 0.0};
+    A.S = fused ? src->dS : nullptr; A.nS = fused ? src->nS : 0; A.scale_k = fused ? src->scale_k : 0;
+    A.nk = nk; A.ks = dks; A.tini = dtini; A.order = dorder; A.nsave = (dusave || fused) ? nsave : 0;
+    A.reltol = reltol; A.abstol = abstol; A.maxiters = maxiters; A.usave = dusave; A.uend = duend; A.retcode = dretcode; A.stats = dstats; A.queue = dqueue;
+    SB_CUDA_CHECK(cudaMemsetAsync(dqueue, 0, sizeof(int), st));
+    int dev, nsm, occ = 0;
+    SB_CUDA_CHECK(cudaGetDevice(&dev));
+    SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_trbdf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_trbdf2_kernel, SB_WARP, SB_SM_BYTES));
+    const int grid = std::min(nk, nsm * std::max(occ, 1));
+    sb_trbdf2_kernel<<<grid, SB_WARP, SB_SM_BYTES, st>>>(A);
+    SB_CUDA_CHECK(cudaGetLastError());
+    return grid;
 }
 // Per-save-time background table of the source evaluation: dsrcbg[nt][sbm_srcbg_stride()] (κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, the β_m and their
 // flow derivatives at dtaus[nt]); input of sbm_solvept_src / sbm_cosmo_t.srcbg and of sbm_sources.

@@ -738,3 +738,35 @@ def test_split_kernel_is_bit_identical(sb, prob5, bg5):
                     assert np.array_equal(a.d_S.cpu().numpy(), b.d_S.cpu().numpy(), equal_nan=True), kw
         auto = sb.solvept(prob, bg, ks[1:])  # the default picks the split mapping for a launch this small
         assert np.array_equal(auto.uend, sb.solvept(prob, bg, ks[1:], split=False).uend)
+
+
+@pytest.mark.gpu
+def test_trbdf2_matches_oracle_and_converges_to_rodas5p(sb, oracle, prob5, bg5, obg_same):
+    """`solvept(alg="TRBDF2")` -- the reference's `ptalg(prob; accuracy = 0)` (src/solve.jl:333-335), exercised by its tests only through `issuccess`
+    (test/runtests.jl:580-590 does the same with KenCarp4).  OrdinaryDiffEq.jl is absent, so both sides implement the published scheme (parity with Julia's
+    step selection unpinned): (i) GPU against the oracle's TRBDF2 on the same knots: P(k) to 1e-6 at a tight tolerance, step counts within 2 %;
+    (ii) TRBDF2 converges to the Rodas5P result with the tolerance; (iii) the reference's own check: success on k = 1, 10, 100, 1000; (iv) dense output and
+    fused sources against the Rodas5P path at a tolerance where both have converged."""
+    ks = np.array([1.0, 10.0, 100.0, 1000.0])
+    f = lambda k: min(1e-2 / k, 1e-4)
+    ref = sb.solvept(prob5, bg5, ks, ptivini=f, reltol=1e-9, abstol=1e-9)
+    errs = []
+    for tol in (1e-4, 1e-6):
+        s = sb.solvept(prob5, bg5, ks, ptivini=f, reltol=tol, abstol=tol, alg="TRBDF2")
+        assert s.success  # (iii)
+        o = oracle.solvept(obg_same, ks, ptivini=f, reltol=tol, abstol=tol, alg="TRBDF2")
+        rel = np.abs(s.uend - o["uend"]).max(axis=1) / np.abs(o["uend"]).max(axis=1)
+        assert (rel < (1e-6 if tol == 1e-6 else 1e-4)).all(), (tol, rel)  # (i): same algorithm on both sides
+        assert np.abs(s.stats[:, 0] / o["stats"][:, 0] - 1).max() < 0.02
+        errs.append((np.abs(s.uend - ref.uend).max(axis=1) / np.abs(ref.uend).max(axis=1)).max())
+    assert errs[1] < 0.2 * errs[0] and errs[1] < 1e-4, errs  # (ii): second order: 100x tighter tolerance, ~20x smaller error
+    taus = np.geomspace(1e-3, bg5.tau0, 30); taus[-1] = bg5.t[-1]
+    kw = dict(saveat=taus, sources=dict(nS=3, scale_k=True), reltol=1e-7, abstol=1e-7)
+    a = sb.solvept(prob5, bg5, ks[:3], **kw)
+    b = sb.solvept(prob5, bg5, ks[:3], alg="TRBDF2", **kw)
+    A, B = a.d_S.cpu().numpy(), b.d_S.cpu().numpy()
+    scale = np.abs(A[:, :, :-1]).max(axis=2, keepdims=True)
+    assert (np.abs(A - B)[:, :, :-1] <= 2e-4 * scale).all(), (np.abs(A - B)[:, :, :-1] / scale).max()  # (iv)
+    assert np.abs(a.usave - b.usave).max() <= 2e-4 * np.abs(a.usave).max()
+    with pytest.raises(ValueError):
+        sb.solvept(prob5, bg5, ks, alg="KenCarp4")

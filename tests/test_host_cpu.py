@@ -398,3 +398,18 @@ def test_background_differentiation(sb, prob5, bg5):
     # A_s and n_s do not enter the background at all: exactly zero.  YHe enters only the recombination unknowns; the expansion a(τ) shares
     # the pivoted 5×5 solves with them, so τ0 moves in its last bits (1e-14 relative) and the quotient is rounding noise, not zero.
     assert (g[-2:] == 0).all() and abs(g[-3]) < 1e-6 and (np.abs(fd[-3:]) < 1e-2).all()
+
+
+def test_oracle_trbdf2_converges_to_rodas5p(oracle):
+    """The oracle's restatement of TRBDF2 (reference `ptalg(prob; accuracy = 0)`, src/solve.jl:333-335; OrdinaryDiffEq.jl absent: published scheme, unpinned
+    against Julia) against its Rodas5P, which IS pinned to the reference's CLASS goldens: P(k) converges at the method's order (error ∝ tol^(2/3)) and the
+    reference's own check for its alternative integrators -- success on k = 1, 10, 100, 1000 (test/runtests.jl:580-582) -- holds."""
+    bg = oracle.Background(oracle.planck18(lmax=5))
+    ks = np.array([1.0, 10.0, 100.0, 1000.0])
+    Pt, _ = oracle.spectrum_matter(bg, ks, reltol=1e-9, abstol=1e-9)
+    errs = []
+    for tol in (1e-4, 1e-6):
+        P, sol = oracle.spectrum_matter(bg, ks, reltol=tol, abstol=tol, alg="TRBDF2")
+        assert (sol["retcode"] == 0).all()
+        errs.append(np.abs(P / Pt - 1).max())
+    assert errs[0] < 2e-2 and errs[1] < 1e-3 and errs[1] < 0.15 * errs[0], errs
