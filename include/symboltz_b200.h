@@ -167,6 +167,17 @@ int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double*
                        const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
                        double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
                        const sbm_src_t* src);
+/* The same with KenCarp4 (`ptalg(prob; accuracy = 1)`, src/solve.jl:336-337; the algorithm of the reference's sparse-Jacobian test, test/runtests.jl:580-590):
+ * the ESDIRK half of Kennedy & Carpenter's ARK4(3)6L[2]SA, gamma = 1/4, six stages, stiffly accurate, third-order companion estimate.  Same caveat. */
+int sbm_solvept_kencarp4(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                         const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                         double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
+                         const sbm_src_t* src);
+/* alg: 1 = TRBDF2, 2 = KenCarp4 */
+int sbm_solvept_sdirk(int alg, const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut,
+                       const double* dtab, int nk, const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat,
+                       double reltol, double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream,
+                       const sbm_src_t* src);
 /* Per-save-time background table of the source evaluation at dtaus[nt]: dsrcbg[nt][sbm_srcbg_stride()] = the first three time
  * derivatives of kappa, exp(-kappa), tau0 - tau, 3 spare, beta_m[NBETA], d beta_m/d tau [NBETA] (derivatives along the background
  * flow, as MTK's symbolic expansion of the observed source expressions does, src/solve.jl:637-657). */

@@ -509,6 +509,71 @@ template <class Sys> struct TRBDF2 {
         }
     }
 };
+// KenCarp4 (Kennedy & Carpenter 2003, ARK4(3)6L[2]SA; the reference's `ptalg(prob; accuracy = 1)`, src/solve.jl:336-337, and the algorithm its sparse-Jacobian
+// test solves with, test/runtests.jl:580-590).  The reference integrates the whole right-hand side implicitly, so only the ESDIRK half of the pair matters:
+// γ = 1/4, six stages, stiffly accurate, third-order companion b̂.  Same caveats as TRBDF2: published tableau (row sums Σ_j a_ij = c_i and Σ b̂ = 1 are
+// asserted in tests/test_host_cpu.py), stages solved exactly with J at the stage time, PARITY UNPINNED against OrdinaryDiffEq.jl's step selection.
+namespace KC4 {
+const double g = 0.25;
+const double c[6] = {0, 0.5, 83.0 / 250, 31.0 / 50, 17.0 / 20, 1};
+const double A[6][5] = {{0, 0, 0, 0, 0},
+                        {0.25, 0, 0, 0, 0},
+                        {8611.0 / 62500, -1743.0 / 31250, 0, 0, 0},
+                        {5012029.0 / 34652500, -654441.0 / 2922500, 174375.0 / 388108, 0, 0},
+                        {15267082809.0 / 155376265600.0, -71443401.0 / 120774400, 730878875.0 / 902184768, 2285395.0 / 8070912, 0},
+                        {82889.0 / 524892, 0, 15625.0 / 83664, 69875.0 / 102672, -2260.0 / 8211}};
+const double b[6] = {82889.0 / 524892, 0, 15625.0 / 83664, 69875.0 / 102672, -2260.0 / 8211, 0.25};
+const double bh[6] = {4586570599.0 / 29645900160.0, 0, 178811875.0 / 945068544, 814220225.0 / 1159782912, -3700637.0 / 11593932, 61727.0 / 225920};
+}
+template <class Sys> struct KenCarp4 {
+    Sys& sys; int n;
+    std::vector<double> W, Wp, F, f0, f1, U, unew, est, tmp, rhs;
+    std::vector<int> perm;
+    SparseLU lu;
+    Stats st;
+    bool have_f0 = false;
+    explicit KenCarp4(Sys& s) : sys(s), n(s.n), W(n * n), Wp(n * n), F(6 * n), f0(n), f1(n), U(n), unew(n), est(n), tmp(n), rhs(n), perm(n) {
+        for (int i = 0; i < n; i++) perm[i] = i;
+        sys.ordering(perm.data());
+    }
+    void solve_inplace(double* b) {
+        for (int i = 0; i < n; i++) tmp[i] = b[perm[i]];
+        lu.solve(tmp.data());
+        for (int i = 0; i < n; i++) b[perm[i]] = tmp[i];
+    }
+    bool factor(double ts, const double* u, double x) {
+        sys.jac(ts, u, W.data()); st.njac++;
+        for (int i = 0; i < n; i++) { const double* Wi = &W[(size_t)perm[i] * n]; double* Pi = &Wp[(size_t)i * n]; for (int j = 0; j < n; j++) Pi[j] = -Wi[perm[j]]; Pi[i] += x; }
+        return lu.factor(n, Wp.data());
+    }
+    bool step(double t, const double* u, double dt) {
+        const double x = 1 / (KC4::g * dt);
+        if (!have_f0) { sys.f(t, u, f0.data()); st.nf++; have_f0 = true; }
+        std::copy(f0.begin(), f0.end(), F.begin());
+        for (int s = 1; s < 6; s++) {
+            for (int i = 0; i < n; i++) { double v = 0; for (int j = 0; j < s; j++) v += KC4::A[s][j] * F[(size_t)j * n + i]; rhs[i] = u[i] + dt * v; U[i] = x * rhs[i]; }
+            if (!factor(t + KC4::c[s] * dt, u, x)) return false;
+            solve_inplace(U.data());
+            for (int i = 0; i < n; i++) F[(size_t)s * n + i] = x * (U[i] - rhs[i]);
+        }
+        unew = U; // stiffly accurate
+        for (int i = 0; i < n; i++) { f1[i] = F[(size_t)5 * n + i]; double v = 0; for (int j = 0; j < 6; j++) v += (KC4::b[j] - KC4::bh[j]) * F[(size_t)j * n + i]; est[i] = x * (dt * v); }
+        solve_inplace(est.data());
+        return true;
+    }
+    void accept() { f0 = f1; }
+    double errnorm(const double* u, double abstol, double reltol) const {
+        double s = 0;
+        for (int i = 0; i < n; i++) { double sc = abstol + reltol * std::max(std::fabs(u[i]), std::fabs(unew[i])); double r = est[i] / sc; s += r * r; }
+        return std::sqrt(s / n);
+    }
+    void interp(const double* u0, double th, double dt, double* out) const {
+        for (int i = 0; i < n; i++) {
+            const double du = unew[i] - u0[i];
+            out[i] = (1 - th) * u0[i] + th * unew[i] + th * (th - 1) * ((1 - 2 * th) * du + (th - 1) * dt * f0[i] + th * dt * f1[i]);
+        }
+    }
+};
 // Step-size control of the implicit methods: Gustafsson's predictive controller in the form OrdinaryDiffEq uses for its Newton-based methods
 // (restated from the published controller, same caveat as above); exponent 1/3 for TRBDF2's O(dt³) estimate, one "Newton iteration" per stage.
 struct PredictiveController {
@@ -813,12 +878,13 @@ struct PtSys {
 };
 
 // Solve one mode. saveat may be empty (then only the final state is returned in uend).
-// the same driver for TRBDF2 (see the struct): initial step as for Rodas5P with the method's order
-static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
-                             long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats);
+// the same driver for the ESDIRK methods (TRBDF2, KenCarp4): initial step as for Rodas5P with the method's order
+template <class Stepper> static int solve_mode_sdirk(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
+                                                     long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats, int order);
 static int solve_mode(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
                       long maxiters, int nsave, const double* saveat, double* usave /*nsave×N*/, double* uend /*N*/, long* stats /*4*/, int alg = 0) {
-    if (alg == 1) return solve_mode_trbdf2(D, spl, k, tini, tend, reltol, abstol, maxiters, nsave, saveat, usave, uend, stats);
+    if (alg == 1) return solve_mode_sdirk<TRBDF2<PtSys>>(D, spl, k, tini, tend, reltol, abstol, maxiters, nsave, saveat, usave, uend, stats, 2);
+    if (alg == 2) return solve_mode_sdirk<KenCarp4<PtSys>>(D, spl, k, tini, tend, reltol, abstol, maxiters, nsave, saveat, usave, uend, stats, 4);
     PtSys sys(D, spl, k);
     int n = sys.n;
     Rodas5P<PtSys> R(sys);
@@ -863,12 +929,13 @@ static int solve_mode(const Derived& D, const Spline& spl, double k, double tini
     return rc;
 }
 
-static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
-                             long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats) {
+template <class Stepper> static int solve_mode_sdirk(const Derived& D, const Spline& spl, double k, double tini, double tend, double reltol, double abstol,
+                                                     long maxiters, int nsave, const double* saveat, double* usave, double* uend, long* stats, int order) {
     PtSys sys(D, spl, k);
     int n = sys.n;
-    TRBDF2<PtSys> R(sys);
+    Stepper R(sys);
     PredictiveController ctl;
+    ctl.expo = 1.0 / (order + (order == 2 ? 1 : 0)); // the estimate is O(dt³) for TRBDF2 (third-order companion of a second-order method), O(dt⁴) for KenCarp4 (4(3) pair)
     std::vector<double> u(n);
     int rc = RC_SUCCESS, isave = 0;
     if (!(k > 0) || !std::isfinite(k)) { for (int i = 0; i < n; i++) uend[i] = NAN; for (long i = 0; i < (long)nsave * n; i++) usave[i] = NAN; if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0; return RC_UNSTABLE; }
@@ -877,7 +944,7 @@ static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, doub
     while (isave < nsave && saveat[isave] <= t) { if (saveat[isave] == t) std::copy(u.begin(), u.end(), usave + (long)isave * n); else for (int i = 0; i < n; i++) usave[(long)isave * n + i] = NAN; isave++; }
     if (tend > tini) {
         double dt;
-        { // Hairer's initial step with the method's order (2): same recipe as Rodas5P::initdt, exponent 1/(order + 1)
+        { // Hairer's initial step with the method's order: same recipe as Rodas5P::initdt, exponent 1/(order + 1)
             std::vector<double> sk(n), fa(n), fb(n), u1(n);
             sys.f(t, u.data(), fa.data()); R.st.nf++;
             double d0 = 0, d1 = 0;
@@ -892,7 +959,7 @@ static int solve_mode_trbdf2(const Derived& D, const Spline& spl, double k, doub
             for (int i = 0; i < n; i++) { double r = (fb[i] - fa[i]) / sk[i]; d2 += r * r; }
             d2 = std::sqrt(d2 / n) / dt0;
             double dm = std::max(d1, d2);
-            double dt1 = (dm <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2 + std::log10(dm)) / 3.0);
+            double dt1 = (dm <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2 + std::log10(dm)) / (order + 1.0));
             dt = std::min(std::min(100 * dt0, dt1), dtmax);
         }
         for (long it = 0;; it++) {
@@ -1049,7 +1116,15 @@ void sbo_solvept(const SboParams* p, int nb, const double* t, const double* y, c
     }
 }
 
-// sbo_solvept with a choice of integrator: alg 0 = Rodas5P (the reference's default, ptalg accuracy = 2), 1 = TRBDF2 (accuracy = 0)
+// sbo_solvept with a choice of integrator: alg 0 = Rodas5P (the reference's default, ptalg accuracy = 2), 1 = TRBDF2 (accuracy = 0), 2 = KenCarp4 (accuracy = 1)
+void sbo_kencarp4_tableau(double* out /*[6][5] A, [6] c, [6] b, [6] bh, gamma*/) {
+    int q = 0;
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 5; j++) out[q++] = KC4::A[i][j];
+    for (int i = 0; i < 6; i++) out[q++] = KC4::c[i];
+    for (int i = 0; i < 6; i++) out[q++] = KC4::b[i];
+    for (int i = 0; i < 6; i++) out[q++] = KC4::bh[i];
+    out[q++] = KC4::g;
+}
 void sbo_solvept_alg(const SboParams* p, int nb, const double* t, const double* y, const double* dy, double tau0, double kappa0,
                      int nk, const double* ks, const double* tini, int nsave, const double* saveat, double reltol, double abstol, long maxiters,
                      int nthreads, double* usave, double* uend, int* retcode, long* stats, int alg) {

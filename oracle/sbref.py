@@ -177,9 +177,9 @@ def solvept(bg, ks, ptivini=-np.inf, saveat=None, reltol=1e-5, abstol=1e-5, maxi
         ns, ps, pu = len(saveat), _p(saveat), _p(usave)
     else:
         usave, ns, ps, pu = None, 0, None, None
-    # alg: "Rodas5P" (reference default) or "TRBDF2" (reference ptalg(accuracy = 0), src/solve.jl:333-335; published scheme, unpinned against Julia)
+    # alg: "Rodas5P" (reference default), "TRBDF2" / "KenCarp4" (reference ptalg(accuracy = 0 / 1), src/solve.jl:333-337; published schemes, unpinned against Julia)
     lib().sbo_solvept_alg(C.byref(bg.p), *bg._spl(), C.c_double(bg.tau0), C.c_double(bg.kappa0), C.c_int(nk), _p(ks), _p(tini), C.c_int(ns), ps,
-                          C.c_double(reltol), C.c_double(abstol), C.c_long(maxiters), C.c_int(nthreads), pu, _p(uend), _p(ret), _p(stats), C.c_int({"Rodas5P": 0, "TRBDF2": 1}[alg]))
+                          C.c_double(reltol), C.c_double(abstol), C.c_long(maxiters), C.c_int(nthreads), pu, _p(uend), _p(ret), _p(stats), C.c_int({"Rodas5P": 0, "TRBDF2": 1, "KenCarp4": 2}[alg]))
     return dict(uend=uend, usave=usave, retcode=ret, stats=stats, tini=tini)
 
 

@@ -567,8 +567,9 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     split: None (default) = choose the mapping by the size of the launch: with no more modes than `split_capacity(prob)` (296 on a B200 for
     the nx = 4 models) every mode gets a CTA of SB_R warps (`sbm_solvept_split`: the row-parallel phases of an attempt are spread over the
     warps; ≈40 % lower latency, bit-identical results), otherwise one warp per mode; True / False force one or the other.
-    alg: "Rodas5P" (the reference's default, `ptalg(prob; accuracy = 2)`) or "TRBDF2" (`accuracy = 0`, src/solve.jl:333-335: second order, three linear
-    solves and no f-evaluation per step; the published scheme -- OrdinaryDiffEq.jl's own step selection cannot be pinned here; one warp per mode, queue only)."""
+    alg: "Rodas5P" (the reference's default, `ptalg(prob; accuracy = 2)`), "KenCarp4" (`accuracy = 1`: the ESDIRK half of ARK4(3)6L[2]SA, five factorisations
+    and six solves per step) or "TRBDF2" (`accuracy = 0`: second order, two factorisations and three solves per step), src/solve.jl:333-337; published schemes
+    with every stage solved exactly (the system is linear) -- OrdinaryDiffEq.jl's own step selection cannot be pinned here; one warp per mode, queue only."""
     _require_cuda()
     ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.float64)
     nk = len(ks)
@@ -602,12 +603,12 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         dsave, usave, ns = None, None, 0
     srcp = C.byref(src) if src is not None else None
     dtrace = torch.zeros((trace, 3), dtype=torch.float64, device=dev) if trace else None  # debug: (t, dt, EEst) of mode 0
-    if alg not in ("Rodas5P", "TRBDF2"):
-        raise ValueError(f"unknown perturbation integrator {alg!r}: Rodas5P or TRBDF2 (KenCarp4 is not built)")
-    if alg == "TRBDF2":
+    if alg not in ("Rodas5P", "TRBDF2", "KenCarp4"):
+        raise ValueError(f"unknown perturbation integrator {alg!r}: Rodas5P, KenCarp4 or TRBDF2 (the reference's ptalg(prob; accuracy = 2 / 1 / 0))")
+    if alg != "Rodas5P":
         if cost is not None or trace or nctas or split is True:
-            raise ValueError("TRBDF2 runs one warp per mode from the atomic queue: no cost=, trace=, nctas= or split=True")
-        rc = prob.lib.sbm_solvept_trbdf2(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
+            raise ValueError(f"{alg} runs one warp per mode from the atomic queue: no cost=, trace=, nctas= or split=True")
+        rc = (prob.lib.sbm_solvept_trbdf2 if alg == "TRBDF2" else prob.lib.sbm_solvept_kencarp4)(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
                                          C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
                                          _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _stream(), srcp)
     elif cost is not None and nk > 0:

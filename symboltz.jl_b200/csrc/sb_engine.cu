@@ -2217,14 +2217,32 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
 //   error estimate: (x − J_1)^{-1} x dt Σ (b_i − b̂_i) f_i, third-order companion b̂ = ((1−ω)/3, (3ω+1)/3, d/3); Gustafsson's predictive controller
 //   dense output / save points: cubic Hermite on (u_n, f_n, u_1, f_1); sources at the save times as in sb_integrate_kernel.
 // One warp per mode, atomic queue, same shared-memory layout as sb_integrate_kernel (K holds f_n, f_γ, f_1, r, the estimate and u_1).
-__global__ void __launch_bounds__(SB_WARP, 4) sb_trbdf2_kernel(const __grid_constant__ SbSolveArgs A) {
+//
+// KenCarp4 (ALG = 2; `ptalg(prob; accuracy = 1)`, src/solve.jl:336-337, the algorithm of the reference's sparse-Jacobian test, test/runtests.jl:580-590): the
+// ESDIRK half of Kennedy & Carpenter's ARK4(3)6L[2]SA (the reference integrates the whole right-hand side implicitly), γ = 1/4, six stages, stiffly accurate:
+//   stage i = 2..6:  (x − J_i) U_i = x (u_n + dt Σ_{j<i} a_ij f_j),  f_i = x (U_i − rhs_i),  x = 1/(γ dt);  u_1 = U_6, f_1 = f_6 (first-same-as-last)
+//   error estimate (x − J_6)^{-1} x dt Σ (b_j − b̂_j) f_j (O(dt⁴)); the same controller and dense output.  K holds f_1..f_6, the stage right-hand side and the estimate.
+// Same caveat: published tableau (row sums checked in tests/test_host_cpu.py), parity with OrdinaryDiffEq.jl's step selection unpinned.
+__constant__ double cKA[6][5] = {{0, 0, 0, 0, 0},
+                                 {0.25, 0, 0, 0, 0},
+                                 {8611.0 / 62500, -1743.0 / 31250, 0, 0, 0},
+                                 {5012029.0 / 34652500, -654441.0 / 2922500, 174375.0 / 388108, 0, 0},
+                                 {15267082809.0 / 155376265600.0, -71443401.0 / 120774400, 730878875.0 / 902184768, 2285395.0 / 8070912, 0},
+                                 {82889.0 / 524892, 0, 15625.0 / 83664, 69875.0 / 102672, -2260.0 / 8211}};
+__constant__ double cKc[6] = {0, 0.5, 83.0 / 250, 31.0 / 50, 17.0 / 20, 1};
+__constant__ double cKe[6] = {82889.0 / 524892 - 4586570599.0 / 29645900160.0, 0, 15625.0 / 83664 - 178811875.0 / 945068544, 69875.0 / 102672 - 814220225.0 / 1159782912,
+                              -2260.0 / 8211 + 3700637.0 / 11593932, 0.25 - 61727.0 / 225920}; // b − b̂
+template <int ALG>
+__global__ void __launch_bounds__(SB_WARP, 4) sb_sdirk_kernel(const __grid_constant__ SbSolveArgs A) {
+    constexpr int ORDER = (ALG == 1) ? 2 : 4;
+    constexpr double EXPO = 1.0 / ((ALG == 1) ? 3 : 4); // exponent of the O(dt³) / O(dt⁴) error estimate in the controller
     extern __shared__ __align__(16) double sm_all[];
     const int lane = threadIdx.x & 31;
     double* const sm = sm_all;
     double *u = sm + SB_SM_U, *U = sm + SB_SM_UU, *K = sm + SB_SM_K, *di = sm + SB_SM_DI, *up = sm + SB_SM_UP, *mm = sm + SB_SM_MM, *Zp = sm + SB_SM_ZP, *Zq = sm + SB_SM_ZQ,
            *bs = sm + SB_SM_BS, *blk = sm + SB_SM_BLK, *kp = sm + SB_SM_KP;
     double* const sbuf = sm + SB_SM_SBUF;
-    double *f0 = K, *fg = K + SB_N, *f1 = K + 2 * SB_N, *rv = K + 3 * SB_N, *ev = K + 4 * SB_N, *un = K + 5 * SB_N;
+    double *f0 = K, *fg = K + SB_N, *f1 = K + (ALG == 1 ? 2 : 5) * SB_N, *rv = K + (ALG == 1 ? 3 : 6) * SB_N, *ev = K + (ALG == 1 ? 4 : 7) * SB_N, *un = (ALG == 1) ? K + 5 * SB_N : U;
     const double reltol = A.reltol, abstol = A.abstol;
     const bool SRC = A.S != nullptr;
     SbLane S;
@@ -2280,7 +2298,7 @@ __global__ void __launch_bounds__(SB_WARP, 4) sb_trbdf2_kernel(const __grid_cons
             __syncwarp();
             sb_eval_f<false>(S, bs, u, f0, lane); nf++;
             double dt;
-            { // automatic initial step (Hairer) with the method's order 2
+            { // automatic initial step (Hairer) with the method's order
                 double d0 = 0, d1 = 0;
                 for (int i = lane; i < SB_N; i += SB_WARP) { const double sk = abstol + fabs(u[i]) * reltol; const double a0 = u[i] / sk, a1 = f0[i] / sk; d0 = fma(a0, a0, d0); d1 = fma(a1, a1, d1); }
                 d0 = sqrt(warp_sum(d0) / SB_N); d1 = sqrt(warp_sum(d1) / SB_N);
@@ -2295,7 +2313,7 @@ __global__ void __launch_bounds__(SB_WARP, 4) sb_trbdf2_kernel(const __grid_cons
                 for (int i = lane; i < SB_N; i += SB_WARP) { const double sk = abstol + fabs(u[i]) * reltol; const double r = (fg[i] - f0[i]) / sk; d2 = fma(r, r, d2); }
                 d2 = sqrt(warp_sum(d2) / SB_N) / dt0;
                 const double dm = fmax(d1, d2);
-                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / 3.0);
+                const double dt1 = (dm <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(dm)) / (ORDER + 1.0));
                 dt = fmin(fmin(100 * dt0, dt1), dtmax);
                 __syncwarp();
             }
@@ -2332,29 +2350,53 @@ __global__ void __launch_bounds__(SB_WARP, 4) sb_trbdf2_kernel(const __grid_cons
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
                 bool last = false;
                 if (t + dt >= tend - 100 * 2.2e-16 * fabs(tend)) { dt = tend - t; last = true; }
-                const double x = 1.0 / (D * dt);
-                for (int i = lane; i < SB_N; i += SB_WARP) U[i] = fma(x, u[i], f0[i]);
-                __syncwarp();
-                const int jg = factor_solve(t + G * dt, x, jt, U);
-                woodbury(U);
-                for (int i = lane; i < SB_N; i += SB_WARP) { fg[i] = x * (U[i] - u[i]) - f0[i]; const double r = BA * U[i] - BB * u[i]; rv[i] = r; un[i] = x * r; }
-                __syncwarp();
-                const int jn = factor_solve(last ? tend : t + dt, x, jg, un);
-                woodbury(un);
-                for (int i = lane; i < SB_N; i += SB_WARP) { const double f = x * (un[i] - rv[i]); f1[i] = f; ev[i] = x * (dt * (E1 * f0[i] + E2 * fg[i] + E3 * f)); }
-                __syncwarp();
+                const double x = 1.0 / ((ALG == 1 ? D : 0.25) * dt);
+                int jn = jt;
+                if (ALG == 1) {
+                    for (int i = lane; i < SB_N; i += SB_WARP) U[i] = fma(x, u[i], f0[i]);
+                    __syncwarp();
+                    const int jg = factor_solve(t + G * dt, x, jt, U);
+                    woodbury(U);
+                    for (int i = lane; i < SB_N; i += SB_WARP) { fg[i] = x * (U[i] - u[i]) - f0[i]; const double r = BA * U[i] - BB * u[i]; rv[i] = r; un[i] = x * r; }
+                    __syncwarp();
+                    jn = factor_solve(last ? tend : t + dt, x, jg, un);
+                    woodbury(un);
+                    for (int i = lane; i < SB_N; i += SB_WARP) { const double f = x * (un[i] - rv[i]); f1[i] = f; ev[i] = x * (dt * (E1 * f0[i] + E2 * fg[i] + E3 * f)); }
+                    __syncwarp();
+                } else {
+#pragma unroll 1
+                    for (int sg = 1; sg < 6; sg++) { // stages 2..6; f_1 = f0 sits in K[0..N)
+                        for (int i = lane; i < SB_N; i += SB_WARP) {
+                            double v = 0;
+                            for (int j = 0; j < sg; j++) v = fma(cKA[sg][j], K[j * SB_N + i], v);
+                            const double r = fma(dt, v, u[i]);
+                            rv[i] = r; U[i] = x * r;
+                        }
+                        __syncwarp();
+                        jn = factor_solve((sg == 5) ? (last ? tend : t + dt) : t + cKc[sg] * dt, x, jn, U);
+                        woodbury(U);
+                        for (int i = lane; i < SB_N; i += SB_WARP) K[sg * SB_N + i] = x * (U[i] - rv[i]);
+                        __syncwarp();
+                    }
+                    for (int i = lane; i < SB_N; i += SB_WARP) {
+                        double v = 0;
+                        for (int j = 0; j < 6; j++) v = fma(cKe[j], K[j * SB_N + i], v);
+                        ev[i] = x * (dt * v);
+                    }
+                    __syncwarp();
+                }
                 { double* const e1[1] = {ev}; sb_bsolve<1>(S, e1, di, up, mm, blk, lane); } nsolve++;
                 woodbury(ev);
                 double es = 0; bool bad = false;
                 for (int i = lane; i < SB_N; i += SB_WARP) { const double r = ev[i] * sb_rcp(abstol + reltol * fmax(fabs(u[i]), fabs(un[i]))); es = fma(r, r, es); }
                 const double EEst = sqrt(warp_sum(es) / SB_N);
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
-                const double q = qold = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, pow(EEst, 1.0 / 3) / 0.9));
+                const double q = qold = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, pow(EEst, EXPO) / 0.9));
                 if (EEst > 1) { nreject++; dt = (success_iter == 0) ? 0.1 * dt : dt / qold; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
                 double qacc = q;
                 if (success_iter > 0) {
-                    double qgus = (dtacc / dt) * pow(EEst * EEst / erracc, 1.0 / 3);
+                    double qgus = (dtacc / dt) * pow(EEst * EEst / erracc, EXPO);
                     qgus = fmax(0.1, fmin(5.0, qgus / 0.9));
                     qacc = fmax(q, qgus);
                 }
@@ -2667,8 +2709,8 @@ int sbm_solvept_split(const double* dP, int nb, const double* dt, const double* 
 #endif
 }
 // The single-cosmology solve with TRBDF2 instead of Rodas5P (reference ptalg(prob; accuracy = 0), src/solve.jl:333-335): arguments and results as
-// sbm_solvept_src (stats[3] counts the linear solves); one warp per mode, atomic queue.
-int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+// sbm_solvept_src (stats[3] counts the linear solves); one warp per mode, atomic queue.  sbm_solvept_sdirk: alg 1 = TRBDF2, 2 = KenCarp4 (accuracy = 1).
+int sbm_solvept_sdirk(int alg, const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
                        const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
                        int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream, const sbm_src_t* src) {
     if (nk <= 0) return 0;
@@ -2685,12 +2727,24 @@ int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double*
     int dev, nsm, occ = 0;
     SB_CUDA_CHECK(cudaGetDevice(&dev));
     SB_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(sb_trbdf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SM_BYTES));
-    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sb_trbdf2_kernel, SB_WARP, SB_SM_BYTES));
+    if (alg != 1 && alg != 2) return -1;
+    auto kern = (alg == 1) ? sb_sdirk_kernel<1> : sb_sdirk_kernel<2>;
+    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SM_BYTES));
+    SB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SB_WARP, SB_SM_BYTES));
     const int grid = std::min(nk, nsm * std::max(occ, 1));
-    sb_trbdf2_kernel<<<grid, SB_WARP, SB_SM_BYTES, st>>>(A);
+    kern<<<grid, SB_WARP, SB_SM_BYTES, st>>>(A);
     SB_CUDA_CHECK(cudaGetLastError());
     return grid;
+}
+int sbm_solvept_trbdf2(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                       const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                       int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream, const sbm_src_t* src) {
+    return sbm_solvept_sdirk(1, dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, stream, src);
+}
+int sbm_solvept_kencarp4(const double* dP, int nb, const double* dt, const double* dy, const double* ddy, int msub, int nlut, double s0, double dsl, const int* dlut, const double* dtab, int nk,
+                         const double* dks, const double* dtini, const int* dorder, double tend, int nsave, const double* dsaveat, double reltol, double abstol,
+                         int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, void* stream, const sbm_src_t* src) {
+    return sbm_solvept_sdirk(2, dP, nb, dt, dy, ddy, msub, nlut, s0, dsl, dlut, dtab, nk, dks, dtini, dorder, tend, nsave, dsaveat, reltol, abstol, maxiters, dusave, duend, dretcode, dstats, dqueue, stream, src);
 }
 // Per-save-time background table of the source evaluation: dsrcbg[nt][sbm_srcbg_stride()] (κ̇, κ̈, κ⃛, e^{−κ}, τ0 − τ, the β_m and their
 // flow derivatives at dtaus[nt]); input of sbm_solvept_src / sbm_cosmo_t.srcbg and of sbm_sources.

@@ -769,4 +769,33 @@ def test_trbdf2_matches_oracle_and_converges_to_rodas5p(sb, oracle, prob5, bg5, 
     assert (np.abs(A - B)[:, :, :-1] <= 2e-4 * scale).all(), (np.abs(A - B)[:, :, :-1] / scale).max()  # (iv)
     assert np.abs(a.usave - b.usave).max() <= 2e-4 * np.abs(a.usave).max()
     with pytest.raises(ValueError):
-        sb.solvept(prob5, bg5, ks, alg="KenCarp4")
+        sb.solvept(prob5, bg5, ks, alg="Tsit5")
+
+
+@pytest.mark.gpu
+def test_kencarp4_matches_oracle_and_converges_to_rodas5p(sb, oracle, prob5, bg5, obg_same):
+    """`solvept(alg="KenCarp4")` -- the reference's `ptalg(prob; accuracy = 1)` and the algorithm of its sparse-Jacobian test (test/runtests.jl:580-590: success on
+    k = 1, 10, 100, 1000).  Published ESDIRK tableau on both sides (unpinned against Julia): GPU against the oracle's KenCarp4 on the same knots, fourth-order
+    convergence to the Rodas5P result, dense output and fused sources against the Rodas5P path."""
+    ks = np.array([1.0, 10.0, 100.0, 1000.0])
+    f = lambda k: min(1e-2 / k, 1e-4)
+    ref = sb.solvept(prob5, bg5, ks, ptivini=f, reltol=1e-10, abstol=1e-10)
+    errs = []
+    for tol in (1e-4, 1e-6):
+        s = sb.solvept(prob5, bg5, ks, ptivini=f, reltol=tol, abstol=tol, alg="KenCarp4")
+        assert s.success
+        o = oracle.solvept(obg_same, ks, ptivini=f, reltol=tol, abstol=tol, alg="KenCarp4")
+        rel = np.abs(s.uend - o["uend"]).max(axis=1) / np.abs(o["uend"]).max(axis=1)
+        assert (rel < 10 * tol).all(), (tol, rel)  # same scheme, but step sequences that part at a dead-band decision differ by the truncation error (≈ tol)
+        assert (np.abs(s.stats[:, 0] - o["stats"][:, 0]) <= np.maximum(4, 0.05 * o["stats"][:, 0])).all(), (s.stats[:, 0], o["stats"][:, 0])  # (k = 1 takes ~10 steps; the controller's dead band 1 <= q <= 1.2 makes the count jumpy)
+        errs.append((np.abs(s.uend - ref.uend).max(axis=1) / np.abs(ref.uend).max(axis=1)).max())
+    assert errs[1] < 0.2 * errs[0] and errs[1] < 5e-5, errs  # max over ALL unknowns (measured 1.2e-4 -> 1.2e-5; P(k) goes 4e-4 -> 5e-6 in the oracle test)
+    taus = np.geomspace(1e-3, bg5.tau0, 30); taus[-1] = bg5.t[-1]
+    kw = dict(saveat=taus, sources=dict(nS=3, scale_k=True), reltol=1e-8, abstol=1e-8)
+    a = sb.solvept(prob5, bg5, ks[:3], **kw)
+    b = sb.solvept(prob5, bg5, ks[:3], alg="KenCarp4", **kw)
+    A, B = a.d_S.cpu().numpy(), b.d_S.cpu().numpy()
+    scale = np.abs(A[:, :, :-1]).max(axis=2, keepdims=True)
+    with np.errstate(invalid="ignore"):
+        assert (np.abs(A - B)[:, :, :-1] <= 2e-4 * scale).all(), (np.abs(A - B)[:, :, :-1] / scale).max()
+    assert np.abs(a.usave - b.usave).max() <= 2e-4 * np.abs(a.usave).max()

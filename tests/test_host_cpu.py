@@ -413,3 +413,31 @@ def test_oracle_trbdf2_converges_to_rodas5p(oracle):
         assert (sol["retcode"] == 0).all()
         errs.append(np.abs(P / Pt - 1).max())
     assert errs[0] < 2e-2 and errs[1] < 1e-3 and errs[1] < 0.15 * errs[0], errs
+
+
+def test_oracle_kencarp4_tableau_and_convergence(oracle):
+    """KenCarp4 (reference `ptalg(prob; accuracy = 1)`, src/solve.jl:336-337; the algorithm of test/runtests.jl:580-590) restated from Kennedy & Carpenter's
+    published ARK4(3)6L[2]SA tableau: consistency (row sums Σ_j a_ij + γ = c_i, Σ b = Σ b̂ = 1, stiffly accurate), order conditions up to 3 for b̂ and 4 for b
+    on the quadrature conditions, and fourth-order convergence of P(k) to the CLASS-pinned Rodas5P result; success on k = 1, 10, 100, 1000."""
+    import ctypes as C
+    out = (C.c_double * 49)()
+    oracle.lib().sbo_kencarp4_tableau(out)
+    v = np.array(out)
+    A, c, b, bh, g = v[:30].reshape(6, 5), v[30:36], v[36:42], v[42:48], v[48]
+    Afull = np.zeros((6, 6)); Afull[:, :5] = A; Afull[np.arange(1, 6), np.arange(1, 6)] = g
+    assert g == 0.25 and np.abs(Afull.sum(axis=1) - c).max() < 1e-15 and np.abs(Afull[5] - b).max() == 0
+    assert abs(b.sum() - 1) < 1e-15 and abs(bh.sum() - 1) < 1e-15
+    for q in (1, 2, 3):
+        assert abs(b @ c**q - 1 / (q + 1)) < 1e-14      # quadrature conditions of order 4
+    for q in (1, 2):
+        assert abs(bh @ c**q - 1 / (q + 1)) < 1e-13     # ... and of order 3 for the companion
+    assert abs(b @ (Afull @ c) - 1 / 6) < 1e-14 and abs(bh @ (Afull @ c) - 1 / 6) < 1e-13
+    bg = oracle.Background(oracle.planck18(lmax=5))
+    ks = np.array([1.0, 10.0, 100.0, 1000.0])
+    Pt, _ = oracle.spectrum_matter(bg, ks, reltol=1e-10, abstol=1e-10)
+    errs = []
+    for tol in (1e-4, 1e-6):
+        P, sol = oracle.spectrum_matter(bg, ks, reltol=tol, abstol=tol, alg="KenCarp4")
+        assert (sol["retcode"] == 0).all()
+        errs.append(np.abs(P / Pt - 1).max())
+    assert errs[0] < 2e-3 and errs[1] < 2e-5 and errs[1] < 0.05 * errs[0], errs
