@@ -548,6 +548,12 @@ def source_background(prob, d, nb, dsave):
     return out
 
 
+def ptalg(prob=None, accuracy=2):
+    """Perturbation integrator by accuracy level (reference ptalg(prob; accuracy), src/solve.jl:326-341): 0 -> "TRBDF2", 1 -> "KenCarp4", otherwise "Rodas5P";
+    pass the result as `alg=` to solvept / solve(ptopts=...) / spectrum_matter / spectrum_cmb(ptopts=...)."""
+    return "TRBDF2" if accuracy == 0 else ("KenCarp4" if accuracy == 1 else "Rodas5P")
+
+
 def split_capacity(prob):
     """Modes that run concurrently under the split mapping (one CTA of SB_R warps per mode, `sbm_solvept_split`); 0 if the model has none."""
     if not hasattr(prob, "_split_cap"):

@@ -770,6 +770,13 @@ def test_trbdf2_matches_oracle_and_converges_to_rodas5p(sb, oracle, prob5, bg5, 
     assert np.abs(a.usave - b.usave).max() <= 2e-4 * np.abs(a.usave).max()
     with pytest.raises(ValueError):
         sb.solvept(prob5, bg5, ks, alg="Tsit5")
+    # the alternative integrators through the spectrum calls, as the reference passes ptopts = (alg = ...,) (docs/src/plot.md:129)
+    assert sb.ptalg(prob5, accuracy=0) == "TRBDF2" and sb.ptalg(prob5, accuracy=1) == "KenCarp4" and sb.ptalg(prob5) == "Rodas5P"
+    kk = sb.loggrid(1e-3, 1.0, length=12) / sb.k0
+    P5 = sb.spectrum_matter(prob5, kk, bgsol=bg5, reltol=1e-9, abstol=1e-9)
+    for acc, bound in ((0, 2e-3), (1, 2e-4)):
+        Pa = sb.spectrum_matter(prob5, kk, bgsol=bg5, alg=sb.ptalg(prob5, accuracy=acc), reltol=1e-6, abstol=1e-6)
+        assert np.abs(Pa / P5 - 1).max() < bound, (acc, np.abs(Pa / P5 - 1).max())
 
 
 @pytest.mark.gpu
