@@ -155,6 +155,14 @@ struct SbController {
     SB_HD double reject(double dt) { return dt / fmin(5.0, q11 / 0.9); }
 };
 
+// The same PI controller for the perturbation kernels, in logarithms: q = EEst^(7/50) / qold^(2/25) = exp2((7/50) log2 EEst − (2/25) log2 qold) with log2 qold
+// carried from the previous accepted step -- one log2 and one exp2 per attempt instead of two pow() (≈2 k cycles of a lone warp, 8 % of an attempt).
+// Shared by every integrator kernel (explicit fma: the same bits everywhere).
+#ifdef __CUDACC__
+__device__ __forceinline__ double sb_ctl_q(double l, double lqold) { return exp2(fma(7.0 / 50.0, l, -(2.0 / 25.0) * lqold)); }   // q11 / qold^β2 from l = log2 EEst
+__device__ __forceinline__ double sb_ctl_q11(double l) { return exp2((7.0 / 50.0) * l); }                                        // EEst^β1 (rejected steps)
+__device__ __forceinline__ double sb_ctl_lq0() { double q0 = 1e-4; asm volatile("" : "+d"(q0)); return log2(q0); }               // log2 of the initial / smallest qold, by the device routine
+#endif
 namespace bgsolve {
 // The background solve proper.  Knots (t, y, y') are written straight into the caller's arrays (capacity cap); returns the number
 // of knots, or -1 if cap is too small / the solve failed before its first accepted step.
@@ -400,7 +408,8 @@ struct SbSolveArgs {
 #if SB_TMA
 #define SB_SM_TAB ((SB_SM_SBUF + 3 * SB_SWIN + 1) & ~1) // 16-byte aligned: [6 slots][4 rows][NBETA]
 #define SB_SM_MBAR (SB_SM_TAB + 6 * 4 * SB_NBETA)
-#define SB_SM_DOUBLES ((SB_SM_MBAR + 1 + 1) & ~1)
+#define SB_SM_BD5 (SB_SM_MBAR + 2) // derivative basis at the last stage time: the next attempt's slot 0 (SB_DEFER)
+#define SB_SM_DOUBLES ((SB_SM_BD5 + SB_NB + 1) & ~1)
 #else
 #define SB_SM_DOUBLES ((SB_SM_SBUF + 3 * SB_SWIN + 1) & ~1)
 #endif
@@ -443,6 +452,10 @@ struct SbSolveArgs {
 #endif
 #ifndef SB_SPLIT_UNROLL
 #define SB_SPLIT_UNROLL 0
+#endif
+// Table rows of the stage times requested at the start of the attempt and swept right before the first stage evaluation (see sb_split_basis_issue)
+#ifndef SB_DEFER
+#define SB_DEFER (SB_TMA && SB_BSLOT)
 #endif
 #ifndef SB_KEEP_MAX
 #define SB_KEEP_MAX 24 // doubles per lane that sb_bsolve may hold across its top step (see KEEP there)
@@ -1324,6 +1337,73 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
     __syncwarp();
 }
 
+// Basis at the stage times 2..6 of an attempt (slots 1..5; slot 0, the time t, is carried over from the previous attempt's last stage time).
+// Deferred form of sb_basis_batch (SB_DEFER; warp-per-mode and split kernel): the rows are requested at the start of the attempt, the factorisation and the
+// first solve need slot 0 only, and the wait + sweep come right before the first stage evaluation -- the L2 latency of the copies (≈1.5 k cycles, 6 % of a lone
+// warp's attempt) is off the dependent chain.  One warp locates the slots and issues the table-row copies ...
+__device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
+    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
+    constexpr unsigned ROWB = 4 * SB_NBETA * 8;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(5 * ROWB) : "memory");
+    if (lane >= 1 && lane < 6) {
+        double* sp = slotp + lane * 8;
+        const int j = sb_slot_locate(tb, fma(cc[lane], dt, t), jt, sp);
+        const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
+        if (lane == 5) *jend = j; // interval of t + dt: the next attempt's starting hint
+    }
+    __syncwarp();
+}
+// ... and the sweeping warps (split kernel: all but warp 0, which runs the eliminations meanwhile; warp kernel: the warp itself) wait for the rows and
+// sweep the slots, `widx` of `nw` each
+__device__ __forceinline__ void sb_split_basis_sweep(const SbLane& S, const double* kp, double* bs, double* bd5, const double* slotp, const double* tabs, unsigned ph, int lane, int widx, int nw) {
+    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
+    asm volatile("{\n .reg .pred p;\n SB_WAITS_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra SB_WAITS_%=;\n}" ::"r"(mbar), "r"(ph) : "memory");
+    double kk[SB_NBR];
+    int be[SB_NBR];
+#pragma unroll
+    for (int r = 0; r < SB_NBR; r++) { be[r] = SB_LO16(S.bp[r]); kk[r] = kp[SB_HI16(S.bp[r])]; }
+#pragma unroll
+    for (int s = 1; s < 6; s++) {
+        if ((s - 1) % nw != widx) continue;
+        const double* sp = slotp + s * 8;
+        const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
+        const double* n0 = tabs + s * 4 * SB_NBETA;
+#pragma unroll
+        for (int r = 0; r < SB_NBR; r++) {
+            const int m = r * 32 + lane;
+            if (m < SB_NB) {
+                const double v0 = n0[be[r]], d0 = n0[SB_NBETA + be[r]], v1 = n0[2 * SB_NBETA + be[r]], d1 = n0[3 * SB_NBETA + be[r]];
+                bs[s * SB_NB + m] = sb_hermite_val(kk[r], w1, v0, w2, d0, w3, v1, w4, d1);
+                if (s == 5) bd5[m] = sb_hermite_der(kk[r], sp[5], v0, v1, sp[6], d0, sp[7], d1); // the next attempt's slot 0 derivative, if this one is accepted
+            }
+        }
+    }
+}
+// Slot 0 (time t, value and derivative) from the table in global memory with the sweep's own expressions: for a mode that resumes a parked solve, whose
+// slot 0 an uninterrupted solve would have carried over from the previous attempt's last stage time (same values bit for bit).
+__device__ __forceinline__ int sb_basis_slot0(const SbLane& S, const SbTable& tb, double t, int jt, const double* kp, double* bs, double* bdv, double* slotp, int lane) {
+    int j = jt;
+    if (lane == 0) j = sb_slot_locate(tb, t, jt, slotp);
+    j = __shfl_sync(SB_FULL, j, 0);
+    __syncwarp();
+    const double* sp = slotp;
+    const double* n0 = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
+#pragma unroll
+    for (int r = 0; r < SB_NBR; r++) {
+        const int m = r * 32 + lane;
+        if (m < SB_NB) {
+            const int be = SB_LO16(S.bp[r]);
+            const double kk = kp[SB_HI16(S.bp[r])];
+            const double v0 = __ldg(n0 + be), d0 = __ldg(n0 + SB_NBETA + be), v1 = __ldg(n0 + 2 * SB_NBETA + be), d1 = __ldg(n0 + 3 * SB_NBETA + be);
+            bs[m] = sb_hermite_val(kk, sp[1], v0, sp[2], d0, sp[3], v1, sp[4], d1);
+            bdv[m] = sb_hermite_der(kk, sp[5], v0, v1, sp[6], d0, sp[7], d1);
+        }
+    }
+    __syncwarp();
+    return j;
+}
 // Initial state of a mode (generated closed-form initial conditions on the background at τini).  One compiled copy for every integrator kernel: inlined,
 // the several hundred generated expressions were contracted into FMAs differently in different kernels (nx = 8: two unknowns off by an ulp between the
 // warp-per-mode and the split kernel), and results must not depend on which kernel runs a mode.
@@ -1450,7 +1530,8 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             continue;
         }
         if (lane < 7) kp[lane] = pow(k, (double)(lane - 3));
-        SbController ctl; ctl.init();
+        const double lq0 = sb_ctl_lq0();
+        double lqold = lq0; // log2 of the controller's qold
         double dt = 0;
         int jt = 0, it0 = 0;
         bool parked = false;
@@ -1478,7 +1559,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             }
             const double* c = A.cont + (size_t)mode * SB_CONT;
             for (int i = lane; i < SB_N; i += SB_WARP) u[i] = __ldcg(c + i);
-            t = __ldcg(c + SB_N); dt = __ldcg(c + SB_N + 1); ctl.qold = __ldcg(c + SB_N + 2); ctl.q11 = __ldcg(c + SB_N + 3);
+            t = __ldcg(c + SB_N); dt = __ldcg(c + SB_N + 1); lqold = __ldcg(c + SB_N + 2);
             isave = (int)__ldcg(c + SB_N + 4); jt = (int)__ldcg(c + SB_N + 5); it0 = (int)__ldcg(c + SB_N + 6);
             wstart = isave & (SB_SWIN - 1); // the parking warp has stored the slots before isave of this window
             naccept = (long long)__ldcg(c + SB_N + 7); nreject = (long long)__ldcg(c + SB_N + 8); nf = (long long)__ldcg(c + SB_N + 9); nsolve = (long long)__ldcg(c + SB_N + 10);
@@ -1535,13 +1616,14 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
             }
             int jend = jt;       // interval of t + dt after the step (becomes jt on accept)
             bool moved = resume; // t advanced since f0, dT and the slot-0 basis were evaluated
+            bool have0 = !resume; // SB_DEFER: slot 0 of the basis (value and derivative at t) is in shared memory (carried over from the last stage time of the accepted step)
             for (int it = it0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
                 if (quota > 0 && moved && it - it0 >= quota) { // park: publish the continuation record
                     double* c = A.cont + (size_t)mode * SB_CONT;
                     for (int i = lane; i < SB_N; i += SB_WARP) c[i] = u[i];
                     if (lane == 0) {
-                        c[SB_N] = t; c[SB_N + 1] = dt; c[SB_N + 2] = ctl.qold; c[SB_N + 3] = ctl.q11; c[SB_N + 4] = isave; c[SB_N + 5] = jt; c[SB_N + 6] = it;
+                        c[SB_N] = t; c[SB_N + 1] = dt; c[SB_N + 2] = lqold; c[SB_N + 3] = 0; c[SB_N + 4] = isave; c[SB_N + 5] = jt; c[SB_N + 6] = it;
                         c[SB_N + 7] = (double)naccept; c[SB_N + 8] = (double)nreject; c[SB_N + 9] = (double)nf; c[SB_N + 10] = (double)nsolve;
                     }
                     if (SRC && (isave & (SB_SWIN - 1)) != 0) sb_source_flush(sbuf, Sout, A.nS, A.nsave, isave - 1, wstart, true, lane); // partial window of source values
@@ -1553,7 +1635,11 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 if (GROUP && closing) last = true; // dt = tend − t was set when the lockstep phase ended
                 else if (t + dt >= tend0 - 100 * 2.2e-16 * fabs(tend0)) { dtc = tend0 - t; dt = GROUP ? dtc : tend - t; last = true; }
                 // basis at the stage times of this attempt (one batched table look-up)
-#if SB_TMA
+#if SB_DEFER
+                if (moved && !have0) { jt = sb_basis_slot0(S, CC.tb, t, jt, kp, bs, bdv, kp + 8, lane); have0 = true; } // (a resumed mode: slot 0 is not in shared memory)
+                sb_split_basis_issue(CC.tb, t, dt, jt, kp + 8, tabs, reinterpret_cast<int*>(kp + 8), lane); // rows of the stage times 2..6: in flight during the factorisation
+                jend = reinterpret_cast<const int*>(kp + 8)[0];
+#elif SB_TMA
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar);
 #else
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
@@ -1587,6 +1673,11 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
                 const double idet = sb_rcp(m11 * m22 - m12 * m21);
                 const double idt = sb_rcp(dt);
+#if SB_DEFER
+                sb_split_basis_sweep(S, kp, bs, sm + SB_SM_BD5, kp + 8, tabs, tpar, lane, 0, 1); // the rows have arrived long ago: wait, Hermite sweep of slots 1..5
+                tpar ^= 1u;
+                __syncwarp();
+#endif
                 // 8 stages.  Per stage: (A) lane-local: finish k_{s-1} with its pending Woodbury correction and accumulate U_s = u + Σ a_sj k_j,
                 // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve.  The hub dot products of the
                 // rank-2 correction k_s += Z c and the correction itself are applied lazily in (A) of the next stage: no extra pass, no extra barrier.
@@ -1726,10 +1817,12 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
                 if (GROUP && closing) { if (!isfinite(EEst)) { rc = SB_RC_UNSTABLE; break; } EEst = fmin(EEst, 1.0); } // the closing step (O(δ) long) is taken as it is
                 if (!isfinite(EEst)) { nreject++; dt = dtc / 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
-                double q = ctl.q_of(EEst);
-                if (EEst > 1) { nreject++; dt = ctl.reject(dtc); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                const double lE = log2(EEst); // (−inf for EEst = 0: q = 1/qmax then, and qold falls back to its floor)
+                const double q = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, sb_ctl_q(lE, lqold) / 0.9));
+                if (EEst > 1) { nreject++; dt = dtc / fmin(5.0, sb_ctl_q11(lE) / 0.9); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
-                const double dtnew = ctl.accept(dtc, q, EEst);
+                const double dtnew = dtc / q;
+                lqold = fmax(lE, lq0); // qold = max(EEst, 1e-4)
                 const bool common = GROUP && !closing;                                   // lockstep phase: decisions on common data
                 const double tn = last ? (common ? tend0 : tend) : t + dt;
                 const double tn0 = common ? (last ? tend0 : t + dtc) : tn;
@@ -1758,6 +1851,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                         isave++;
                     }
                 }
+#if SB_DEFER
+                for (int m = lane; m < SB_NB; m += SB_WARP) { bs[m] = bs[5 * SB_NB + m]; bdv[m] = sm[SB_SM_BD5 + m]; } // the basis at the new time is the one of the last stage time (c = 1)
+#endif
                 for (int i = lane; i < SB_N; i += SB_WARP) { double un = U[i] + K[7 * SB_N + i]; if (isnan(un)) bad = true; u[i] = un; }
                 t = tn;
                 bad = __any_sync(SB_FULL, bad);
@@ -1814,9 +1910,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #define SB_HAVE_SPLIT 1
 static_assert(SB_J_F2 < 32 && SB_J_G0 < 32 && SB_J_G2 < 32, "the split kernel closes the source evaluation on the warp of round 0");
 #define SB_XS_SUM 8 // exchange area: ints [0] work index, [1] knot interval of t + dt; doubles [2..5] the controller warp's mailbox; [8 + r·32 + lane] per-lane terms of round r
-#define SB_XS_P1 2  // EEst^(7/50) of the current command
+#define SB_XS_P1 2  // answer: q11 / qold^β2 (accepted) or q11 (rejected) of the current command
 #define SB_XS_CMD 3 // command to the controller warp: the error estimate (NaN: exit)
-#define SB_XS_P2 4  // max(EEst, 1e-4)^(2/25), double-buffered by command parity
+#define SB_XS_P2 4  // [4] log2 qold posted with the command, [5] log2 EEst returned with the answer
 #define SB_XS_KC (SB_XS_SUM + 32 * SB_R)   // corrected stage vectors k_1..k_7, [7][SB_N]
 #define SB_XS_BD5 (SB_XS_KC + 7 * SB_N)    // derivative basis at the last stage time, [SB_NB]
 #define SB_XS_DOUBLES (SB_XS_BD5 + SB_NB)
@@ -1830,48 +1926,7 @@ __device__ __forceinline__ double sb_split_sumsq(double v, double* xs, int rb, i
     sb_rows_sync();
     return warp_sum(t);
 }
-// Basis at the stage times 2..6 of an attempt (slots 1..5; slot 0, the time t, is carried over from the previous attempt's last stage time).
-// One warp locates the slots and issues the table-row copies ...
-__device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
-    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
-    constexpr unsigned ROWB = 4 * SB_NBETA * 8;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(5 * ROWB) : "memory");
-    if (lane >= 1 && lane < 6) {
-        double* sp = slotp + lane * 8;
-        const int j = sb_slot_locate(tb, fma(cc[lane], dt, t), jt, sp);
-        const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
-        if (lane == 5) *jend = j; // interval of t + dt: the next attempt's starting hint
-    }
-    __syncwarp();
-}
-// ... and all warps but warp 0 (which runs the eliminations meanwhile) wait for the rows and sweep the slots, `widx` of SB_R − 1 each
 __device__ __forceinline__ void sb_split_bar_others() { asm volatile("bar.sync 1, %0;" ::"n"(SB_WARP * (SB_R - 1)) : "memory"); }
-__device__ __forceinline__ void sb_split_basis_sweep(const SbLane& S, const double* kp, double* bs, double* bd5, const double* slotp, const double* tabs, unsigned ph, int lane, int widx) {
-    const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
-    asm volatile("{\n .reg .pred p;\n SB_WAITS_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra SB_WAITS_%=;\n}" ::"r"(mbar), "r"(ph) : "memory");
-    double kk[SB_NBR];
-    int be[SB_NBR];
-#pragma unroll
-    for (int r = 0; r < SB_NBR; r++) { be[r] = SB_LO16(S.bp[r]); kk[r] = kp[SB_HI16(S.bp[r])]; }
-#pragma unroll
-    for (int s = 1; s < 6; s++) {
-        if ((s - 1) % (SB_R - 1) != widx) continue;
-        const double* sp = slotp + s * 8;
-        const double w1 = sp[1], w2 = sp[2], w3 = sp[3], w4 = sp[4];
-        const double* n0 = tabs + s * 4 * SB_NBETA;
-#pragma unroll
-        for (int r = 0; r < SB_NBR; r++) {
-            const int m = r * 32 + lane;
-            if (m < SB_NB) {
-                const double v0 = n0[be[r]], d0 = n0[SB_NBETA + be[r]], v1 = n0[2 * SB_NBETA + be[r]], d1 = n0[3 * SB_NBETA + be[r]];
-                bs[s * SB_NB + m] = sb_hermite_val(kk[r], w1, v0, w2, d0, w3, v1, w4, d1);
-                if (s == 5) bd5[m] = sb_hermite_der(kk[r], sp[5], v0, v1, sp[6], d0, sp[7], d1); // the next attempt's slot 0 derivative, if this one is accepted
-            }
-        }
-    }
-}
 __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel(const __grid_constant__ SbSolveArgs A) {
     constexpr bool SPL = true;
     extern __shared__ __align__(16) double sm_all[];
@@ -1891,22 +1946,18 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     if (warp == SB_R) {
-        // Controller warp.  The step controller (SbController::q_of) needs EEst^(7/50) -- 1.3 k cycles of one warp's time in pow() -- before the next step
-        // size is known, and max(EEst, 1e-4)^(2/25) for the step after that.  The row warps post EEst as soon as the error norm is formed (barrier 3) and go
-        // on with everything of an accepted step that does not depend on the new step size (dense output, state update, f0 and dT at the new time);
-        // they pick the power up at barrier 4.  NaN is the exit command.
-        int par = 0;
+        // Controller warp.  The step controller needs log2 EEst and an exp2 (sb_ctl_q) -- ≈0.6 k cycles of one warp's time -- before the next step size is
+        // known.  The row warps post (EEst, log2 qold) as soon as the error norm is formed (barrier 3) and go on with everything of an accepted step that does
+        // not depend on the new step size (dense output, state update, f0 and dT at the new time); they pick the answer up at barrier 4.  NaN is the exit command.
         while (true) {
             asm volatile("bar.sync 3, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
-            const double E = xs[SB_XS_CMD];
+            const double E = xs[SB_XS_CMD], lq = xs[SB_XS_P2];
             if (E != E) break;
-            const double p1 = pow(E, 7.0 / 50.0);
-            if (lane == 0) xs[SB_XS_P1] = p1;
+            const double l = log2(E);
+            const double r = (E > 1) ? sb_ctl_q11(l) : sb_ctl_q(l, lq);
+            if (lane == 0) { xs[SB_XS_P1] = r; xs[SB_XS_P2 + 1] = l; }
             __threadfence_block();
             asm volatile("bar.arrive 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
-            const double p2 = pow(fmax(E, 1e-4), 2.0 / 25.0);
-            if (lane == 0) xs[SB_XS_P2 + par] = p2;
-            par ^= 1;
         }
         return;
     }
@@ -1914,12 +1965,10 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
     const bool SRC = A.S != nullptr;
     SbLane S;
     S.load_split(lane, rb);
-    int cpar = 0; // parity of the next command to the controller warp
-    auto ctl_send = [&](double E) {
-        if (tid == 0) xs[SB_XS_CMD] = E;
+    auto ctl_send = [&](double E, double lq) {
+        if (tid == 0) { xs[SB_XS_CMD] = E; xs[SB_XS_P2] = lq; }
         __threadfence_block();
         asm volatile("bar.arrive 3, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
-        cpar ^= 1;
     };
     const SbCosmo& CC = A.c0;
     const int i0 = rb * 32 + lane;         // this thread's row
@@ -1931,7 +1980,7 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
         if (tid == 0) reinterpret_cast<int*>(xs)[0] = atomicAdd(A.queue, 1);
         sb_rows_sync();
         const int qi = reinterpret_cast<const int*>(xs)[0];
-        if (qi >= A.nk) { ctl_send(NAN); break; }
+        if (qi >= A.nk) { ctl_send(NAN, 0.0); break; }
         const int mode = A.order ? A.order[qi] : qi;
         const double k = A.ks[mode];
         double t = A.tini[mode];
@@ -1948,7 +1997,8 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
             continue;
         }
         if (tid < 7) kp[tid] = pow(k, (double)(tid - 3));
-        SbController ctl; ctl.init();
+        const double lq0 = sb_ctl_lq0();
+        double lqold = lq0; // log2 of the controller's qold
         double dt = 0;
         int jt = 0;
         if (tid == 0) sb_initial_state(CC.spl, CC.P, t, k, U); // natural order
@@ -2028,21 +2078,16 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
             }
             int jend = jt;
             bool moved = false;
-            double qoldp; // the controller's power of the previous error estimate, carried along (see below)
-            { double q0 = ctl.qold; asm volatile("" : "+d"(q0)); qoldp = pow(q0, 2.0 / 25.0); } // (opaque argument: evaluated by the device routine like every later one, not folded at compile time)
             bool pend = false;  // the controller's answer to the last accepted step is still outstanding (dt holds that step's size meanwhile)
             double Epend = 0;   // its error estimate
-            int pslot = 0, qslot = -1; // mailbox slot of the pending command's second power; slot from which qoldp is due
-            // the controller's answer: the new step size after an accepted (dt / q) or a rejected step, exactly as SbController computes it
+            // the controller's answer: the new step size after an accepted (dt / q) or a rejected step, the same expressions as sb_integrate_kernel
             auto ctl_resolve = [&](double E, bool rejected, double dtstep) {
                 asm volatile("bar.sync 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
-                if (qslot >= 0) { qoldp = xs[SB_XS_P2 + qslot]; qslot = -1; } // (of the last accepted step before this one: written before the controller warp took this command)
-                const double pw1 = xs[SB_XS_P1];
-                double q = 0.1;
-                if (E != 0.0) { ctl.q11 = pw1; q = fmax(0.1, fmin(5.0, (pw1 / qoldp) / 0.9)); }
-                if (rejected) return ctl.reject(dtstep);
-                qslot = pslot;
-                return ctl.accept(dtstep, q, E);
+                const double r = xs[SB_XS_P1], lE = xs[SB_XS_P2 + 1];
+                if (rejected) return dtstep / fmin(5.0, r / 0.9);
+                const double q = (E == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, r / 0.9));
+                lqold = fmax(lE, lq0); // qold = max(EEst, 1e-4)
+                return dtstep / q;
             };
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
@@ -2069,7 +2114,7 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
                 if (!w0) {
                     if (warp == 1) sb_split_basis_issue(CC.tb, t, dt, jt, kp + 8, tabs, reinterpret_cast<int*>(xs) + 1, lane);
                     sb_split_bar_others(); // slot descriptors visible to the sweeping warps
-                    sb_split_basis_sweep(S, kp, bs, xs + SB_XS_BD5, kp + 8, tabs, tpar, lane, warp - 1);
+                    sb_split_basis_sweep(S, kp, bs, xs + SB_XS_BD5, kp + 8, tabs, tpar, lane, warp - 1, SB_R - 1);
                 }
                 tpar ^= 1u;
                 sb_rows_sync();
@@ -2157,13 +2202,13 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (has) mm[i0] = 0; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; } // (0·NaN may sit in structurally-zero slots)
                 if (EEst > 1) { // rejected: nothing to overlap, the answer is needed at once
                     nreject++;
-                    pslot = cpar; ctl_send(EEst);
+                    ctl_send(EEst, lqold);
                     dt = ctl_resolve(EEst, true, dt);
                     if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; }
                     continue;
                 }
                 naccept++;
-                if (!last) { pslot = cpar; ctl_send(EEst); pend = true; Epend = EEst; } // the new step size is picked up after f0, dT of the next attempt
+                if (!last) { ctl_send(EEst, lqold); pend = true; Epend = EEst; } // the new step size is picked up after f0, dT of the next attempt
                 const double tn = last ? tend : t + dt;
                 const double un_ = has ? U[i0] + k8 : 0.0;
                 if (isave < A.nsave && CC.saveat[isave] <= tn) { // dense output (4th order)
