@@ -441,3 +441,19 @@ def test_oracle_kencarp4_tableau_and_convergence(oracle):
         assert (sol["retcode"] == 0).all()
         errs.append(np.abs(P / Pt - 1).max())
     assert errs[0] < 2e-3 and errs[1] < 2e-5 and errs[1] < 0.05 * errs[0], errs
+
+
+def test_schedule_with_costs_in_other_units_and_ptalg(sb):
+    """`build_schedule(cost, nlists, attempts=...)`: costs in any unit (e.g. measured time per mode); the quota of a split-off piece is converted to attempts with
+    the mode's own attempts per unit of cost, so a cost vector scaled by a constant yields the same schedule.  `ptalg` mirrors src/solve.jl:326-341."""
+    rng = np.random.default_rng(5)
+    att = rng.integers(200, 3000, 500).astype(float)
+    a_items, a_ibeg, _ = sb.build_schedule(att, 64)
+    b_items, b_ibeg, _ = sb.build_schedule(att * 17.3e-6, 64, attempts=att)  # "seconds" instead of attempts
+    assert np.array_equal(a_ibeg, b_ibeg) and np.array_equal(a_items[:, [0, 2]], b_items[:, [0, 2]])
+    assert np.abs(a_items[:, 1] - b_items[:, 1]).max() <= 1  # quotas agree up to rounding
+    for items, ibeg in ((a_items, a_ibeg), (b_items, b_ibeg)):
+        first = items[items[:, 2] == 0]
+        assert sorted(first[:, 0].tolist()) == list(range(500))
+        assert ((first[:, 1] == 0) | (first[:, 1] < att[first[:, 0]])).all()
+    assert [sb.ptalg(None, a) for a in (0, 1, 2, 3)] == ["TRBDF2", "KenCarp4", "Rodas5P", "Rodas5P"]
