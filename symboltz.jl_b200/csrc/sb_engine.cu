@@ -799,6 +799,9 @@ __device__ __forceinline__ void sb_eval_dT(const SbLane& S, const double* b, con
 }
 
 
+#if defined(SB_WARP_PROF) && !defined(SB_SPLIT_PROF)
+#define SB_SPLIT_PROF 1
+#endif
 #ifdef SB_SPLIT_PROF
 // cycle accounting of one attempt by phase (debug builds only: scripts/split_prof.py); slot i = cycles between mark i-1 and mark i, thread 0 of each CTA
 __device__ unsigned long long sb_split_prof[24];
@@ -807,9 +810,15 @@ __device__ unsigned long long sb_split_prof[24];
 #define SB_PROF_PARM , unsigned long long* pf_ = nullptr, long long* pcp_ = nullptr
 #define SB_PROF_PASS , pf_, &pc_
 #define SB_PROF_F(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - *pcp_); *pcp_ = c_; }
+#ifdef SB_WARP_PROF
+#define SB_WPROF(i) if (!BATCH && !GROUP) SB_PROF(i)
+#else
+#define SB_WPROF(i)
+#endif
 #define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 20; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[20], (unsigned long long)(naccept + nreject)); }
 #else
 #define SB_PROF_DECL
+#define SB_WPROF(i)
 #define SB_PROF_PARM
 #define SB_PROF_PASS
 #define SB_PROF_F(i)
@@ -1344,13 +1353,17 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
 __device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
     const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
     constexpr unsigned ROWB = 4 * SB_NBETA * 8;
+#ifndef SB_EXP_NOFENCE
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the previous attempt's generic-proxy reads of the staging area come first
+#endif
     if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(5 * ROWB) : "memory");
     if (lane >= 1 && lane < 6) {
         double* sp = slotp + lane * 8;
         const int j = sb_slot_locate(tb, fma(cc[lane], dt, t), jt, sp);
         const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
+#ifndef SB_EXP_NOCOPY
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
+#endif
         if (lane == 5) *jend = j; // interval of t + dt: the next attempt's starting hint
     }
     __syncwarp();
@@ -1456,6 +1469,10 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #endif
     const double reltol = A.reltol, abstol = A.abstol;
     const bool SRC = A.S != nullptr; // fused source evaluation at the save times (scratch: di = state in natural order, up = its derivative, bs = basis)
+#ifdef SB_WARP_PROF
+    SB_PROF_DECL // (debug builds: cycle account of the attempt by phase, scripts/warp_prof.py)
+    const int tid = threadIdx.x;
+#endif
     SbLane S;
     S.load(lane);
     const SbCosmo& CC = *(BATCH ? reinterpret_cast<const SbCosmo*>(sm + SB_SM_COSMO) : &A.c0);
@@ -1630,6 +1647,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                     parked = true;
                     break;
                 }
+                SB_WPROF(0)
                 bool last = false;
                 double dtc = dt; // the step as the (shared) controller sees it; dt is what this lane integrates over (differs only on the last step of a GROUP lane)
                 if (GROUP && closing) last = true; // dt = tend − t was set when the lockstep phase ended
@@ -1645,9 +1663,12 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane);
 #endif
                 __syncwarp();
+                SB_WPROF(1)
                 if (moved) { sb_eval_f<false>(S, bs, u, f0, lane); nf++; sb_eval_dT(S, bs, bdv, u, dT, lane); moved = false; }
+                SB_WPROF(2)
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
                 sb_factor(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane);
+                SB_WPROF(3)
 #pragma unroll
                 for (int r = 0; r < SB_R; r++) {
                     const int i = r * 32 + lane;
@@ -1673,11 +1694,13 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 m11 = 1 - m11; m12 = -m12; m21 = -m21; m22 = 1 - m22;
                 const double idet = sb_rcp(m11 * m22 - m12 * m21);
                 const double idt = sb_rcp(dt);
+                SB_WPROF(4)
 #if SB_DEFER
                 sb_split_basis_sweep(S, kp, bs, sm + SB_SM_BD5, kp + 8, tabs, tpar, lane, 0, 1); // the rows have arrived long ago: wait, Hermite sweep of slots 1..5
                 tpar ^= 1u;
                 __syncwarp();
 #endif
+                SB_WPROF(5)
                 // 8 stages.  Per stage: (A) lane-local: finish k_{s-1} with its pending Woodbury correction and accumulate U_s = u + Σ a_sj k_j,
                 // R_s = Σ (C_sj/dt) k_j; (B) f(U_s) with the right-hand side assembled in the same pass; (C) B-solve.  The hub dot products of the
                 // rank-2 correction k_s += Z c and the correction itself are applied lazily in (A) of the next stage: no extra pass, no extra barrier.
@@ -1760,7 +1783,9 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #pragma unroll
                         for (int r = 0; r < SB_R; r++) if (r * 32 + lane < SB_N) U[ii[r]] = ua[r];
                         __syncwarp();
+                        SB_WPROF(6)
                         sb_eval_f<true>(S, bs + cslot[s] * SB_NB, U, ks, lane, Racc, hd_, dT); nf++;
+                        SB_WPROF(7)
                     } else {
 #if SB_Z3
                         continue; // solved together with Z
@@ -1771,6 +1796,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #endif
                     }
                     { double* const k1[1] = {ks}; sb_bsolve<1>(S, k1, di, up, mm, blk, lane); } nsolve++;
+                    SB_WPROF(8)
                 }
                 {
                     double s1, s2;
@@ -1814,6 +1840,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es = fma(r, r, es); }
 #endif
                 double EEst = sqrt(warp_sum(es) / SB_N);
+                SB_WPROF(9)
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
                 if (GROUP && closing) { if (!isfinite(EEst)) { rc = SB_RC_UNSTABLE; break; } EEst = fmin(EEst, 1.0); } // the closing step (O(δ) long) is taken as it is
                 if (!isfinite(EEst)) { nreject++; dt = dtc / 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
@@ -1823,6 +1850,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 naccept++;
                 const double dtnew = dtc / q;
                 lqold = fmax(lE, lq0); // qold = max(EEst, 1e-4)
+                SB_WPROF(10)
                 const bool common = GROUP && !closing;                                   // lockstep phase: decisions on common data
                 const double tn = last ? (common ? tend0 : tend) : t + dt;
                 const double tn0 = common ? (last ? tend0 : t + dtc) : tn;
@@ -1866,8 +1894,12 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 dt = dtnew;
                 jt = jend;
                 moved = true;
+                SB_WPROF(11)
             }
         }
+#ifdef SB_WARP_PROF
+        if (!BATCH && !GROUP) { SB_PROF_OUT }
+#endif
         if (parked) {
             __threadfence();
             __syncwarp();
