@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-for v in wprof wprof_nofence; do timeout 600 python scripts/warp_prof.py scripts/variants/$v.so 2>&1 | head -4 | cut -c1-150; done
+timeout 600 python scripts/warp_prof.py scripts/variants/wprof.so > gpurun_out/warp_prof_r3l.txt 2>&1; head -16 gpurun_out/warp_prof_r3l.txt | cut -c1-170

@@ -625,13 +625,15 @@ __device__ __forceinline__ int sb_basis_at(const SbLane& S, const SbTable& tb, d
 // (v0, d0, v1, d1), plus the derivative weights, into sp[0..7]; returns the knot interval.
 __device__ __forceinline__ int sb_slot_locate(const SbTable& tb, double tau, int j, double* sp) {
     while (j < tb.nb - 2 && __ldg(tb.t + j + 1) <= tau) j++;
-    const double tj = __ldg(tb.t + j), hs = (__ldg(tb.t + j + 1) - tj) / tb.msub;
-    const double f = (tau - tj) / hs;
+    // (Newton reciprocals instead of three dependent IEEE divisions: the search sits at the head of every attempt)
+    const double tj = __ldg(tb.t + j), dtj = __ldg(tb.t + j + 1) - tj;
+    const double hs = dtj * sb_rcp((double)tb.msub), ihs = (double)tb.msub * sb_rcp(dtj);
+    const double f = (tau - tj) * ihs;
     const int sidx = max(0, min((int)f, tb.msub - 1));
     const double w = f - sidx, w1 = w - 1.0;
     sp[0] = __longlong_as_double((long long)j * tb.msub + sidx);
     sp[1] = (1 + 2 * w) * w1 * w1; sp[2] = w * w1 * w1 * hs; sp[3] = w * w * (3 - 2 * w); sp[4] = w * w * w1 * hs;
-    sp[5] = 6 * w * w1 / hs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
+    sp[5] = 6 * w * w1 * ihs; sp[6] = (3 * w - 1) * w1; sp[7] = w * (3 * w - 2);
     return j;
 }
 __device__ __forceinline__ double sb_hermite_val(double kk, double w1, double v0, double w2, double d0, double w3, double v1, double w4, double d1) { return kk * (w1 * v0 + w2 * d0 + w3 * v1 + w4 * d1); }
@@ -812,13 +814,17 @@ __device__ unsigned long long sb_split_prof[24];
 #define SB_PROF_F(i) { const long long c_ = clock64(); pf_[i] += (unsigned long long)(c_ - *pcp_); *pcp_ = c_; }
 #ifdef SB_WARP_PROF
 #define SB_WPROF(i) if (!BATCH && !GROUP) SB_PROF(i)
+#define SB_WPROF_PASS , ((!BATCH && !GROUP) ? pf_ : nullptr), &pc_
 #else
 #define SB_WPROF(i)
+#define SB_WPROF_PASS
 #endif
-#define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 20; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[20], (unsigned long long)(naccept + nreject)); }
+#define SB_PROF_OUT if (tid == 0) { for (int i_ = 0; i_ < 16; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } atomicAdd(&sb_split_prof[20], (unsigned long long)(naccept + nreject)); } \
+    if (tid == 1) { for (int i_ = 16; i_ < 20; i_++) { atomicAdd(&sb_split_prof[i_], pf_[i_]); pf_[i_] = 0; } } /* (slots 16..19: marks taken on thread 1) */
 #else
 #define SB_PROF_DECL
 #define SB_WPROF(i)
+#define SB_WPROF_PASS
 #define SB_PROF_PARM
 #define SB_PROF_PASS
 #define SB_PROF_F(i)
@@ -1350,7 +1356,7 @@ __device__ __forceinline__ void sb_source_point(const SbLane& S, const double* _
 // Deferred form of sb_basis_batch (SB_DEFER; warp-per-mode and split kernel): the rows are requested at the start of the attempt, the factorisation and the
 // first solve need slot 0 only, and the wait + sweep come right before the first stage evaluation -- the L2 latency of the copies (≈1.5 k cycles, 6 % of a lone
 // warp's attempt) is off the dependent chain.  One warp locates the slots and issues the table-row copies ...
-__device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane) {
+__device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t, double dt, int jt, double* slotp, double* tabs, int* jend, int lane SB_PROF_PARM) {
     const unsigned mbar = sb_smem_u32(tabs + 6 * 4 * SB_NBETA);
     constexpr unsigned ROWB = 4 * SB_NBETA * 8;
 #ifndef SB_EXP_NOFENCE
@@ -1361,10 +1367,16 @@ __device__ __forceinline__ void sb_split_basis_issue(const SbTable& tb, double t
         double* sp = slotp + lane * 8;
         const int j = sb_slot_locate(tb, fma(cc[lane], dt, t), jt, sp);
         const double* src = tb.tab + (size_t)__double_as_longlong(sp[0]) * 2 * SB_NBETA;
+#ifdef SB_WARP_PROF
+        if (pf_ && lane == 1) { SB_PROF_F(16) } // (debug: the search is done)
+#endif
 #ifndef SB_EXP_NOCOPY
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb_smem_u32(tabs + lane * 4 * SB_NBETA)), "l"(src), "r"(ROWB), "r"(mbar) : "memory");
 #endif
         if (lane == 5) *jend = j; // interval of t + dt: the next attempt's starting hint
+#ifdef SB_WARP_PROF
+        if (pf_ && lane == 1) { SB_PROF_F(17) } // (debug: the copies are issued)
+#endif
     }
     __syncwarp();
 }
@@ -1655,7 +1667,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 // basis at the stage times of this attempt (one batched table look-up)
 #if SB_DEFER
                 if (moved && !have0) { jt = sb_basis_slot0(S, CC.tb, t, jt, kp, bs, bdv, kp + 8, lane); have0 = true; } // (a resumed mode: slot 0 is not in shared memory)
-                sb_split_basis_issue(CC.tb, t, dt, jt, kp + 8, tabs, reinterpret_cast<int*>(kp + 8), lane); // rows of the stage times 2..6: in flight during the factorisation
+                sb_split_basis_issue(CC.tb, t, dt, jt, kp + 8, tabs, reinterpret_cast<int*>(kp + 8), lane SB_WPROF_PASS); // rows of the stage times 2..6: in flight during the factorisation
                 jend = reinterpret_cast<const int*>(kp + 8)[0];
 #elif SB_TMA
                 jend = sb_basis_batch(S, CC.tb, t, dt, jt, moved, kp, bs, bdv, kp + 8, lane, tabs, &tpar);
