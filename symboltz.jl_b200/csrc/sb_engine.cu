@@ -511,6 +511,12 @@ __device__ __forceinline__ double sb_rcp(double x) {
     return 1.0 / x;
 #endif
 }
+// Scalar pieces of the attempt's tail, shared by the kernels, with multiplications by reciprocals where the reference formula divides (each IEEE division is a
+// ~200-cycle dependent chain on a lone warp; the constants differ from the quotients by at most an ulp)
+__device__ __forceinline__ double sb_ctl_qacc(double r) { return fmax(0.1, fmin(5.0, r * (1.0 / 0.9))); }   // clamp(q / γ_c) of an accepted step
+__device__ __forceinline__ double sb_ctl_qrej(double r11) { return fmin(5.0, r11 * (1.0 / 0.9)); }           // min(1/qmin, q11 / γ_c) of a rejected step
+__device__ __forceinline__ double sb_rms(double sumsq) { return sqrt(sumsq * (1.0 / SB_N)); }                // RMS norm from the sum of squares
+__device__ __forceinline__ double sb_wdiag(double dt) { return sb_rcp(SB_R5_GAMMA * dt); }                   // 1 / (γ dt)
 __device__ __forceinline__ unsigned sb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -1679,7 +1685,7 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
                 if (moved) { sb_eval_f<false>(S, bs, u, f0, lane); nf++; sb_eval_dT(S, bs, bdv, u, dT, lane); moved = false; }
                 SB_WPROF(2)
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ
-                sb_factor(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane);
+                sb_factor(S, sb_wdiag(dt), bs, di, up, mm, blk, lane);
                 SB_WPROF(3)
 #pragma unroll
                 for (int r = 0; r < SB_R; r++) {
@@ -1851,16 +1857,16 @@ __global__ void __launch_bounds__(GROUP ? SB_WARP * SB_GROUP_MAX : SB_WARP * SB_
 #else
                 for (int i = lane; i < SB_N; i += SB_WARP) { double k8 = K[7 * SB_N + i], un = U[i] + k8; double r = k8 / (abstol + reltol * fmax(fabs(u[i]), fabs(un))); es = fma(r, r, es); }
 #endif
-                double EEst = sqrt(warp_sum(es) / SB_N);
+                double EEst = sb_rms(warp_sum(es));
                 SB_WPROF(9)
                 if (A.trace && mode == 0 && lane == 0 && it < A.ntrace) { A.trace[3 * it] = t; A.trace[3 * it + 1] = dt; A.trace[3 * it + 2] = EEst; }
                 if (GROUP && closing) { if (!isfinite(EEst)) { rc = SB_RC_UNSTABLE; break; } EEst = fmin(EEst, 1.0); } // the closing step (O(δ) long) is taken as it is
                 if (!isfinite(EEst)) { nreject++; dt = dtc / 5; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; }
                 const double lE = log2(EEst); // (−inf for EEst = 0: q = 1/qmax then, and qold falls back to its floor)
-                const double q = (EEst == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, sb_ctl_q(lE, lqold) / 0.9));
-                if (EEst > 1) { nreject++; dt = dtc / fmin(5.0, sb_ctl_q11(lE) / 0.9); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
+                const double q = (EEst == 0.0) ? 0.1 : sb_ctl_qacc(sb_ctl_q(lE, lqold));
+                if (EEst > 1) { nreject++; dt = dtc * sb_rcp(sb_ctl_qrej(sb_ctl_q11(lE))); if (dt < 1e-15 * fabs(t)) { rc = SB_RC_DTMIN; break; } continue; }
                 naccept++;
-                const double dtnew = dtc / q;
+                const double dtnew = dtc * sb_rcp(q);
                 lqold = fmax(lE, lq0); // qold = max(EEst, 1e-4)
                 SB_WPROF(10)
                 const bool common = GROUP && !closing;                                   // lockstep phase: decisions on common data
@@ -2128,10 +2134,10 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
             auto ctl_resolve = [&](double E, bool rejected, double dtstep) {
                 asm volatile("bar.sync 4, %0;" ::"n"(SB_SPLIT_THREADS) : "memory");
                 const double r = xs[SB_XS_P1], lE = xs[SB_XS_P2 + 1];
-                if (rejected) return dtstep / fmin(5.0, r / 0.9);
-                const double q = (E == 0.0) ? 0.1 : fmax(0.1, fmin(5.0, r / 0.9));
+                if (rejected) return dtstep * sb_rcp(sb_ctl_qrej(r));
+                const double q = (E == 0.0) ? 0.1 : sb_ctl_qacc(r);
                 lqold = fmax(lE, lq0); // qold = max(EEst, 1e-4)
-                return dtstep / q;
+                return dtstep * sb_rcp(q);
             };
             for (int it = 0;; it++) {
                 if (it >= A.maxiters) { rc = SB_RC_MAXITERS; break; }
@@ -2150,7 +2156,7 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
                 SB_PROF(10)
                 // factor W = I/(γ dt) − J(t) = B − p φᵀ − q ψᵀ: rows by all warps, eliminations by warp 0.  Meanwhile the other warps set up Z and the
                 // stage-1 right-hand side and bring in the basis at the stage times 2..6 (table rows by TMA, Hermite sweep): none of it is on warp 0's path.
-                sb_factor<SPL>(S, 1.0 / (SB_R5_GAMMA * dt), bs, di, up, mm, blk, lane, rb, w0 SB_PROF_PASS);
+                sb_factor<SPL>(S, sb_wdiag(dt), bs, di, up, mm, blk, lane, rb, w0 SB_PROF_PASS);
                 if (has) {
                     Zp[i0] = S.pqc[0] * bs[SB_LO16(S.pqi[0])]; Zq[i0] = S.pqc[1] * bs[SB_HI16(S.pqi[0])];
                     K[i0] = f0[i0] + dt * cd[0] * dT[i0];
@@ -2241,7 +2247,7 @@ __global__ void __launch_bounds__(SB_SPLIT_THREADS, 1) sb_integrate_split_kernel
                     es = k8 / (abstol + reltol * fmax(fabs(u[i0]), fabs(un)));
 #endif
                 }
-                const double EEst = sqrt(sb_split_sumsq(es, xs, rb, lane) / SB_N);
+                const double EEst = sb_rms(sb_split_sumsq(es, xs, rb, lane));
                 SB_PROF(9)
                 if (!isfinite(EEst)) { nreject++; dt /= 5; if (has) mm[i0] = 0; if (dt < 1e-15 * fabs(t)) { rc = SB_RC_UNSTABLE; break; } continue; } // (0·NaN may sit in structurally-zero slots)
                 if (EEst > 1) { // rejected: nothing to overlap, the answer is needed at once
