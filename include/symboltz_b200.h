@@ -144,7 +144,7 @@ int sbm_solvept_batch_src(int ncosmo, const void* dcosmos, int nk, const double*
 int sbm_solvept_lanes(int ncosmo, const void* dcosmos, int nk, const double* dks, const double* dtini, const int* dcosmo_of, const int* dorder, int nsave, double reltol,
                       double abstol, int maxiters, double* dusave, double* duend, int* dretcode, long long* dstats, int* dqueue, const double* invdelta, double tend_common,
                       void* stream, const sbm_src_t* src);
-/* The single-cosmology solve with ONE CTA per mode ("one CTA per k-mode": SB_R row warps + one warp that computes the step controller's powers) instead of one warp per mode: for launches with no
+/* The single-cosmology solve with ONE CTA per mode ("one CTA per k-mode": SB_R row warps + one warp that evaluates the step controller) instead of one warp per mode: for launches with no
  * more modes than sbm_split_capacity() (BASELINE config 1: 100 modes; the default 61-node C_l path), where the warp-per-mode mapping leaves
  * most of the GPU idle and the run time is the slowest mode's sequential attempts.  The row-parallel phases of an attempt (basis sweep,
  * Jacobian scatter, f-evaluations, stage combinations, error norm, dense output) are spread over the warps, the first solve's three
