@@ -27,6 +27,9 @@
 // pinned against the reference's own golden vectors test/class_Pk.dat and test/class_Cl.dat
 // (test/runtests.jl:872-886) at the reference's own tolerances -- see tests/test_oracle_golden.py.
 // Step-level behaviour of OrdinaryDiffEq is "parity unpinned" (no fixture exists).
+// The alternative integrators TRBDF2 and KenCarp4 (reference ptalg(accuracy = 0 / 1), src/solve.jl:333-337) are restatements of the PUBLISHED schemes
+// (OrdinaryDiffEqSDIRK is an un-vendored dependency): "parity unpinned" against Julia's step selection; they are anchored on the CLASS-pinned Rodas5P
+// result (convergence at the methods' orders, tests/test_host_cpu.py) and on the tableau's order conditions.
 // =====================================================================================
 #include <algorithm>
 #include <cmath>
