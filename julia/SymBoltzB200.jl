@@ -15,7 +15,10 @@ module SymBoltzB200
 
 using SymBoltz, CUDA   # CUDA.jl is used only as a device allocator (CuArray / CuPtr); all kernels live in the shared libraries
 
-struct B200Rodas5P end  # marker algorithm type
+struct B200Rodas5P end  # marker algorithm types: dispatch targets for `solvept(...; alg = ...)` / `ptalg(prob; accuracy)` (src/solve.jl:326-341)
+struct B200KenCarp4 end # accuracy = 1
+struct B200TRBDF2 end   # accuracy = 0
+const B200Alg = Union{B200Rodas5P, B200KenCarp4, B200TRBDF2}
 
 const RETCODE = Dict(0 => :Success, 1 => :MaxIters, 2 => :DtLessThanMin, 3 => :Unstable, 4 => :ScheduleTimeout)
 
@@ -66,7 +69,7 @@ end
 `solvept` on the staged (device-pointer) level: upload knots -> `sbm_build_table` -> `sbm_solvept_src` (sources formed inside the
 integrator at `saveat` when `sources = true`, the reference's output_func of source_grid, src/observables/fourier.jl:272-278).
 """
-function SymBoltz.solvept(ptprob, bgsol, ks::AbstractArray, ptivini, ::B200Rodas5P; lib, reltol = 1e-5, abstol = 1e-5, saveat = Float64[], maxiters = 100_000, msub = 16,
+function SymBoltz.solvept(ptprob, bgsol, ks::AbstractArray, ptivini, alg::B200Alg; lib, reltol = 1e-5, abstol = 1e-5, saveat = Float64[], maxiters = 100_000, msub = 16,
                           sources = false, scale_k = true, τrec = 0.0, P)
     info = model_info(lib); N = info.N
     ts = bgsol.t; nb = length(ts); nk = length(ks); ns = length(saveat)
@@ -91,7 +94,14 @@ function SymBoltz.solvept(ptprob, bgsol, ks::AbstractArray, ptivini, ::B200Rodas
         end
         srcp = (sources && ns > 0) ? src : C_NULL
         # few modes (config 1, the default 61-node C_l path): one CTA per mode, same results bit for bit, about half the latency
-        if 0 < nk <= ccall((:sbm_split_capacity, lib), Cint, ())
+        if !(alg isa B200Rodas5P)  # the ESDIRK integrators: one warp per mode, same argument list as the split entry point
+            sym = alg isa B200KenCarp4 ? :sbm_solvept_kencarp4 : :sbm_solvept_trbdf2
+            rc = ccall((sym, lib), Cint,
+                       (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, CuPtr{Int32}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64},
+                        CuPtr{Int32}, Cdouble, Cint, CuPtr{Float64}, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, Ptr{Cvoid}, Ptr{SbmSrc}),
+                       dP, nb, dt, dy_, ddy, msub, length(lut), s0, dsl, dlut, dtab, nk, dks, dtini, dorder, ts[end], ns, dsave, reltol, abstol, maxiters,
+                       CU_NULL, duend, dret, dstats, dqueue, st, srcp)
+        elseif 0 < nk <= ccall((:sbm_split_capacity, lib), Cint, ())
             rc = ccall((:sbm_solvept_split, lib), Cint,
                        (CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cint, Cint, Cdouble, Cdouble, CuPtr{Int32}, CuPtr{Float64}, Cint, CuPtr{Float64}, CuPtr{Float64},
                         CuPtr{Int32}, Cdouble, Cint, CuPtr{Float64}, Cdouble, Cdouble, Cint, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Int32}, CuPtr{Int64}, CuPtr{Int32}, Ptr{Cvoid}, Ptr{SbmSrc}),
