@@ -806,3 +806,19 @@ def test_kencarp4_matches_oracle_and_converges_to_rodas5p(sb, oracle, prob5, bg5
     with np.errstate(invalid="ignore"):
         assert (np.abs(A - B)[:, :, :-1] <= 2e-4 * scale).all(), (np.abs(A - B)[:, :, :-1] / scale).max()
     assert np.abs(a.usave - b.usave).max() <= 2e-4 * np.abs(a.usave).max()
+
+
+@pytest.mark.gpu
+def test_esdirk_integrators_on_the_other_model_structures(sb):
+    """KenCarp4 / TRBDF2 on the w0waCDM model of config 4 and on larger systems (nx = 8: N = 126; lmax = 32: N = 236, long elimination paths): success and
+    agreement of the final states with a converged Rodas5P solve."""
+    ks = np.array([0.7, 30.0, 400.0])
+    for M in (sb.w0waCDM(lmax=10), sb.ΛCDM(lmax=10, nx=8), sb.ΛCDM(lmax=32)):
+        prob = sb.CosmologyProblem(M, sb.parameters_Planck18(M))
+        bg = sb.solvebg(prob)
+        ref = sb.solvept(prob, bg, ks, reltol=1e-9, abstol=1e-9)
+        scale = np.abs(ref.uend).max(axis=1, keepdims=True)
+        for alg, tol, bound in (("KenCarp4", 1e-7, 1e-5), ("TRBDF2", 1e-7, 2e-5)):  # measured ≤ 3.6e-6 / ≤ 7.1e-6 (scripts/esdirk_models.py)
+            s = sb.solvept(prob, bg, ks, reltol=tol, abstol=tol, alg=alg)
+            assert s.success, (M, alg, s.retcode)
+            assert (np.abs(s.uend - ref.uend) <= bound * scale).all(), (M, alg, (np.abs(s.uend - ref.uend) / scale).max())
