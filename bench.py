@@ -421,7 +421,7 @@ def run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl, model=
                     torch.cuda.synchronize()
                     ts.append(maxtime(time.perf_counter() - t0))
             ex["strong_single_cosmology"] = {"workload": "the headline cosmology's C_l with its ~2020 modes strided over the ranks: NCCL all-reduce (disjoint supports = all-gather) of S[nk][2][300] (9.7 MB), LOS on contiguous fine-k slices, NCCL all-reduce of the partial C_l sums [3][129]",
-                                             "ms": 1e3 * float(np.median(ts)), "ranks": world, "modes_per_rank": nk_rank, "work_distribution": ("one CTA per mode (split kernel)" if nk_rank <= sb.split_capacity(prob0) else "atomic queue, one warp per mode"),
+                                             "ms": 1e3 * float(np.median(ts)), "ranks": world, "modes_per_rank": nk_rank, "work_distribution": ("one CTA per mode (split kernel)" if sb.split_pays(prob0, sb.cmb_grids(bg0)[0][rank::world]) else "atomic queue, one warp per mode"),
                                              "limiter": "latency of the slowest mode (its sequential Rosenbrock attempts), not the collectives"}
         except Exception as e:
             ex["strong_single_cosmology"] = {"error": repr(e)}

@@ -554,6 +554,27 @@ def ptalg(prob=None, accuracy=2):
     return "TRBDF2" if accuracy == 0 else ("KenCarp4" if accuracy == 1 else "Rodas5P")
 
 
+# Which mapping for a launch?  The split kernel's CTAs are persistent (atomic queue, descending k): with more modes than CTAs fit, a second wave of (cheaper) modes
+# follows on the CTAs that finish first.  At ≈8.5 us per attempt against ≈12.5 us for a lone warp that pays as long as the work per CTA stays below 1.5 x the slowest mode:
+# decided from a crude estimate of the attempts per mode, a(k) = 250 + 27 k^0.6 (k in H0/c; within 25 % of the step counters of the LCDM models at the default tolerance).
+# Measured (scripts/split_waves.py): C_l grid 253 / 404 / 505 / 673 modes: split 23.1 / 25.0 / 32.6 / 38.0 ms, warp per mode 32.0 / 32.1 / 32.2 / 36.2 ms; P(k) log grids of
+# 300 ... 800 modes: 27.5 ... 27.9 ms against 38.1 ... 39.7 ms.
+SPLIT_WAVES = 4  # hard limit on the launch size, in units of split_capacity
+
+
+def split_pays(prob, ks):
+    cap = split_capacity(prob)
+    ks = np.asarray(ks, dtype=np.float64)
+    if cap <= 0 or len(ks) == 0 or len(ks) > SPLIT_WAVES * cap:
+        return False
+    if len(ks) <= cap:
+        return True
+    a = 250.0 + 27.0 * np.maximum(np.nan_to_num(ks, nan=0.0), 0.0) ** 0.6
+    t_split = 8.5 * max(a.max(), 1.15 * a.sum() / cap)
+    t_warp = 12.5 * max(a.max(), a.sum() / max(1, resident_warps(prob)))
+    return bool(t_split < t_warp)
+
+
 def split_capacity(prob):
     """Modes that run concurrently under the split mapping (one CTA of SB_R warps per mode, `sbm_solvept_split`); 0 if the model has none."""
     if not hasattr(prob, "_split_cap"):
@@ -570,8 +591,8 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
     sources: dict(nS = 2 | 3, scale_k = True, taurec = bgsol.taurec) -- evaluate the CMB source functions at the `saveat` times INSIDE the
     integrator (the reference's output_func, src/observables/fourier.jl:272-278) into sol.d_S[nk][nS][nsave]; with keep_states = False the saved
     states never leave the SM (sol.d_usave is None).
-    split: None (default) = choose the mapping by the size of the launch: with no more modes than `split_capacity(prob)` (296 on a B200 for
-    the nx = 4 models) every mode gets a CTA of SB_R warps (`sbm_solvept_split`: the row-parallel phases of an attempt are spread over the
+    split: None (default) = choose the mapping by the size of the launch (`split_pays`): with no more modes than `split_capacity(prob)` (296 on a B200 for the nx = 4
+    models), or somewhat more when most of them are cheap, every mode gets a CTA of SB_R warps (`sbm_solvept_split`: the row-parallel phases of an attempt are spread over the
     warps; ≈40 % lower latency, bit-identical results), otherwise one warp per mode; True / False force one or the other.
     alg: "Rodas5P" (the reference's default, `ptalg(prob; accuracy = 2)`), "KenCarp4" (`accuracy = 1`: the ESDIRK half of ARK4(3)6L[2]SA, five factorisations
     and six solves per step) or "TRBDF2" (`accuracy = 0`: second order, two factorisations and three solves per step), src/solve.jl:333-337; published schemes
@@ -628,7 +649,7 @@ def solvept(prob, bgsol, ks, ptivini=-math.inf, reltol=1e-5, abstol=1e-5, saveat
         rc = prob.lib.sbm_solvept_sched_src(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
                                             C.c_int(nk), _cptr(dks), _cptr(dtini), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
                                             _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _cptr(ditems), _cptr(dibeg), C.c_int(nlists), _cptr(dcont), _cptr(dflags), _stream(), srcp)
-    elif (split is True or (split is None and trace == 0 and nctas == 0 and 0 < nk <= split_capacity(prob))) and split_capacity(prob) > 0:
+    elif (split is True or (split is None and trace == 0 and nctas == 0 and split_pays(prob, ks))) and split_capacity(prob) > 0:
         rc = prob.lib.sbm_solvept_split(_cptr(d["P"]), C.c_int(len(bgsol.t)), _cptr(d["t"]), _cptr(d["y"]), _cptr(d["dy"]), C.c_int(d["msub"]), C.c_int(d["nlut"]), C.c_double(d["s0"]), C.c_double(d["dsl"]), _cptr(d["lut"]), _cptr(d["tab"]),
                                         C.c_int(nk), _cptr(dks), _cptr(dtini), _cptr(dorder), C.c_double(bgsol.tau0), C.c_int(ns), _cptr(dsave), C.c_double(reltol), C.c_double(abstol), C.c_int(maxiters),
                                         _cptr(usave), _cptr(uend), _cptr(retcode), _cptr(stats), _cptr(queue), _stream(), srcp)
@@ -1673,7 +1694,7 @@ class CMBPlan:
             if rc < 0:
                 raise RuntimeError(f"sbm_solvept_sched_src failed with code {rc}")
             return
-        if self.split and 0 < self.nk <= split_capacity(self.prob):  # few modes (the default 61-node path): one CTA of SB_R warps per mode
+        if self.split and split_pays(self.prob, self.ks_solve):  # few modes (the default 61-node path): one CTA of SB_R warps per mode
             rc = lib.sbm_solvept_split(_cptr(P), C.c_int(self.nb), _cptr(t), _cptr(y), _cptr(dy), C.c_int(self.msub), C.c_int(self.nlut), C.c_double(self.s0), C.c_double(self.dsl), _cptr(self.d_lut), _cptr(self.d_tab),
                                        C.c_int(self.nk), _cptr(self.d_ks), _cptr(self.d_tini), _cptr(self.d_order), C.c_double(self.tau0), C.c_int(self.nt), _cptr(self.d_taus), C.c_double(self.reltol), C.c_double(self.abstol),
                                        C.c_int(self.maxiters), _cptr(self.d_usave), _cptr(self.d_uend), _cptr(self.d_ret), _cptr(self.d_stats), _cptr(self.d_queue), _stream(), srcp)

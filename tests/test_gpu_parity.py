@@ -737,6 +737,9 @@ def test_split_kernel_is_bit_identical(sb, prob5, bg5):
                 if a.d_S is not None:
                     assert np.array_equal(a.d_S.cpu().numpy(), b.d_S.cpu().numpy(), equal_nan=True), kw
         auto = sb.solvept(prob, bg, ks[1:])  # the default picks the split mapping for a launch this small
+        if M.lmax == 5:  # more modes than CTAs fit: the persistent CTAs take a second wave from the queue
+            kmany = np.linspace(0.3, 300.0, sb.split_capacity(prob) + 120)
+            assert np.array_equal(sb.solvept(prob, bg, kmany, split=True).uend, sb.solvept(prob, bg, kmany, split=False).uend)
         assert np.array_equal(auto.uend, sb.solvept(prob, bg, ks[1:], split=False).uend)
 
 
