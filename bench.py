@@ -382,6 +382,23 @@ def run_extras(sb, torch, dist, args, rank, world, problem, prob, bg, jl, model=
                             "k_modes_per_s": 100 / float(np.median(ts)), "max_attempts_of_a_mode": int((st[:, 0] + st[:, 1]).max()), "success": bool(sol.success)}
     except Exception as e:
         ex["config1_pk"] = {"error": repr(e)}
+    # (1b) the same workload with the reference's lower-accuracy integrators (ptalg(prob; accuracy = 1 / 0), src/solve.jl:333-337), each with its P(k) error against a
+    # converged solve beside the time: what the accuracy knob buys on this engine (nothing: Rodas5P on the split mapping is the fastest AND the most accurate of the three)
+    try:
+        Pt = sb.spectrum_matter(prob, ks, bgsol=bg, reltol=1e-10, abstol=1e-10)
+        alt = {}
+        for alg, tol in (("Rodas5P", 1e-5), ("KenCarp4", 1e-5), ("TRBDF2", 1e-5)):  # (the accuracy knob changes the algorithm, not the default tolerances)
+            sb.spectrum_matter(prob, ks, bgsol=bg, alg=alg, reltol=tol, abstol=tol)
+            torch.cuda.synchronize()
+            tt = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                Pa = sb.spectrum_matter(prob, ks, bgsol=bg, alg=alg, reltol=tol, abstol=tol)
+                tt.append(time.perf_counter() - t0)
+            alt[f"{alg}, reltol = abstol = {tol:g}"] = {"ms": 1e3 * float(np.median(tt)), "max_rel_error_of_Pk_vs_converged": float(np.abs(Pa / Pt - 1).max())}
+        ex["config1_pk_integrators"] = alt
+    except Exception as e:
+        ex["config1_pk_integrators"] = {"error": repr(e)}
     # (2) the reference's default C_l path: 61 Chebyshev nodes + barycentric interpolation (the paper's 3.1 s workload)
     try:
         planc = sb.CMBPlan(prob, bg, jl, modes=MODES, direct=False)
