@@ -825,3 +825,17 @@ def test_esdirk_integrators_on_the_other_model_structures(sb):
             s = sb.solvept(prob, bg, ks, reltol=tol, abstol=tol, alg=alg)
             assert s.success, (M, alg, s.retcode)
             assert (np.abs(s.uend - ref.uend) <= bound * scale).all(), (M, alg, (np.abs(s.uend - ref.uend) / scale).max())
+
+
+@pytest.mark.gpu
+def test_spectrum_cmb_with_the_alternative_integrators(sb, prob5, bg5):
+    """`spectrum_cmb(...; ptopts = (alg = ...,))` (the reference passes the integrator through ptopts, docs/src/plot.md:129): the ESDIRK kernels form the sources at
+    the save times like the Rodas5P kernel, so the default C_l path runs on them unchanged; at a tight tolerance all three integrators give the same D_l."""
+    ls = np.array([10, 50, 200, 600])
+    jl = sb.SphericalBesselCache(ls, xcut=2e3 * bg5.tau0 * 1.001)
+    tight = dict(reltol=1e-8, abstol=1e-8)
+    ref = sb.spectrum_cmb(["TT", "EE", "TE"], prob5, jl, normalization="Dl", bgsol=bg5, ptopts=tight)
+    for alg, bound in (("KenCarp4", 2e-5), ("TRBDF2", 2e-3)):
+        Dl = sb.spectrum_cmb(["TT", "EE", "TE"], prob5, jl, normalization="Dl", bgsol=bg5, ptopts=dict(alg=alg, **tight))
+        dev = np.abs(Dl - ref).max(axis=0) / np.abs(ref).max(axis=0)
+        assert (dev < bound).all(), (alg, dev)
