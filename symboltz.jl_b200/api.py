@@ -952,11 +952,15 @@ class CosmologySolution:
             raise RuntimeError("Solution wavenumbers are not sorted in ascending order")
         scal = (isinstance(vars, str), np.ndim(taus) == 0, np.ndim(ks) == 0)
         names = self.prob.info["unames"]
+        observed = {"ST": 0, "SE": 1, "Spsi": 2, "Sψ": 2}  # the CMB source functions (reference M.ST, M.SE, M.Sψ, src/models/cosmologies.jl:99-105): formed at the query times
         idx = []
         for v in ([vars] if scal[0] else list(vars)):
-            if v not in names:
-                raise KeyError(f"{v!r} is not a perturbation unknown of {self.prob.M} (available: {names[:8]} ...)")
-            idx.append(names.index(v))
+            if v in observed:
+                idx.append(-1 - observed[v])
+            elif v in names:
+                idx.append(names.index(v))
+            else:
+                raise KeyError(f"{v!r} is neither a perturbation unknown of {self.prob.M} (available: {names[:8]} ...) nor one of the observed source functions {sorted(observed)}")
         taus = np.ascontiguousarray(np.atleast_1d(taus), dtype=np.float64)
         kq = np.atleast_1d(np.asarray(ks, dtype=np.float64))
         kmin, kmax = self.ks[0], self.ks[-1]
@@ -964,7 +968,15 @@ class CosmologySolution:
             raise ValueError(f"Requested wavenumber k = {kq.min()} is below the minimum solved wavenumber {kmin}")
         if kq.max() > kmax:
             raise ValueError(f"Requested wavenumber k = {kq.max()} is above the maximum solved wavenumber {kmax}")
-        U = self._states_at(taus)[:, :, idx]          # [nk_solved][nτ][nvars]
+        U = self._states_at(taus)
+        if any(i < 0 for i in idx):                   # observed source functions at (τ, k_solved): the integrator's fused evaluation, unscaled (ST, SE, Sψ)
+            key = b"S" + taus.tobytes()
+            if key not in self._dense:
+                opts = {k: v for k, v in self._ptopts.items() if k not in ("saveat", "sources", "keep_states")}
+                sg = source_grid(self.prob, taus, self.ks, self.bg, scale_k=False, lensing=True, ptivini=self._ptivini, warn=False, **opts)
+                self._dense[key] = sg.dS.cpu().numpy().transpose(0, 2, 1)  # [nk][nτ][3]
+            U = np.concatenate([U, self._dense[key][:, :, ::-1]], axis=2)   # (index −1 − s addresses source s)
+        U = U[:, :, idx]                              # [nk_solved][nτ][nvars]
         out = np.empty((len(idx), len(taus), len(kq)))
         for ik, k in enumerate(kq):                   # neighboring_modes_indices, src/solve.jl:706-717
             if k == kmin:

@@ -641,6 +641,15 @@ def test_solution_object_interpolates_in_time_and_k(sb, oracle, prob5, bg5, obg_
     osol = oracle.solvept(obg_same, ks[[0, 5]], saveat=taus)
     ref = osol["usave"][:, :, 0]  # Φ is the first unknown of the oracle's state as well
     assert np.abs(out[0][:, :2].T - ref).max() <= 1e-5 * np.abs(ref).max()
+    # observed (non-unknown) variables: the CMB source functions ST, SE, Sψ (reference M.ST, M.SE, M.Sψ) at the query times, against the oracle's sources from its own states
+    obs = sol(["ST", "SE", "Spsi", "Phi"], taus, ks[[0, 5]])
+    oS = oracle.sources(obg_same, ks[[0, 5]], taus, osol["usave"])  # [nk][nτ][7] = (ST, SE, ..., Sψ)
+    for iv, col in ((0, 0), (1, 1), (2, 6)):
+        got, want = obs[iv].T, oS[:, :, col]
+        assert np.abs(got - want).max() <= (1e-3 if iv == 2 else 2e-4) * np.abs(want).max(), (iv, np.abs(got - want).max() / np.abs(want).max())  # (two default-tolerance solves with their own step sequences; measured 4e-5, 1e-7, 2e-4: Sψ ∝ 1/χ near today)
+    assert np.array_equal(obs[3], out[0][:, :2])
+    sg = sb.source_grid(prob5, taus, ks[[3, 4]], sol.bg, scale_k=False, lensing=True).dS.cpu().numpy()  # [nk][nS][nτ]
+    assert np.allclose(sol("SE", taus, kmid), 0.5 * (sg[0, 1] + sg[1, 1]), rtol=1e-12, atol=0)
     with pytest.raises(ValueError):
         sol("Phi", taus, 0.1)
     with pytest.raises(ValueError):
